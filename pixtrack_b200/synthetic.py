@@ -1,0 +1,218 @@
+"""Deterministic synthetic scenes for tests and bench.
+
+No real assets (PixLoc checkpoint, premier_protein, YCB, NeRF snapshots) exist
+in the build container, so every configuration is restated on seeded
+synthetic inputs.  All randomness comes from `torch.Generator(seed)` on the
+CPU, so the same seed gives the same bytes here and on the GPU box.
+
+Nothing here is on the measured path: it only manufactures inputs.
+"""
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as tF
+
+Tensor = torch.Tensor
+
+
+def _gen(seed: int) -> torch.Generator:
+    g = torch.Generator(device='cpu')
+    g.manual_seed(int(seed))
+    return g
+
+
+def _blur(x: Tensor, sigma: float) -> Tensor:
+    """Separable Gaussian low-pass of a [C,H,W] map (reflect borders)."""
+    if sigma <= 0:
+        return x
+    r = max(1, int(math.ceil(3 * sigma)))
+    k = torch.exp(-0.5 * (torch.arange(-r, r + 1, dtype=x.dtype) / sigma) ** 2)
+    k = k / k.sum()
+    C = x.shape[0]
+    x = x[None]
+    x = tF.conv2d(tF.pad(x, (r, r, 0, 0), mode='replicate'), k.view(1, 1, 1, -1).expand(C, 1, 1, -1), groups=C)
+    x = tF.conv2d(tF.pad(x, (0, 0, r, r), mode='replicate'), k.view(1, 1, -1, 1).expand(C, 1, -1, 1), groups=C)
+    return x[0]
+
+
+def smooth_feature_map(C: int, H: int, W: int, seed: int, sigma: float = 2.0,
+                       normalize: bool = True) -> Tensor:
+    """Low-pass Gaussian noise [C,H,W], unit L2 norm over C at every pixel, so
+    that the feature-metric cost has a basin of a few pixels."""
+    x = _blur(torch.randn(C, H, W, generator=_gen(seed)), sigma)
+    x = x / x.std()
+    return tF.normalize(x, dim=0) if normalize else x
+
+
+def smooth_confidence(H: int, W: int, seed: int, sigma: float = 4.0) -> Tensor:
+    x = _blur(torch.randn(1, H, W, generator=_gen(seed)), sigma)
+    return torch.sigmoid(2.0 * x / x.std())
+
+
+def axis_angle_to_R(w: Tensor) -> Tensor:
+    th = float(w.norm())
+    if th < 1e-12:
+        return torch.eye(3, dtype=w.dtype)
+    k = w / th
+    K = torch.tensor([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]], dtype=w.dtype)
+    return torch.eye(3, dtype=w.dtype) + math.sin(th) * K + (1 - math.cos(th)) * (K @ K)
+
+
+def pixtrack_camera(width: int = 1920, height: int = 1080, k1: float = 0.0) -> Tensor:
+    """The prior r9 gets from pycolmap.infer_camera_from_image: SIMPLE_RADIAL,
+    f = 1.2*max(w,h), c = (w/2, h/2), then Camera.from_colmap's -0.5 shift
+    (reference pixtrack/pose_trackers/pixloc_tracker_r9.py:108-118,
+    pixloc/pixloc/pixlib/geometry/wrappers.py:229-255)."""
+    f = 1.2 * max(width, height)
+    return torch.tensor([width, height, f, f, width / 2 - 0.5, height / 2 - 0.5, k1, 0.0])
+
+
+def scale_cam(cam: Tensor, s: Sequence[float]) -> Tensor:
+    s = torch.tensor([float(s[0]), float(s[1])], dtype=cam.dtype)
+    return torch.cat([cam[0:2] * s, cam[2:4] * s, (cam[4:6] + 0.5) * s - 0.5, cam[6:]])
+
+
+def project_pinhole_radial(cam: Tensor, R: Tensor, t: Tensor, p3d: Tensor) -> Tensor:
+    """Plain projection used only to place synthetic reference descriptors."""
+    pc = p3d @ R.t() + t
+    xy = pc[:, :2] / pc[:, 2:3]
+    if cam.numel() > 6:
+        r2 = (xy ** 2).sum(-1, keepdim=True)
+        xy = xy * (1 + cam[6] * r2 + cam[7] * r2 ** 2)
+    return xy * cam[2:4] + cam[4:6]
+
+
+def bilinear(Fm: Tensor, uv: Tensor) -> Tensor:
+    C, H, W = Fm.shape
+    g = uv / torch.tensor([W - 1, H - 1], dtype=uv.dtype) * 2 - 1
+    return tF.grid_sample(Fm[None], g[None, :, None], mode='bilinear', align_corners=True).reshape(C, -1).t()
+
+
+def object_points(N: int, seed: int, depth: float = 1.2, spread: float = 0.15) -> Tensor:
+    p = torch.randn(N, 3, generator=_gen(seed)) * spread
+    p[:, 2] += depth
+    return p
+
+
+def perturb_pose(R: Tensor, t: Tensor, seed: int, rot_deg: float, trans: float):
+    g = _gen(seed)
+    ax = torch.randn(3, generator=g)
+    ax = ax / ax.norm() * math.radians(rot_deg)
+    dt = torch.randn(3, generator=g)
+    dt = dt / dt.norm() * trans
+    Rd = axis_angle_to_R(ax)
+    return Rd @ R, Rd @ t + dt
+
+
+def level_problem(seed: int = 0, N: int = 500, C: int = 128, H: int = 144, W: int = 256,
+                  level_scale: float = (1024 / 1920) / 4, B: int = 1, noise: float = 0.05,
+                  rot_deg: float = 2.0, trans: float = 0.02, sigma: float = 2.0,
+                  k1: float = 0.0) -> Dict[str, Tensor]:
+    """One pyramid level of a PixTrack-shaped problem (SURVEY config C1b): a
+    1920x1080 SIMPLE_RADIAL camera scaled to the level, smooth unit-norm query
+    map, reference descriptors = query map sampled at the ground-truth
+    projection + noise (re-normalised), B perturbed initial poses."""
+    cam = scale_cam(pixtrack_camera(k1=k1), (level_scale, level_scale))
+    cam[0], cam[1] = float(W), float(H)
+    Fq = smooth_feature_map(C, H, W, seed * 7 + 1, sigma)
+    Wq = smooth_confidence(H, W, seed * 7 + 2)
+    p3d = object_points(N, seed * 7 + 3)
+    R_gt = axis_angle_to_R(torch.randn(3, generator=_gen(seed * 7 + 4)) * 0.05)
+    t_gt = torch.randn(3, generator=_gen(seed * 7 + 5)) * 0.02
+    uv = project_pinhole_radial(cam, R_gt, t_gt, p3d)
+    g = _gen(seed * 7 + 6)
+    F_ref, W_ref, R0, t0 = [], [], [], []
+    for b in range(B):
+        fr = bilinear(Fq, uv) + noise * torch.randn(N, C, generator=g) / math.sqrt(C)
+        F_ref.append(tF.normalize(fr, dim=1))
+        W_ref.append(0.5 + 0.5 * torch.rand(N, 1, generator=g))
+        Rb, tb = perturb_pose(R_gt, t_gt, seed * 1000 + b, rot_deg, trans)
+        R0.append(Rb)
+        t0.append(tb)
+    return dict(cam=cam, F_q=Fq, W_q=Wq, p3d=p3d, R_gt=R_gt, t_gt=t_gt,
+                F_ref=torch.stack(F_ref), W_ref=torch.stack(W_ref),
+                R0=torch.stack(R0), t0=torch.stack(t0))
+
+
+def toy_problem(seed: int = 0, n_points: int = 500) -> Dict[str, Tensor]:
+    """The reference's own fixture, regenerated with the same RNG call order
+    (reference pixloc/pixloc/pixlib/geometry/check_jacobians.py:32-54):
+    640x480, f=(300,350), c=(320,240), radial (0.1, 0.01), 16 channels.
+    Adds the confidences SURVEY config C1a asks for (drawn AFTER the fixture's
+    own draws so those stay identical to the reference's)."""
+    torch.random.manual_seed(seed)
+    aa = torch.randn(3) / 10
+    t = torch.randn(3) / 5
+    w, h = 640, 480
+    cam = torch.tensor([w, h, 300., 350., w / 2, h / 2, 0.1, 0.01])
+    p3d = torch.randn(n_points, 3)
+    p3d[:, -1] += 2
+    F_ref = torch.randn(n_points, 16)
+    F_q = torch.randn(16, h, w)
+    W_ref = torch.rand(n_points, 1)
+    W_q = torch.rand(1, h, w)
+    return dict(aa=aa, t0=t, R0=axis_angle_to_R(aa), cam=cam, p3d=p3d, F_ref=F_ref, F_q=F_q,
+                W_ref=W_ref, W_q=W_q)
+
+
+# ---------------------------------------------------------------------------
+# procedural image + random extractor weights
+# ---------------------------------------------------------------------------
+def textured_image(H: int, W: int, seed: int) -> Tensor:
+    """HxWx3 float32 in 0..255: multi-octave smooth noise (object-like texture)."""
+    g = _gen(seed)
+    img = torch.zeros(3, H, W)
+    for octave, amp in ((4, 1.0), (16, 0.6), (64, 0.35)):
+        h, w = max(2, H // octave), max(2, W // octave)
+        n = torch.randn(1, 3, h, w, generator=g)
+        img += amp * tF.interpolate(n, size=(H, W), mode='bilinear', align_corners=False)[0]
+    img = (img - img.min()) / (img.max() - img.min())
+    return (img * 255.0).permute(1, 2, 0).contiguous()
+
+
+VGG19_BLOCKS = ((64, 64), (128, 128), (256, 256, 256, 256), (512, 512, 512, 512), (512, 512, 512, 512))
+DECODER = (64, 64, 64, 32)
+OUTPUT_SCALES = (0, 2, 4)
+OUTPUT_DIM = (32, 128, 128)
+
+
+def unet_weights(seed: int = 0) -> Dict[str, Tensor]:
+    """Random (He-scaled) weights for the PixLoc UNet, keyed like the
+    checkpoint's `extractor.*` state dict (reference
+    pixloc/pixloc/pixlib/models/unet.py:68-156; config
+    pixloc/pixloc/pixlib/configs/train_pixloc_megadepth.yaml: vgg19 encoder,
+    decoder [64,64,64,32], output_dim [32,128,128], output_scales [0,2,4],
+    uncertainty heads).  Encoder keys follow torchvision's vgg19.features
+    indexing regrouped into 5 blocks (block b, position i inside the block)."""
+    g = _gen(seed)
+    sd: Dict[str, Tensor] = {}
+
+    def conv(name, cout, cin, k, bias=True, gain=2.0):
+        fan = cin * k * k
+        sd[name + '.weight'] = torch.randn(cout, cin, k, k, generator=g) * math.sqrt(gain / fan)
+        if bias:
+            sd[name + '.bias'] = 0.1 * torch.randn(cout, generator=g)
+
+    cin = 3
+    for b, chans in enumerate(VGG19_BLOCKS):
+        pos = 0 if b == 0 else 1            # blocks 1.. start with the max-pool
+        for c in chans:
+            conv(f'encoder.{b}.{pos}', c, cin, 3)
+            cin = c
+            pos += 2                        # conv, relu
+    skip = [c[-1] for c in VGG19_BLOCKS]
+    prev = skip[-1]
+    for i, (out, sk) in enumerate(zip(DECODER, skip[:-1][::-1])):
+        conv(f'decoder.{i}.layers.0', out, prev + sk, 3, bias=False)
+        sd[f'decoder.{i}.layers.1.weight'] = 1.0 + 0.1 * torch.randn(out, generator=g)
+        sd[f'decoder.{i}.layers.1.bias'] = 0.1 * torch.randn(out, generator=g)
+        sd[f'decoder.{i}.layers.1.running_mean'] = 0.1 * torch.randn(out, generator=g)
+        sd[f'decoder.{i}.layers.1.running_var'] = 0.5 + torch.rand(out, generator=g)
+        sd[f'decoder.{i}.layers.1.num_batches_tracked'] = torch.tensor(1)
+        prev = out
+    for idx, s in enumerate(OUTPUT_SCALES):
+        cin = skip[s] if s == len(VGG19_BLOCKS) - 1 else DECODER[-1 - s]
+        conv(f'adaptation.{idx}.0', OUTPUT_DIM[idx], cin, 1, gain=1.0)
+        conv(f'uncertainty.{idx}.0', 1, cin, 1, gain=1.0)
+    return sd
