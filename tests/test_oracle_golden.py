@@ -76,7 +76,7 @@ def test_projection_and_jacobian():
         np.testing.assert_allclose(uv.numpy(), g[f'{tag}_uv'], rtol=1e-6, atol=1e-4)
         np.testing.assert_allclose(J.numpy(), g[f'{tag}_J'], rtol=1e-5, atol=1e-3)
     # the distortion limit really bites: some points land inside the image yet are rejected
-    cam = torch.tensor([640., 480., 300., 350., 320., 240., -0.2, 0.05])
+    cam = torch.tensor([640., 480., 300., 350., 320., 240., 0.15, -0.3, 0.002, -0.001])
     uv, valid = lm.world_to_image(cam, pc)
     inside = ((uv >= 0) & (uv <= cam[:2] - 1)).all(-1) & (pc[:, 2] > 1e-3)
     assert (inside & ~valid).sum() > 0
