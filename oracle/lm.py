@@ -285,12 +285,16 @@ def sample_reference(maps: Sequence[Tensor], scales: Sequence[Tuple[float, float
                      cam: Tensor, R: Tensor, t: Tensor, p3d: Tensor, pad: int = 1):
     """maps[l] is [(C_l+1), H_l, W_l] (descriptor channels + confidence last).
     Returns per-level observations [N, C_l+1] and the AND-over-levels keep mask
-    (points are kept only if they project inside every level)."""
+    (points are kept only if they project inside every level).
+    The reference does the projection in the dtype of the COLMAP model, i.e.
+    float64 (numpy xyz, qvec2rotmat, `Camera.from_colmap`), and casts the pixel
+    coordinates to the map dtype only for the interpolation
+    (`p2d_feat.to(feats)`, :349-351): pass float64 cam/R/t/p3d to get that."""
     p_cam = p3d @ R.t() + t
     obs, keep = [], torch.ones(p3d.shape[0], dtype=torch.bool)
     for Fm, sc in zip(maps, scales):
         uv, vis = world_to_image(scale_camera(cam, sc), p_cam)
-        val, inb, _ = sample_map(Fm, uv, pad)
+        val, inb, _ = sample_map(Fm, uv.to(Fm.dtype), pad)
         obs.append(val)
         keep &= inb & vis
     return obs, keep

@@ -206,7 +206,7 @@ def gold_refine():
     refiner.reference_scale = 1.0
     ids = list(range(p3d.shape[0]))
     # F: interp_sparse_observations at the render pose (pixloc_pose_refiners.py:327-368)
-    fd = refiner.interp_sparse_observations(maps, scales, 7, ids, Pose.from_Rt(R_gt, t_gt))
+    fd = refiner.interp_sparse_observations(maps, scales, 7, ids, Pose.from_Rt(R_gt, t_gt).double())  # r9 poses are cpu float64 (base_refiner.py:128)
     kept = np.array(sorted(fd.keys()))
     obs = [torch.stack([fd[i][lv] for i in kept]).numpy() for lv in range(3)]
     # G: refine_pose_using_features from a perturbed pose, DebugTracker attached (r9.py:239,251)

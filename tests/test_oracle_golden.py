@@ -98,7 +98,7 @@ def test_reference_sampling_and_refine_levels():
     g = cases.gold('refine')
     cam_q, scales, maps, p3d, R_gt, t_gt = cases.pyramid_scene(1)
     np.testing.assert_allclose(cases.checksum(*maps, p3d), g['chk'], rtol=1e-9)
-    obs, keep = lm.sample_reference(maps, scales, cam_q, R_gt, t_gt, p3d)
+    obs, keep = lm.sample_reference(maps, scales, cam_q.double(), R_gt.double(), t_gt.double(), p3d.double())
     kept = torch.nonzero(keep)[:, 0]
     assert np.array_equal(kept.numpy(), g['kept'])
     for lv in range(3):
