@@ -1,0 +1,157 @@
+/*
+ * pixtrack_b200.h -- C ABI of libpixtrack_b200.so (sm_100a).
+ *
+ * The reference (GiantAI/pixtrack) has no FFI on this path: its boundary is
+ * Python duck typing.  This header is the C-level
+ * contract the Python adapters in pixtrack_b200/ bind with ctypes; each entry
+ * point names the reference interface it replaces (paths relative to
+ * /root/reference).
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer owned by the caller (e.g. a
+ *    torch allocation) unless the name says `host_`;
+ *  - all calls are stream-ordered on `stream` (a cudaStream_t passed as
+ *    void*; NULL = legacy default stream) and never synchronise the device;
+ *  - return value 0 = ok, negative = error; `ptk_last_error()` gives the text
+ *    of the last error on the calling thread; nothing throws across the ABI;
+ *  - a PtkContext owns a small device workspace, so at most one call per
+ *    context may be in flight on different streams at a time
+ *    (thread-compatible, not thread-safe -- like the reference's single
+ *    Python caller).  Create one context per device / per worker.
+ *  - batch strides (`*_bstride`) are in ELEMENTS between consecutive
+ *    problems; 0 means "shared by all problems of the batch".
+ */
+#ifndef PIXTRACK_B200_H_
+#define PIXTRACK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTK_ABI_VERSION 1
+
+/* error codes */
+#define PTK_OK 0
+#define PTK_ERR_INVALID -1   /* bad argument (NULL pointer, unsupported size)  */
+#define PTK_ERR_CUDA -2      /* a CUDA runtime/driver call failed               */
+#define PTK_ERR_UNSUPPORTED -3
+
+typedef struct PtkContext PtkContext;
+
+int ptk_abi_version(void);
+const char* ptk_last_error(void);
+/* Creates the per-device context (workspace, SM count).  Fails (PTK_ERR_CUDA)
+ * when no sm_100 device is present: there is no CPU fallback. */
+int ptk_create(int device, PtkContext** out);
+void ptk_destroy(PtkContext* ctx);
+int ptk_num_sms(const PtkContext* ctx);
+/* SYNCHRONISING health check for tests: PTK_OK unless a device-side abort (a
+ * barrier that timed out instead of hanging the GPU) was recorded. */
+int ptk_device_status(PtkContext* ctx);
+
+/* ------------------------------------------------------------------------
+ * Fused Levenberg-Marquardt pose refinement on one pyramid level.
+ *
+ * Replaces  PixTrackOptimizer.run / LearnedOptimizer._run
+ *   pixloc/pixloc/pixlib/models/learned_optimizer.py:48-95,
+ *   pixtrack/optimizers/pixtrack_optimizer.py:6-18 (stop test every iteration)
+ * and everything it calls per iteration:
+ *   DirectAbsoluteCost.residual_jacobian  pixlib/geometry/costs.py:15-67
+ *   Camera.world2image / J_world2image    pixlib/geometry/wrappers.py:308-362
+ *   undistort_points / J_undistort_points pixlib/geometry/utils.py:36-95
+ *   interpolate_tensor_bilinear           pixlib/geometry/interpolation.py:57-89
+ *   scaled_barron(0, c)                   pixlib/geometry/losses.py:8-19,38-82
+ *   BaseOptimizer.build_system            pixlib/models/base_optimizer.py:83-92
+ *   optimizer_step (damped Cholesky)      pixlib/geometry/optimization.py:13-47
+ *   Pose.from_aa / compose, so3exp_map    wrappers.py:127-175, optimization.py:62-76
+ * The whole iteration loop, the 6x6 solve, the SE(3) update and the stop test
+ * run on the device: no host synchronisation between iterations.
+ *
+ * B independent problems (reference views / frames) are solved by one launch.
+ * ---------------------------------------------------------------------- */
+#define PTK_LOG_STRIDE 64
+/* per-iteration log record, PTK_LOG_STRIDE floats:
+ *  [0] sum over valid points of the robust cost      [1] number of valid points
+ *  [2..13] pose AFTER the update (R row-major, t)     [14] |dt|   [15] dR in degrees
+ *  [16] |g| (unmasked gradient)   [17..22] g          [23..28] delta (dt, dw)
+ *  [29] 1 if the stop test fired  [30] 1 if failed    [31] 1 if the damped H was not
+ *  positive definite (the reference raises there)     [32..52] H, upper triangle,
+ *  row-major (00 01 .. 05 11 12 .. 55), BEFORE damping.
+ * This is what DebugTracker.log_optim_iter (pixtrack/localization/tracker.py:32-46)
+ * needs: cost_sum/n_valid, T, |dt|. */
+
+typedef struct PtkLmProblem {
+  int32_t B;          /* number of independent problems                          */
+  int32_t N;          /* 3D points per problem                                   */
+  int32_t C;          /* descriptor channels, multiple of 4, <= 512              */
+  int32_t H, W;       /* query map size                                          */
+  int32_t n_cam;      /* camera vector length: 6, 8 (k1,k2) or 10 (+p1,p2)       */
+  int32_t num_iters;  /* conf.num_iters                                          */
+  int32_t pad;        /* conf.interpolation.pad (>= 0)                           */
+  int32_t min_valid;  /* fail when fewer valid points (reference: 10)            */
+  int32_t reserved0;
+  const float* p3d;      int64_t p3d_bstride;    /* [N][3]                        */
+  const float* f_ref;    int64_t f_ref_bstride;  /* [N][C]                        */
+  const float* w_ref;    int64_t w_ref_bstride;  /* [N] or NULL (no confidences)  */
+  const float* fq;       int64_t fq_bstride;     /* [H][W][C]  channels-last      */
+  const float* wq;       int64_t wq_bstride;     /* [H][W] or NULL                */
+  const uint8_t* mask;   int64_t mask_bstride;   /* [N] or NULL                   */
+  const float* cam;      int64_t cam_bstride;    /* [n_cam] w h fx fy cx cy k1 k2 p1 p2 */
+  const float* T_init;   int64_t T_bstride;      /* [12] R row-major then t       */
+  const float* lambda;   int64_t lambda_bstride; /* [6] damping (DampingNet out)  */
+  const uint8_t* skip;                           /* [B] or NULL: nonzero -> problem is
+                                                    passed through untouched (used to chain
+                                                    levels: skip = previous level's failed) */
+  float loss_scale;   /* c of scaled_barron(0, c): 0.1                            */
+  float grad_stop;    /* conf.grad_stop_criteria                                  */
+  float dt_stop;      /* conf.dt_stop_criteria                                    */
+  float dR_stop;      /* conf.dR_stop_criteria (degrees)                          */
+} PtkLmProblem;
+
+typedef struct PtkLmResult {
+  float* T;           /* [B][12]                                                  */
+  uint8_t* failed;    /* [B]  (sticky OR with skip[b])                            */
+  int32_t* n_iters;   /* [B]  iterations executed                                 */
+  float* log;         /* [B][num_iters][PTK_LOG_STRIDE] or NULL                   */
+} PtkLmResult;
+
+int ptk_lm_run(PtkContext* ctx, const PtkLmProblem* prob, const PtkLmResult* res, void* stream);
+
+/* Launch geometry the next ptk_lm_run with this problem would use (for
+ * benchmarks / tests): CTAs per problem and number of problem groups. */
+int ptk_lm_plan(const PtkContext* ctx, const PtkLmProblem* prob, int32_t* ctas_per_problem, int32_t* n_groups);
+
+/* ------------------------------------------------------------------------
+ * Map layout / normalisation helpers.
+ *
+ * ptk_chw_to_hwc: [C][H][W] -> [H][W][C]; with normalize != 0 each pixel's C
+ * vector is L2-normalised on the way (F.normalize(dim=0), eps 1e-12), i.e. the
+ * query-side normalisation of BaseRefiner.refine_pose_using_features
+ * (pixloc/pixloc/localization/base_refiner.py:92-94).
+ * ---------------------------------------------------------------------- */
+int ptk_chw_to_hwc(PtkContext* ctx, const float* src, float* dst, int32_t C, int32_t H, int32_t W,
+                   int32_t normalize, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Sparse bilinear sampling of a dense map at N pixel positions.
+ *
+ * Replaces Interpolator.__call__ / interpolate_tensor(mode='linear')
+ *   pixloc/pixloc/pixlib/geometry/interpolation.py:57-141
+ * as called by PoseTrackerRefiner.interp_sparse_observations
+ *   pixtrack/localization/pixloc_pose_refiners.py:349-351.
+ * The map is addressed as map[c*stride_c + y*stride_y + x*stride_x] (element
+ * strides), so both [C][H][W] and channels-last [H][W][C] storage work.
+ * pts [N][2] = (x, y) pixels.  Outputs: vals [N][C]; mask [N] (1 when
+ * pad <= p <= size-1-pad), may be NULL; grads [N][C][2] central differences,
+ * may be NULL.
+ * ---------------------------------------------------------------------- */
+int ptk_sample_points(PtkContext* ctx, const float* map, int64_t stride_c, int64_t stride_y, int64_t stride_x,
+                      int32_t C, int32_t H, int32_t W, const float* pts, int32_t N, int32_t pad, float* vals,
+                      uint8_t* mask, float* grads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXTRACK_B200_H_ */

@@ -1,0 +1,114 @@
+"""ctypes binding of libpixtrack_b200.so (include/pixtrack_b200.h).
+
+There is NO fallback: if the library is missing or no sm_100 device is
+present, loading / context creation raises.  The oracle is never imported
+from here.
+"""
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libpixtrack_b200.so')
+LOG_STRIDE = 64
+
+c_f32p = C.POINTER(C.c_float)
+c_u8p = C.POINTER(C.c_uint8)
+c_i32p = C.POINTER(C.c_int32)
+
+
+class PtkError(RuntimeError):
+    pass
+
+
+class LmProblem(C.Structure):
+    _fields_ = [
+        ('B', C.c_int32), ('N', C.c_int32), ('C', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+        ('n_cam', C.c_int32), ('num_iters', C.c_int32), ('pad', C.c_int32), ('min_valid', C.c_int32),
+        ('reserved0', C.c_int32),
+        ('p3d', C.c_void_p), ('p3d_bstride', C.c_int64),
+        ('f_ref', C.c_void_p), ('f_ref_bstride', C.c_int64),
+        ('w_ref', C.c_void_p), ('w_ref_bstride', C.c_int64),
+        ('fq', C.c_void_p), ('fq_bstride', C.c_int64),
+        ('wq', C.c_void_p), ('wq_bstride', C.c_int64),
+        ('mask', C.c_void_p), ('mask_bstride', C.c_int64),
+        ('cam', C.c_void_p), ('cam_bstride', C.c_int64),
+        ('T_init', C.c_void_p), ('T_bstride', C.c_int64),
+        ('lambda_', C.c_void_p), ('lambda_bstride', C.c_int64),
+        ('skip', C.c_void_p),
+        ('loss_scale', C.c_float), ('grad_stop', C.c_float), ('dt_stop', C.c_float), ('dR_stop', C.c_float),
+    ]
+
+
+class LmResult(C.Structure):
+    _fields_ = [('T', C.c_void_p), ('failed', C.c_void_p), ('n_iters', C.c_void_p), ('log', C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/pixtrack_b200.h declares
+SYMBOLS = {
+    'ptk_abi_version': (C.c_int, []),
+    'ptk_last_error': (C.c_char_p, []),
+    'ptk_create': (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    'ptk_destroy': (None, [C.c_void_p]),
+    'ptk_num_sms': (C.c_int, [C.c_void_p]),
+    'ptk_device_status': (C.c_int, [C.c_void_p]),
+    'ptk_lm_run': (C.c_int, [C.c_void_p, C.POINTER(LmProblem), C.POINTER(LmResult), C.c_void_p]),
+    'ptk_lm_plan': (C.c_int, [C.c_void_p, C.POINTER(LmProblem), c_i32p, c_i32p]),
+    'ptk_sample_points': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    'ptk_chw_to_hwc': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_contexts = {}
+
+
+def load():
+    """dlopen the library and bind every declared symbol (no GPU needed)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise PtkError(f'{LIB_PATH} not found: build it with `python -m pixtrack_b200.build` '
+                               '(there is no CPU fallback)')
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+                fn.restype = res
+                fn.argtypes = args
+            if lib.ptk_abi_version() != 1:
+                raise PtkError('ABI version mismatch between _lib.py and libpixtrack_b200.so')
+            _lib = lib
+    return _lib
+
+
+def check(code: int):
+    if code != 0:
+        raise PtkError(f'libpixtrack_b200 error {code}: {load().ptk_last_error().decode()}')
+
+
+def context(device_index: int) -> int:
+    """Per-device PtkContext handle (created on first use)."""
+    lib = load()
+    import torch
+    if not torch.cuda.is_available():
+        # never enter the CUDA runtime without a device (it can block for minutes on a GPU-less host)
+        raise PtkError('no CUDA device: pixtrack_b200 runs only on sm_100a GPUs (no CPU fallback)')
+    with _lock:
+        if device_index not in _contexts:
+            h = C.c_void_p()
+            check(lib.ptk_create(int(device_index), C.byref(h)))
+            _contexts[device_index] = h
+        return _contexts[device_index]
+
+
+def current_stream_ptr(device) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def device_status(device_index: int):
+    check(load().ptk_device_status(context(device_index)))

@@ -1,0 +1,163 @@
+"""Pose / Camera tensor wrappers with the reference's interface.
+
+The drop-in optimizer accepts the reference's own `pixloc.pixlib.geometry.
+{Pose, Camera}` objects (duck-typed through `._data`); these local classes
+exist so the package, tests and bench work where /root/reference is absent.
+Same data layout as reference pixloc/pixloc/pixlib/geometry/wrappers.py:
+Pose._data = [R row-major (9), t (3)], Camera._data = [w, h, fx, fy, cx, cy,
+dist...] with 0, 2 or 4 distortion terms.
+"""
+import math
+from typing import Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+Tensor = torch.Tensor
+
+
+def _as_tensor(x, like: Tensor = None) -> Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x)
+    elif not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    if like is not None:
+        x = x.to(device=like.device, dtype=like.dtype)
+    return x
+
+
+class _Wrapper:
+    def __init__(self, data: Tensor):
+        self._data = _as_tensor(data)
+
+    @property
+    def shape(self):
+        return self._data.shape[:-1]
+
+    @property
+    def device(self):
+        return self._data.device
+
+    @property
+    def dtype(self):
+        return self._data.dtype
+
+    def to(self, *a, **k):
+        if a and isinstance(a[0], _Wrapper):
+            a = (a[0]._data,) + a[1:]
+        return self.__class__(self._data.to(*a, **k))
+
+    def cpu(self):
+        return self.__class__(self._data.cpu())
+
+    def cuda(self):
+        return self.__class__(self._data.cuda())
+
+    def float(self):
+        return self.__class__(self._data.float())
+
+    def double(self):
+        return self.__class__(self._data.double())
+
+    def __getitem__(self, i):
+        return self.__class__(self._data[i])
+
+
+class Pose(_Wrapper):
+    def __init__(self, data):
+        super().__init__(data)
+        assert self._data.shape[-1] == 12
+
+    @classmethod
+    def from_Rt(cls, R, t):
+        R, t = _as_tensor(R), _as_tensor(t)
+        return cls(torch.cat([R.flatten(start_dim=-2), t.to(R)], -1))
+
+    @classmethod
+    def from_aa(cls, aa, t):
+        aa = _as_tensor(aa)
+        theta = aa.norm(dim=-1, keepdim=True)
+        small = theta < 1e-7
+        k = aa / torch.where(small, torch.ones_like(theta), theta)
+        z = torch.zeros_like(k[..., 0])
+        W = torch.stack([z, -k[..., 2], k[..., 1], k[..., 2], z, -k[..., 0], -k[..., 1], k[..., 0], z], -1)
+        W = W.reshape(aa.shape[:-1] + (3, 3))
+        th = theta[..., None]
+        res = torch.where(small[..., None], W, W * torch.sin(th) + (W @ W) * (1 - torch.cos(th)))
+        return cls.from_Rt(torch.eye(3).to(W) + res, t)
+
+    @property
+    def R(self) -> Tensor:
+        return self._data[..., :9].reshape(self._data.shape[:-1] + (3, 3))
+
+    @property
+    def t(self) -> Tensor:
+        return self._data[..., 9:]
+
+    def inv(self) -> 'Pose':
+        Rt = self.R.transpose(-1, -2)
+        return Pose.from_Rt(Rt, -(Rt @ self.t[..., None])[..., 0])
+
+    def compose(self, other: 'Pose') -> 'Pose':
+        return Pose.from_Rt(self.R @ other.R, self.t + (self.R @ other.t[..., None])[..., 0])
+
+    __matmul__ = compose
+
+    def transform(self, p3d) -> Tensor:
+        p3d = _as_tensor(p3d, self._data)
+        return p3d @ self.R.transpose(-1, -2) + self.t[..., None, :]
+
+    __mul__ = transform
+
+    def magnitude(self) -> Tuple[Tensor, Tensor]:
+        tr = torch.diagonal(self.R, dim1=-1, dim2=-2).sum(-1)
+        cos = torch.clamp((tr - 1) / 2, -1, 1)
+        return torch.acos(cos).abs() / math.pi * 180, torch.norm(self.t, dim=-1)
+
+    def numpy(self):
+        return self.R.numpy(), self.t.numpy()
+
+
+class Camera(_Wrapper):
+    def __init__(self, data):
+        super().__init__(data)
+        assert self._data.shape[-1] in (6, 8, 10)
+
+    @classmethod
+    def from_colmap(cls, camera) -> 'Camera':
+        """COLMAP camera dict/tuple -> Camera; pixel-centre origin (c - 0.5)."""
+        if hasattr(camera, '_asdict'):
+            camera = camera._asdict()
+        model, params = camera['model'], np.asarray(camera['params'], dtype=np.float64)
+        if model in ('OPENCV', 'PINHOLE'):
+            (fx, fy, cx, cy), rest = params[:4], params[4:]
+        elif model in ('SIMPLE_PINHOLE', 'SIMPLE_RADIAL', 'RADIAL'):
+            (f, cx, cy), rest = params[:3], params[3:]
+            fx = fy = f
+            if model == 'SIMPLE_RADIAL':
+                rest = np.r_[rest, 0.]
+        else:
+            raise NotImplementedError(model)
+        return cls(torch.from_numpy(np.r_[camera['width'], camera['height'], fx, fy, cx - 0.5, cy - 0.5, rest]))
+
+    @property
+    def size(self):
+        return self._data[..., :2]
+
+    @property
+    def f(self):
+        return self._data[..., 2:4]
+
+    @property
+    def c(self):
+        return self._data[..., 4:6]
+
+    @property
+    def dist(self):
+        return self._data[..., 6:]
+
+    def scale(self, scales: Union[float, int, Sequence[float]]) -> 'Camera':
+        if isinstance(scales, (int, float)):
+            scales = (scales, scales)
+        s = self._data.new_tensor(scales)
+        return Camera(torch.cat([self.size * s, self.f * s, (self.c + 0.5) * s - 0.5, self.dist], -1))

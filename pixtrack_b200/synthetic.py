@@ -216,3 +216,46 @@ def unet_weights(seed: int = 0) -> Dict[str, Tensor]:
         conv(f'adaptation.{idx}.0', OUTPUT_DIM[idx], cin, 1, gain=1.0)
         conv(f'uncertainty.{idx}.0', 1, cin, 1, gain=1.0)
     return sd
+
+
+# ---------------------------------------------------------------------------
+# full frames (SURVEY configs C2 / C4): 3-level pyramid, B views, N points
+# ---------------------------------------------------------------------------
+def frame_problem(seed: int, N: int = 5000, B: int = 8, size: Tuple[int, int] = (576, 1024),
+                  dims: Sequence[int] = (32, 128, 128), strides: Sequence[int] = (1, 4, 16),
+                  sigmas: Sequence[float] = (4.0, 2.0, 1.0), noise: float = 0.05, rot_deg: float = 1.0,
+                  trans: float = 0.005) -> Dict:
+    """One tracked frame: a 1920x1080 query resized to 1024x576 gives level
+    maps 32x576x1024 / 128x144x256 / 128x36x64.  Each of the B
+    reference views contributes N observations whose descriptors are the query
+    maps sampled at the ground-truth projection + noise; each view starts from
+    its own perturbed pose (frame-to-frame motion of SURVEY C2).
+    Returns per-level lists (fine -> coarse) of CHW query maps `F_q`, `W_q`
+    [1,H,W], cameras, `F_ref` [B,N,C], `W_ref` [B,N], plus p3d, T_init [B,12],
+    R_gt, t_gt."""
+    Hf, Wf = size
+    cam0 = scale_cam(pixtrack_camera(), (Wf / 1920.0, Wf / 1920.0))
+    p3d = object_points(N, seed * 13 + 1)
+    R_gt = axis_angle_to_R(torch.randn(3, generator=_gen(seed * 13 + 2)) * 0.05)
+    t_gt = torch.randn(3, generator=_gen(seed * 13 + 3)) * 0.02
+    g = _gen(seed * 13 + 4)
+    out = dict(F_q=[], W_q=[], cam=[], F_ref=[], W_ref=[], p3d=p3d, R_gt=R_gt, t_gt=t_gt)
+    for lv, (C, s, sg) in enumerate(zip(dims, strides, sigmas)):
+        H, W = Hf // s, Wf // s
+        cam = scale_cam(cam0, (1.0 / s, 1.0 / s))
+        Fq = smooth_feature_map(C, H, W, seed * 13 + 5 + lv, sg)
+        Wq = smooth_confidence(H, W, seed * 13 + 8 + lv)
+        uv = project_pinhole_radial(cam, R_gt, t_gt, p3d)
+        base = bilinear(Fq, uv)
+        fr = base[None] + noise * torch.randn(B, N, C, generator=g) / math.sqrt(C)
+        out['F_q'].append(Fq)
+        out['W_q'].append(Wq)
+        out['cam'].append(cam)
+        out['F_ref'].append(tF.normalize(fr, dim=2))
+        out['W_ref'].append(0.5 + 0.5 * torch.rand(B, N, generator=g))
+    T0 = []
+    for b in range(B):
+        Rb, tb = perturb_pose(R_gt, t_gt, seed * 1000 + b, rot_deg, trans)
+        T0.append(torch.cat([Rb.reshape(-1), tb]))
+    out['T_init'] = torch.stack(T0)
+    return out

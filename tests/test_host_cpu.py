@@ -1,0 +1,86 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, 'include', 'pixtrack_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    return sorted(set(re.findall(r'\b(ptk_[a-z0-9_]+)\s*\(', hdr)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from pixtrack_b200 import _lib
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/pixtrack_b200.h but not exported'
+        assert n in _lib.SYMBOLS, f'{n} has no ctypes prototype in _lib.py'
+    assert lib.ptk_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    from pixtrack_b200 import _lib
+    # 10 int32, 9 (pointer, int64) pairs, 1 pointer, 4 floats
+    assert ctypes.sizeof(_lib.LmProblem) == 40 + 9 * 16 + 8 + 16
+    assert _lib.LmProblem.p3d.offset == 40 and _lib.LmProblem.skip.offset == 40 + 9 * 16
+    assert ctypes.sizeof(_lib.LmResult) == 32
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_product_path_fails_loudly_without_cuda():
+    from pixtrack_b200 import _lib
+    from pixtrack_b200.geometry import Camera, Pose
+    from pixtrack_b200.optimizer import B200Optimizer
+    from pixtrack_b200.sampling import sample_points
+    with pytest.raises(_lib.PtkError):
+        _lib.context(0)
+    opt = B200Optimizer(dict(num_iters=3, pad=1, loss_fn='scaled_barron(0, 0.1)'))
+    with pytest.raises(_lib.PtkError):
+        opt.run(np.zeros((20, 3)), torch.zeros(20, 16), torch.zeros(16, 8, 8), Pose(torch.zeros(12)),
+                Camera(torch.ones(8)))
+    with pytest.raises(_lib.PtkError):
+        sample_points(torch.zeros(4, 8, 8), torch.zeros(3, 2))
+
+
+def test_product_package_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'pixtrack_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def test_conf_merge_and_damping():
+    from pixtrack_b200.optimizer import B200Optimizer, parse_loss
+    opt = B200Optimizer(dict(num_iters=150, pad=1, loss_fn='scaled_barron(0, 0.1)'))   # r9.py:46-49 style
+    assert opt.conf.num_iters == 150 and opt.conf.interpolation.pad == 1 and opt.interpolator.pad == 1
+    assert opt.conf.grad_stop_criteria == 1e-4 and opt.conf.dt_stop_criteria == 5e-3
+    assert parse_loss('scaled_barron(0, 0.1)') == 0.1
+    with pytest.raises(NotImplementedError):
+        parse_loss('squared_loss')
+    lam = opt.dampingnet()
+    np.testing.assert_allclose(lam.detach().numpy(), np.full(6, 10 ** -0.5), rtol=1e-6)
+    assert 'dampingnet.const' in opt.state_dict()       # checkpoint key optimizer.{l}.dampingnet.const
+
+
+def test_geometry_wrappers():
+    from pixtrack_b200.geometry import Camera, Pose
+    cam = Camera.from_colmap(dict(model='SIMPLE_RADIAL', width=1920, height=1080,
+                                  params=np.array([2304., 960., 540., 0.01])))
+    np.testing.assert_allclose(cam._data.numpy(), [1920, 1080, 2304, 2304, 959.5, 539.5, 0.01, 0.0])
+    s = cam.scale((0.5, 0.25))
+    np.testing.assert_allclose(s._data.numpy(), [960, 270, 1152, 576, 479.5, 134.5, 0.01, 0.0])
+    T = Pose.from_aa(torch.tensor([0.1, -0.2, 0.3]), torch.tensor([1., 2., 3.]))
+    I = (T.inv() @ T)._data
+    np.testing.assert_allclose(I.numpy(), np.r_[np.eye(3).ravel(), 0, 0, 0], atol=1e-6)
+    dr, dt = T.magnitude()
+    np.testing.assert_allclose(float(dr), np.degrees(np.linalg.norm([0.1, -0.2, 0.3])), rtol=1e-5)
