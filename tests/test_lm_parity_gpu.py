@@ -52,9 +52,10 @@ def check_vs_golden(out, g, prefix='', rtol_H=2e-4, atol_T=2e-5):
 
 
 def pose_error(Ta, Tb):
-    Ra, Rb = Ta[:9].reshape(3, 3), Tb[:9].reshape(3, 3)
-    c = np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1)
-    return math.acos(c), float(np.abs(Ta[9:] - Tb[9:]).max())
+    # rotation angle from the skew part of Ra^T Rb (sin form: well conditioned near 0, unlike acos(trace))
+    M = Ta[:9].reshape(3, 3).astype(np.float64).T @ Tb[:9].reshape(3, 3).astype(np.float64)
+    s = 0.5 * np.array([M[2, 1] - M[1, 2], M[0, 2] - M[2, 0], M[1, 0] - M[0, 1]])
+    return math.asin(min(1.0, float(np.linalg.norm(s)))), float(np.abs(Ta[9:] - Tb[9:]).max())
 
 
 def test_toy_fixture_golden():
