@@ -124,11 +124,39 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+def lm_stress(dev, lam, peak):
+    """LM kernel alone at BASELINE config-4 scale (level 1: C=128, 144x256, N=20000, B=16, 30 fixed
+    iterations): the regime where a roofline fraction is meaningful."""
+    from pixtrack_b200.optimizer import LmLaunch, query_map_to_hwc
+    p = syn.level_problem(seed=9, N=20000, C=128, H=144, W=256, B=16, noise=0.02, rot_deg=0.5, trans=0.005)
+    T0 = torch.cat([p['R0'].reshape(16, 9), p['t0']], 1).to(dev)
+    L = LmLaunch(p['p3d'].to(dev), p['F_ref'].to(dev), query_map_to_hwc(p['F_q'].to(dev)), T0, p['cam'].to(dev), lam,
+                 p['W_ref'].reshape(16, -1).to(dev), p['W_q'].to(dev), num_iters=30, grad_stop=0.0, dt_stop=0.0,
+                 dR_stop=0.0)
+    for _ in range(3):
+        L.launch()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    a.record()
+    for _ in range(reps):
+        L.launch()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    nv = float(L.log[:, :, 1].sum())
+    byts = nv * (52 * 128 + 32)
+    g, ng = L.plan()
+    return {'workload': 'C4 level 1: C=128 144x256, N=20000, B=16, 30 fixed iterations', 'ms_per_launch': ms,
+            'us_per_iteration': 1e3 * ms / 30, 'achieved': byts / (ms * 1e-3) / 1e9, 'unit': 'GB/s',
+            'frac': byts / (ms * 1e-3) / 1e9 / peak, 'ctas_per_problem': g, 'problems_in_flight': ng,
+            'note': 'algorithmic bytes (52C+32 per valid point per iteration); the 19 MB map stays L2-resident'}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from pixtrack_b200 import _lib
-    from pixtrack_b200.optimizer import query_map_to_hwc
-    from pixtrack_b200.refiner import refine_levels_batched
+    from pixtrack_b200.refiner import FramePlan
 
     torch.set_grad_enabled(False)
     dev = torch.device('cuda', local_rank)
@@ -138,24 +166,22 @@ def run_ours(args, rank, world, local_rank):
     lam = lam0().to(dev)
     frames = host_frames(rank)
 
-    # host (pinned) and device copies of the per-frame inputs
-    host, devf = [], []
+    # per ring slot: pinned host copies of the per-frame inputs (query pyramid, channels-last),
+    # device-resident copies, a device staging area for the end-to-end leg, and prepared launch chains
+    host, plans, plans_e2e, staging = [], [], [], []
     for fr in frames:
         h = dict(fq=[f.permute(1, 2, 0).contiguous().pin_memory() for f in fr['F_q']],
                  wq=[w[0].contiguous().pin_memory() for w in fr['W_q']])
-        d = dict(fq=[x.to(dev) for x in h['fq']], wq=[x.to(dev) for x in h['wq']],
-                 cam=[c.to(dev) for c in fr['cam']], F_ref=[x.to(dev) for x in fr['F_ref']],
-                 W_ref=[x.to(dev) for x in fr['W_ref']], p3d=fr['p3d'].to(dev), T0=fr['T_init'].to(dev))
+        ref = dict(cams=[c.to(dev) for c in fr['cam']], F_ref=[x.to(dev) for x in fr['F_ref']],
+                   W_ref=[x.to(dev) for x in fr['W_ref']], p3d=fr['p3d'].to(dev), T_init=fr['T_init'].to(dev))
+        fq, wq = [x.to(dev) for x in h['fq']], [x.to(dev) for x in h['wq']]
+        st = dict(fq=[torch.empty_like(x) for x in fq], wq=[torch.empty_like(x) for x in wq])
         host.append(h)
-        devf.append(d)
+        staging.append(st)
+        plans.append(FramePlan(fq, wq, lams=[lam] * 3, **ref, **STOP).capture())
+        plans_e2e.append(FramePlan(st['fq'], st['wq'], lams=[lam] * 3, **ref, **STOP).capture())
     ring_bytes = sum(x.numel() * 4 for x in host[0]['fq'] + host[0]['wq']) * RING
-
-    launches = [0]
-
-    def step(d, fq=None, wq=None):
-        launches[0] += 3
-        return refine_levels_batched(fq or d['fq'], wq or d['wq'], d['cam'], d['F_ref'], d['W_ref'], d['p3d'], d['T0'],
-                                     [lam] * 3, **STOP)
+    graphs = plans[0].graph is not None
 
     def barrier():
         torch.cuda.synchronize()
@@ -163,53 +189,48 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing --------------------------------------------------------------
+    # ---- device-resident timing: K frames, inputs already in HBM ---------------------------------
     for i in range(args.warmup):
-        step(devf[i % RING])
+        plans[i % RING].run()
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    outs = []
+        time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches[0] = 0
     ev0.record()
     for i in range(args.steps):
-        outs.append(step(devf[i % RING]))
+        plans[i % RING].run()
     ev1.record()
     barrier()
-    n_launch = launches[0]
+    n_launch = 3 * args.steps
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
-    clk = clocks.stop() if rank == 0 else None
     _lib.device_status(local_rank)
 
-    # ---- per-launch timing of the LM kernel for the roofline (same inputs, events around each launch)
-    from pixtrack_b200.optimizer import lm_run_batched
+    # ---- per-launch timing of the LM kernel for the roofline (events around each bare launch) ------
     per_level = {}
-    for i in range(min(args.steps, 2 * RING)):
-        d = devf[i % RING]
-        T, skip = d['T0'], None
-        for lv in (2, 1, 0):
+    for i in range(min(args.steps, 4 * RING)):
+        pl = plans[i % RING]
+        for k, L in enumerate(pl.launches):
+            lv = 2 - k
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            T, failed, n_it, log = lm_run_batched(d['p3d'], d['F_ref'][lv], d['fq'][lv], T, d['cam'][lv], lam,
-                                                  d['W_ref'][lv], d['wq'][lv], None, skip, **STOP)
+            L.launch()
             b.record()
             torch.cuda.synchronize()
-            skip = failed
-            C = d['fq'][lv].shape[-1]
-            nv = 0.0
-            lg = log.cpu()
-            for v in range(N_VIEWS):
-                nv += float(lg[v, :int(n_it[v]), 1].sum())
+            Cc = L.shape[2]
+            n_it = L.n_iters.cpu()
+            lg = L.log[:, :, 1].cpu()
+            nv = sum(float(lg[v, :int(n_it[v])].sum()) for v in range(N_VIEWS))
             rec = per_level.setdefault(lv, dict(ms=0.0, bytes=0.0, n=0, iters=0))
             rec['ms'] += a.elapsed_time(b)
-            rec['bytes'] += nv * (52 * C + 32)
+            rec['bytes'] += nv * (52 * Cc + 32)
             rec['n'] += 1
             rec['iters'] += int(n_it.max())
+    clk = clocks.stop() if rank == 0 else None
     dom = max(per_level, key=lambda k: per_level[k]['ms'])
     peaks = {}
     try:
@@ -218,19 +239,20 @@ def run_ours(args, rank, world, local_rank):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     ach = per_level[dom]['bytes'] / (per_level[dom]['ms'] * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': f'lm_kernel level {dom}', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                'frac': ach / peak, 'traffic': None,
+    roofline = {'bound': 'hbm', 'kernel': f'lm_kernel (pyramid level {dom} launch)', 'achieved': ach, 'peak': peak,
+                'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
-                'per_level': {str(k): {'ms_per_launch': v['ms'] / v['n'], 'GBps': v['bytes'] / (v['ms'] * 1e-3) / 1e9,
+                'per_level': {str(k): {'us_per_launch': 1e3 * v['ms'] / v['n'], 'GBps': v['bytes'] / (v['ms'] * 1e-3) / 1e9,
                                        'max_iters_per_launch': v['iters'] / v['n']} for k, v in per_level.items()}}
+    stress = lm_stress(dev, lam, peak) if rank == 0 else None
 
-    # ---- end to end: host buffers in, poses out ------------------------------------------------
+    # ---- end to end: host buffers in (pinned -> staging), poses out ---------------------------------
     def e2e_step(i):
-        h, d = host[i % RING], devf[i % RING]
-        fq = [x.to(dev, non_blocking=True) for x in h['fq']]
-        wq = [x.to(dev, non_blocking=True) for x in h['wq']]
-        out = step(d, fq, wq)
-        return out['T'].cpu(), out['failed'].cpu()
+        h, st, pl = host[i % RING], staging[i % RING], plans_e2e[i % RING]
+        for dst, src in zip(st['fq'] + st['wq'], h['fq'] + h['wq']):
+            dst.copy_(src, non_blocking=True)
+        pl.run()
+        return pl.T.cpu(), pl.failed.cpu()
     for i in range(max(1, args.warmup // 2)):
         e2e_step(i)
     barrier()
@@ -244,38 +266,40 @@ def run_ours(args, rank, world, local_rank):
     h2d = sum(x.numel() * 4 for x in host[0]['fq'] + host[0]['wq'])
     d2h = N_VIEWS * 13
 
-    # ---- final gather of per-frame results (the only collective on this path) -------------------
-    res = torch.stack([torch.cat([o['T'], o['failed'].float()[:, None]], 1) for o in outs[-RING:]])
+    # ---- final gather of per-frame results (the only collective on this path) -----------------------
+    res = torch.stack([torch.cat([pl.T, pl.failed.float()[:, None]], 1) for pl in plans])
     if world > 1:
         gathered = [torch.empty_like(res) for _ in range(world)]
         dist.all_gather(gathered, res)
-    iters = [[int(x.max()) for x in o['n_iters']] for o in outs[-RING:]]
-    ok = all(not bool(o['failed'].any()) for o in outs)
+    iters = [[int(x.max()) for x in pl.n_iters] for pl in plans]
+    ok = all(not bool(pl.failed.any()) for pl in plans)
 
     if rank == 0:
         cpu = None
         if world == 1:
             th = os.cpu_count() or 1
+            cpu_refine_view(frames[0], 0, th)
             t0 = time.perf_counter()
             n_v = 0
-            while n_v < 2 and time.perf_counter() - t0 < 25:
-                cpu_refine_view(frames[0], n_v, th)
+            while n_v < 40 and time.perf_counter() - t0 < 15:
+                cpu_refine_view(frames[n_v // N_VIEWS % RING], n_v % N_VIEWS, th)
                 n_v += 1
             dt = time.perf_counter() - t0
             cpu = {'value': n_v / dt / N_VIEWS, 'unit': 'frames/s', 'cores': th, 'kind': 'port',
-                   'sample': f'{n_v} of the 8 views of one C2 frame (3 levels to convergence) via oracle/lm.py, '
-                             f'{dt:.1f} s; frames/s = views/s / 8'}
+                   'sample': f'{n_v} view refinements (each 3 levels to convergence) of the same C2 frames via '
+                             f'oracle/lm.py in {dt:.1f} s; frames/s = views/s / 8'}
         fps = args.steps * world / (ms_total * 1e-3)
         line = {
             'metric': 'tracked frames/sec (LM-to-convergence)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'l2': f'inputs larger than L2: ring of {RING} frames, {ring_bytes / 1e6:.0f} MB of maps',
+            'config': {'workload': WORKLOAD,
+                       'l2': f'inputs larger than L2: ring of {RING} frames, {ring_bytes / 1e6:.0f} MB of maps',
                        'stage': 'LM only (pyramids synthetic; extractor and NeRF render not in the timed step yet)',
-                       'lm_iters_last_frames_coarse_to_fine': iters, 'all_converged_without_failure': ok},
+                       'cuda_graph': graphs, 'lm_iters_coarse_to_fine': iters, 'no_failures': ok},
             'e2e': {'value': args.steps * world / float(e2e_s), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h},
-            'gpu_launches': n_launch, 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
+            'gpu_launches': n_launch, 'clocks': clk, 'roofline': roofline, 'lm_stress': stress, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -115,71 +115,99 @@ def query_map_to_hwc(F_q: Tensor, normalize: bool = False) -> Tensor:
     return dst
 
 
-def lm_run_batched(p3d: Tensor, F_ref: Tensor, fq_hwc: Tensor, T_init: Tensor, cam: Tensor, lam: Tensor,
-                   W_ref: Optional[Tensor] = None, wq: Optional[Tensor] = None, mask: Optional[Tensor] = None,
-                   skip: Optional[Tensor] = None, *, num_iters: int, pad: int = 1, loss_scale: float = 0.1,
-                   grad_stop: float = 1e-4, dt_stop: float = 5e-3, dR_stop: float = 5e-2, min_valid: int = 10,
-                   want_log: bool = True):
-    """Batched device-resident entry (what bench and the refiner use).
+class LmLaunch:
+    """A prepared ptk_lm_run call: argument struct, output buffers and keep-alive
+    references are built once; `launch()` is then a single ctypes call (a few
+    microseconds of host time), so chains of launches stay GPU-bound and can be
+    captured in a CUDA graph.
 
     Shapes (fp32 CUDA, contiguous; a leading batch dim of 1 / a missing batch
     dim means "shared by all B problems"):
       p3d [B|1,N,3]  F_ref [B,N,C]  fq_hwc [B|1,H,W,C]  T_init [B,12]
       cam [B|1,6|8|10]  lam [B|1,6]  W_ref [B,N]  wq [B|1,H,W]  mask [B,N] uint8/bool
-      skip [B] uint8.
-    Returns (T [B,12], failed [B] uint8, n_iters [B] int32, log [B,num_iters,64] or None);
-    nothing is synchronised."""
-    dev = F_ref.device
-    assert dev.type == 'cuda', 'B200 LM path needs CUDA tensors (no CPU fallback)'
-    B, N, Cc = F_ref.shape
+      skip [B] uint8 (e.g. the `failed` output of the previous level's launch).
+    Outputs: T [B,12], failed [B] uint8, n_iters [B] int32, log [B,num_iters,64] or None."""
 
-    def prep(x, nd):
-        x = _f32c(x)
-        return x if x.dim() == nd else x[None]
+    def __init__(self, p3d: Tensor, F_ref: Tensor, fq_hwc: Tensor, T_init: Tensor, cam: Tensor, lam: Tensor,
+                 W_ref: Optional[Tensor] = None, wq: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+                 skip: Optional[Tensor] = None, *, num_iters: int, pad: int = 1, loss_scale: float = 0.1,
+                 grad_stop: float = 1e-4, dt_stop: float = 5e-3, dR_stop: float = 5e-2, min_valid: int = 10,
+                 want_log: bool = True):
+        dev = F_ref.device
+        if dev.type != 'cuda':
+            raise _lib.PtkError('the LM path needs CUDA tensors (no CPU fallback)')
+        B, N, Cc = F_ref.shape
 
-    p3d, fq_hwc, cam, lam = prep(p3d, 3), prep(fq_hwc, 4), prep(cam, 2), prep(lam, 2)
-    F_ref, T_init = _f32c(F_ref), _f32c(T_init).reshape(B, 12)
-    H, W = fq_hwc.shape[1:3]
-    assert fq_hwc.shape[3] == Cc and p3d.shape[1] == N
+        def prep(x, nd):
+            x = _f32c(x)
+            return x if x.dim() == nd else x[None]
 
-    def bs(x, per):
-        return 0 if x.shape[0] == 1 and B > 1 else per
+        p3d, fq_hwc, cam, lam = prep(p3d, 3), prep(fq_hwc, 4), prep(cam, 2), prep(lam, 2)
+        F_ref, T_init = _f32c(F_ref), _f32c(T_init).reshape(B, 12)
+        H, W = fq_hwc.shape[1:3]
+        assert fq_hwc.shape[3] == Cc and p3d.shape[1] == N
 
-    prob = _lib.LmProblem()
-    prob.B, prob.N, prob.C, prob.H, prob.W = B, N, Cc, H, W
-    prob.n_cam, prob.num_iters, prob.pad, prob.min_valid = cam.shape[-1], int(num_iters), int(pad), int(min_valid)
-    prob.p3d, prob.p3d_bstride = p3d.data_ptr(), bs(p3d, N * 3)
-    prob.f_ref, prob.f_ref_bstride = F_ref.data_ptr(), N * Cc
-    keep = [p3d, F_ref, fq_hwc, cam, lam, T_init]
-    if W_ref is not None:
-        W_ref = _f32c(W_ref).reshape(B, N)
-        wq = prep(wq.reshape(-1, H, W) if wq.dim() > 2 else wq, 3)
-        prob.w_ref, prob.w_ref_bstride = W_ref.data_ptr(), N
-        prob.wq, prob.wq_bstride = wq.data_ptr(), bs(wq, H * W)
-        keep += [W_ref, wq]
-    prob.fq, prob.fq_bstride = fq_hwc.data_ptr(), bs(fq_hwc, H * W * Cc)
-    if mask is not None:
-        mask = mask.to(torch.uint8).contiguous().reshape(B, N)
-        prob.mask, prob.mask_bstride = mask.data_ptr(), N
-        keep.append(mask)
-    prob.cam, prob.cam_bstride = cam.data_ptr(), bs(cam, cam.shape[-1])
-    prob.T_init, prob.T_bstride = T_init.data_ptr(), 12
-    prob.lambda_, prob.lambda_bstride = lam.data_ptr(), bs(lam, 6)
-    if skip is not None:
-        skip = skip.to(torch.uint8).contiguous()
-        prob.skip = skip.data_ptr()
-        keep.append(skip)
-    prob.loss_scale, prob.grad_stop, prob.dt_stop, prob.dR_stop = loss_scale, grad_stop, dt_stop, dR_stop
+        def bs(x, per):
+            return 0 if x.shape[0] == 1 and B > 1 else per
 
-    T = torch.empty((B, 12), dtype=torch.float32, device=dev)
-    failed = torch.empty((B,), dtype=torch.uint8, device=dev)
-    n_iters = torch.empty((B,), dtype=torch.int32, device=dev)
-    log = torch.zeros((B, max(1, num_iters), _lib.LOG_STRIDE), dtype=torch.float32, device=dev) if want_log else None
-    res = _lib.LmResult(T.data_ptr(), failed.data_ptr(), n_iters.data_ptr(), _ptr(log))
-    di = dev.index if dev.index is not None else torch.cuda.current_device()
-    _lib.check(_lib.load().ptk_lm_run(_lib.context(di), C.byref(prob), C.byref(res), _lib.current_stream_ptr(dev)))
-    del keep
-    return T, failed, n_iters, log
+        prob = _lib.LmProblem()
+        prob.B, prob.N, prob.C, prob.H, prob.W = B, N, Cc, H, W
+        prob.n_cam, prob.num_iters, prob.pad, prob.min_valid = cam.shape[-1], int(num_iters), int(pad), int(min_valid)
+        prob.p3d, prob.p3d_bstride = p3d.data_ptr(), bs(p3d, N * 3)
+        prob.f_ref, prob.f_ref_bstride = F_ref.data_ptr(), N * Cc
+        keep = [p3d, F_ref, fq_hwc, cam, lam, T_init]
+        if W_ref is not None:
+            W_ref = _f32c(W_ref).reshape(B, N)
+            wq = prep(wq.reshape(-1, H, W) if wq.dim() > 2 else wq, 3)
+            prob.w_ref, prob.w_ref_bstride = W_ref.data_ptr(), N
+            prob.wq, prob.wq_bstride = wq.data_ptr(), bs(wq, H * W)
+            keep += [W_ref, wq]
+        prob.fq, prob.fq_bstride = fq_hwc.data_ptr(), bs(fq_hwc, H * W * Cc)
+        if mask is not None:
+            mask = mask.to(torch.uint8).contiguous().reshape(B, N)
+            prob.mask, prob.mask_bstride = mask.data_ptr(), N
+            keep.append(mask)
+        prob.cam, prob.cam_bstride = cam.data_ptr(), bs(cam, cam.shape[-1])
+        prob.T_init, prob.T_bstride = T_init.data_ptr(), 12
+        prob.lambda_, prob.lambda_bstride = lam.data_ptr(), bs(lam, 6)
+        if skip is not None:
+            assert skip.dtype == torch.uint8 and skip.is_contiguous()
+            prob.skip = skip.data_ptr()
+            keep.append(skip)
+        prob.loss_scale, prob.grad_stop, prob.dt_stop, prob.dR_stop = loss_scale, grad_stop, dt_stop, dR_stop
+
+        self.T = torch.empty((B, 12), dtype=torch.float32, device=dev)
+        self.failed = torch.empty((B,), dtype=torch.uint8, device=dev)
+        self.n_iters = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.log = (torch.zeros((B, max(1, num_iters), _lib.LOG_STRIDE), dtype=torch.float32, device=dev)
+                    if want_log else None)
+        self._res = _lib.LmResult(self.T.data_ptr(), self.failed.data_ptr(), self.n_iters.data_ptr(), _ptr(self.log))
+        self._prob, self._keep, self.device = prob, keep, dev
+        di = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._ctx, self._fn = _lib.context(di), _lib.load().ptk_lm_run
+        self.shape = (B, N, Cc, H, W)
+
+    def launch(self, stream_ptr: Optional[int] = None):
+        """Stream-ordered, never synchronises.  Returns self for chaining."""
+        if stream_ptr is None:
+            stream_ptr = torch.cuda.current_stream(self.device).cuda_stream
+        code = self._fn(self._ctx, C.byref(self._prob), C.byref(self._res), stream_ptr)
+        if code != 0:
+            _lib.check(code)
+        return self
+
+    def plan(self):
+        """(CTAs per problem, problems in flight) the launch uses."""
+        g, n = C.c_int32(), C.c_int32()
+        _lib.check(_lib.load().ptk_lm_plan(self._ctx, C.byref(self._prob), C.byref(g), C.byref(n)))
+        return g.value, n.value
+
+
+def lm_run_batched(*args, **kw):
+    """One-shot form: build an LmLaunch, launch it, return
+    (T [B,12], failed [B] uint8, n_iters [B] int32, log or None); nothing is synchronised."""
+    L = LmLaunch(*args, **kw).launch()
+    return L.T, L.failed, L.n_iters, L.log
 
 
 def unpack_H(rec: np.ndarray) -> np.ndarray:

@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from .optimizer import lm_run_batched
+from .optimizer import LmLaunch, lm_run_batched
 
 Tensor = torch.Tensor
 
@@ -41,3 +41,61 @@ def refine_levels_batched(fq_hwc: Sequence[Tensor], wq: Sequence[Optional[Tensor
         n_all.append(n_it)
         logs.append(log)
     return dict(T=T, failed=skip, n_iters=n_all, logs=logs)
+
+
+class FramePlan:
+    """The coarse-to-fine chain of one frame batch as prepared launches.
+
+    Built once over STATIC buffers (query pyramid, reference observations,
+    initial poses); `run()` is then L bare ctypes launches (coarse -> fine),
+    each reading the previous level's pose / failed outputs directly on the
+    device.  `capture()` records the chain into a CUDA graph so a frame costs
+    one graph launch."""
+
+    def __init__(self, fq_hwc, wq, cams, F_ref, W_ref, p3d, T_init, lams, **kw):
+        self.launches = []
+        T, skip = T_init, None
+        for lv in reversed(range(len(fq_hwc))):
+            L = LmLaunch(p3d, F_ref[lv], fq_hwc[lv], T, cams[lv], lams[lv], W_ref[lv], wq[lv], None, skip, **kw)
+            self.launches.append(L)
+            T, skip = L.T, L.failed
+        self.T, self.failed = T, skip
+        self.graph = None
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return self
+        sp = torch.cuda.current_stream(self.launches[0].device).cuda_stream
+        for L in self.launches:
+            L.launch(sp)
+        return self
+
+    def capture(self):
+        """Capture the chain in a CUDA graph (falls back to direct launches if
+        the driver refuses to capture a cooperative launch)."""
+        dev = self.launches[0].device
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            self.run()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g, stream=s):
+                for L in self.launches:
+                    L.launch(s.cuda_stream)
+            self.graph = g
+        except Exception:       # noqa: BLE001 - capture is an optimisation, the direct chain is equivalent
+            self.graph = None
+            torch.cuda.synchronize(dev)
+        return self
+
+    @property
+    def n_iters(self):
+        return [L.n_iters for L in self.launches]
+
+    @property
+    def logs(self):
+        return [L.log for L in self.launches]

@@ -159,11 +159,12 @@ def test_full_size_properties():
     every view agrees, and the logged cost decreases."""
     from pixtrack_b200.optimizer import lm_run_batched, query_map_to_hwc
     d = _dev()
-    p = syn.level_problem(seed=9, N=20000, C=128, H=144, W=256, B=16, noise=0.02)
+    p = syn.level_problem(seed=9, N=20000, C=128, H=144, W=256, B=16, noise=0.02, rot_deg=0.5, trans=0.005)
     T0 = torch.cat([p['R0'].reshape(16, 9), p['t0']], 1).to(d)
     T, failed, n, log = lm_run_batched(p['p3d'].to(d), p['F_ref'].to(d), query_map_to_hwc(p['F_q'].to(d)), T0,
-                                       p['cam'].to(d), cases.damping(torch.full((6,), -2.0)).to(d),
-                                       p['W_ref'].reshape(16, -1).to(d), p['W_q'].to(d), num_iters=100)
+                                       p['cam'].to(d), cases.damping(torch.zeros(6)).to(d),
+                                       p['W_ref'].reshape(16, -1).to(d), p['W_q'].to(d), num_iters=150,
+                                       grad_stop=0.0, dt_stop=1e-5, dR_stop=1e-3)
     torch.cuda.synchronize()
     assert not bool(failed.any())
     Tg = torch.cat([p['R_gt'].reshape(-1), p['t_gt']]).numpy()
