@@ -18,9 +18,10 @@
 //    (A = 2x6 projection chain of the point) the per-point sums collapse to
 //      H_n = A^T [Sxx Sxy; Sxy Syy] A,   g_n = A^T [Sxr; Syr],
 //    so only 6 channel sums (+1 confidence) cross lanes (xor shuffles).
-//  * Each lane owns a slice of the 29 accumulated scalars (21 H, 6 g, cost, count);
-//    warp -> CTA -> problem reduction is fixed-order (bit-reproducible), no float
-//    atomics.  G CTAs share one problem; they meet once per iteration at a
+//  * Scalar per-point work (projection, robust weight, Jacobian chain, the 29
+//    accumulated scalars: 21 H, 6 g, cost, count) is done by ONE thread per point;
+//    the warps that gather texels do nothing else (see lm_kernel).  thread -> warp
+//    -> CTA -> problem reduction is fixed-order (bit-reproducible), no float atomics.  G CTAs share one problem; they meet once per iteration at a
 //    counter barrier in global memory, then every CTA redundantly sums the G
 //    partial vectors in the same order, solves the 6x6 system and updates its own
 //    copy of the pose -- identical arithmetic, so no broadcast is needed.
@@ -46,23 +47,6 @@ struct LmParams {
   unsigned int* counters;
   int* error;
 };
-
-__device__ __forceinline__ float pick6(const float (&a)[6], int i) {
-  float v = a[0];
-  v = (i == 1) ? a[1] : v;
-  v = (i == 2) ? a[2] : v;
-  v = (i == 3) ? a[3] : v;
-  v = (i == 4) ? a[4] : v;
-  v = (i == 5) ? a[5] : v;
-  return v;
-}
-
-// entry e of the accumulated vector -> (row, col) of the upper triangle (e < 21)
-__device__ __forceinline__ void entry_rc(int e, int& r, int& c) {
-  r = (e >= 6) + (e >= 11) + (e >= 15) + (e >= 18) + (e >= 20);
-  const int start = r * 6 - (r * (r - 1)) / 2;
-  c = r + (e - start);
-}
 
 // One channel of the 12-texel cross footprint: bilinear value and the two
 // central differences (interpolation.py:61-83), folded into the 6 sums.
@@ -231,10 +215,90 @@ __device__ __noinline__ void solve_and_update(const float* tot, const float* lam
   }
 }
 
+// Per-problem constants of the camera model, hoisted out of the point loops.
+struct CamK {
+  float cw, ch, fx, fy, cx, cy, k1, k2, p1, p2;
+  float limit, xmax, ymax, padf;
+  int n_cam;
+  bool limited;
+};
+
+// Projection of one 3D point (wrappers.py:177-185,308-355; utils.py:36-69) and, when kJac, the 2x6
+// chain A = diag(f) * J_undist * J_project * [I | -skew(p_cam)] (wrappers.py:195-203,316-362; utils.py:72-95).
+template <bool kJac>
+__device__ __forceinline__ bool point_geometry(const CamK& c, const float* __restrict__ T, float X, float Y, float Z,
+                                               float& u, float& v, float (&A0)[6], float (&A1)[6]) {
+  const float px = fmaf(T[2], Z, fmaf(T[1], Y, T[0] * X)) + T[9];
+  const float py = fmaf(T[5], Z, fmaf(T[4], Y, T[3] * X)) + T[10];
+  const float pz = fmaf(T[8], Z, fmaf(T[7], Y, T[6] * X)) + T[11];
+  bool valid = pz > kZEps;                               // wrappers.py:311
+  const float z = fmaxf(pz, kZEps);
+  const float xn = px / z, yn = py / z;
+  float xd = xn, yd = yn;
+  float jxx = 1.f, jyy = 1.f, jxy = 0.f, jyx = 0.f;
+  if (c.n_cam > 6) {
+    const float r2 = xn * xn + yn * yn;
+    const float radial = c.k1 * r2 + c.k2 * r2 * r2;
+    xd = xn + xn * radial;
+    yd = yn + yn * radial;
+    valid = valid && (!c.limited || r2 < c.limit);
+    const float uvn = xn * yn;
+    if (kJac) {
+      const float drad = 2.f * c.k1 + 4.f * c.k2 * r2;
+      jxx += radial + xn * xn * drad;
+      jyy += radial + yn * yn * drad;
+      jxy += uvn * drad;
+      jyx += uvn * drad;
+    }
+    if (c.n_cam > 8) {
+      xd += 2.f * c.p1 * uvn + c.p2 * (r2 + 2.f * xn * xn);
+      yd += 2.f * c.p2 * uvn + c.p1 * (r2 + 2.f * yn * yn);
+      if (kJac) {
+        jxx += 2.f * c.p1 * yn + 6.f * c.p2 * xn;
+        jyy += 2.f * c.p2 * xn + 6.f * c.p1 * yn;
+        jxy += 2.f * c.p1 * xn + 2.f * c.p2 * yn;
+        jyx += 2.f * c.p2 * yn + 2.f * c.p1 * xn;
+      }
+    }
+  }
+  u = xd * c.fx + c.cx;
+  v = yd * c.fy + c.cy;
+  valid = valid && (u >= 0.f) && (v >= 0.f) && (u <= c.cw - 1.f) && (v <= c.ch - 1.f);     // Camera.in_image
+  valid = valid && (u >= c.padf) && (v >= c.padf) && (u <= c.xmax) && (v <= c.ymax);       // mask_in_image
+  if (kJac) {
+    const float iz = 1.f / z;
+    const float jp02 = -px / (z * z), jp12 = -py / (z * z);
+    const float m00 = c.fx * jxx, m01 = c.fx * jxy, m10 = c.fy * jyx, m11 = c.fy * jyy;
+    const float q00 = m00 * iz, q01 = m01 * iz, q02 = m00 * jp02 + m01 * jp12;
+    const float q10 = m10 * iz, q11 = m11 * iz, q12 = m10 * jp02 + m11 * jp12;
+    A0[0] = q00; A0[1] = q01; A0[2] = q02;
+    A0[3] = q02 * py - q01 * pz;
+    A0[4] = q00 * pz - q02 * px;
+    A0[5] = q01 * px - q00 * py;
+    A1[0] = q10; A1[1] = q11; A1[2] = q12;
+    A1[3] = q12 * py - q11 * pz;
+    A1[4] = q10 * pz - q12 * px;
+    A1[5] = q11 * px - q10 * py;
+  }
+  return valid;
+}
+
+constexpr int kPass = 1024;                   // points a CTA stages per pass
+constexpr int kRounds = kPass / kThreads;     // points per thread per pass
+
+// One LM launch.  Per iteration and per pass of <= kPass points a CTA runs three phases:
+//  A  one THREAD per point: projection + validity, (u,v) to shared memory, deterministic compaction
+//     of the valid points into a list;
+//  B  WARPS walk the list: LPP lanes per point gather the 12-texel footprint (float4 per lane per
+//     texel), fold it into 6 channel sums + the confidence sample, xor-reduce them inside the lane
+//     group and park the 7 totals in shared memory;
+//  C  one THREAD per point again: robust weight, Jacobian chain, and the 29 contributions
+//     (21 H, 6 g, cost, count) accumulated in that thread's registers.
+// Only phase B touches the maps, and it carries no per-point scalar math, so the issue slots go to
+// loads and the interpolation FMAs.
 template <int LPP>
 __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
-  constexpr int PPW = 32 / LPP;                       // points a warp handles at once
-  constexpr int K = (kEntries + LPP - 1) / LPP;       // accumulated entries per lane
+  constexpr int PPW = 32 / LPP;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int sub = lane % LPP;
@@ -243,34 +307,19 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
   const int rank = blockIdx.x - group * P.G;
   const unsigned full = 0xffffffffu;
 
+  __shared__ float2 sUV[kPass];
+  __shared__ __align__(16) float sSums[kPass][8];
+  __shared__ unsigned short sList[kPass];
+  __shared__ unsigned sMask[kRounds * kWarps];
+  __shared__ int sOffs[kRounds * kWarps];
+  __shared__ int sNValid;
   __shared__ float sWarp[kWarps][32];
   __shared__ float sTot[32];
   __shared__ float sT[12];
   __shared__ float sCam[12];
   __shared__ float sLam[6];
   __shared__ int sStop, sFailed, sAbort;
-
-  // which entries this lane accumulates
-  int eType[K], eR[K], eC[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int e = sub + LPP * k;
-    eR[k] = 0;
-    eC[k] = 0;
-    if (e < 21) {
-      eType[k] = 0;
-      entry_rc(e, eR[k], eC[k]);
-    } else if (e < 27) {
-      eType[k] = 1;
-      eR[k] = e - 21;
-    } else if (e == 27) {
-      eType[k] = 2;
-    } else if (e == 28) {
-      eType[k] = 3;
-    } else {
-      eType[k] = 4;
-    }
-  }
+  static_assert(kRounds * kWarps <= 32, "prefix scan is done by one warp");
 
   const PtkLmProblem& p = P.p;
   const int C4 = p.C >> 2;
@@ -305,184 +354,186 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
     const bool skipped = p.skip != nullptr && p.skip[b] != 0;
     int it = 0;
     if (!skipped) {
-      const float cw = sCam[0], ch = sCam[1], fx = sCam[2], fy = sCam[3], cx = sCam[4], cy = sCam[5];
-      const float k1 = sCam[6], k2 = sCam[7], p1 = sCam[8], p2 = sCam[9];
-      // validity limit of the radial model, utils.py:49-60
-      bool limited = false;
-      float limit = 0.f;
-      if (p.n_cam > 6) {
-        const float disc = 9.f * k1 * k1 - 20.f * k2;
-        limited = ((k2 > 0.f) && (disc > 0.f)) || ((k2 <= 0.f) && (k1 > 0.f));
-        limit = fabsf(k2 > 0.f ? (sqrtf(disc) - 3.f * k1) / (10.f * k2) : 1.f / (3.f * k1));
+      CamK ck;
+      ck.cw = sCam[0]; ck.ch = sCam[1]; ck.fx = sCam[2]; ck.fy = sCam[3]; ck.cx = sCam[4]; ck.cy = sCam[5];
+      ck.k1 = sCam[6]; ck.k2 = sCam[7]; ck.p1 = sCam[8]; ck.p2 = sCam[9];
+      ck.n_cam = p.n_cam;
+      ck.limited = false;
+      ck.limit = 0.f;
+      if (p.n_cam > 6) {   // validity limit of the radial model, utils.py:49-60
+        const float disc = 9.f * ck.k1 * ck.k1 - 20.f * ck.k2;
+        ck.limited = ((ck.k2 > 0.f) && (disc > 0.f)) || ((ck.k2 <= 0.f) && (ck.k1 > 0.f));
+        ck.limit = fabsf(ck.k2 > 0.f ? (sqrtf(disc) - 3.f * ck.k1) / (10.f * ck.k2) : 1.f / (3.f * ck.k1));
       }
-      const float xmax = (float)(p.W - 1 - p.pad), ymax = (float)(p.H - 1 - p.pad), padf = (float)p.pad;
+      ck.xmax = (float)(p.W - 1 - p.pad);
+      ck.ymax = (float)(p.H - 1 - p.pad);
+      ck.padf = (float)p.pad;
 
       for (it = 0; it < p.num_iters; ++it) {
-        float R[9], t[3];
+        float T[12];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) R[i] = sT[i];
+        for (int i = 0; i < 12; ++i) T[i] = sT[i];
+        float acc[kEntries];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) t[i] = sT[9 + i];
+        for (int e = 0; e < kEntries; ++e) acc[e] = 0.f;
 
-        float acc[K];
+        for (int pass0 = start; pass0 < end; pass0 += kPass) {
+          const int cnt = min(kPass, end - pass0);
+          // ---- phase A: projection, validity, compaction ------------------------------------
+          unsigned myvalid = 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = 0.f;
-
-        for (int base = start + warp * PPW; base < end; base += kWarps * PPW) {
-          const int pt = base + grp;
-          bool valid = pt < end;
-          float A0[6], A1[6];
-          float u = 0.f, v = 0.f;
+          for (int r = 0; r < kRounds; ++r) {
+            const int i = r * kThreads + threadIdx.x;
+            bool ok = false;
+            if (i < cnt) {
+              const int pt = pass0 + i;
+              float u, v, d0[6], d1[6];
+              ok = point_geometry<false>(ck, T, p3d[3 * pt], p3d[3 * pt + 1], p3d[3 * pt + 2], u, v, d0, d1);
+              if (mask != nullptr) ok = ok && (mask[pt] != 0);
+              if (ok) sUV[i] = make_float2(u, v);
+            }
+            const unsigned m = __ballot_sync(full, ok);
+            if (lane == 0) sMask[r * kWarps + warp] = m;
+            myvalid |= (ok ? 1u : 0u) << r;
+          }
+          __syncthreads();
+          if (warp == 0) {
+            const int c = (lane < kRounds * kWarps) ? __popc(sMask[lane]) : 0;
+            int incl = c;
 #pragma unroll
-          for (int i = 0; i < 6; ++i) A0[i] = A1[i] = 0.f;
-          if (valid) {
-            const float X = p3d[3 * pt], Y = p3d[3 * pt + 1], Z = p3d[3 * pt + 2];
-            const float px = fmaf(R[2], Z, fmaf(R[1], Y, R[0] * X)) + t[0];
-            const float py = fmaf(R[5], Z, fmaf(R[4], Y, R[3] * X)) + t[1];
-            const float pz = fmaf(R[8], Z, fmaf(R[7], Y, R[6] * X)) + t[2];
-            valid = pz > kZEps;                               // wrappers.py:311
-            const float z = fmaxf(pz, kZEps);
-            const float xn = px / z, yn = py / z;
-            float xd = xn, yd = yn;
-            float jxx = 1.f, jyy = 1.f, jxy = 0.f, jyx = 0.f;  // J_undistort, utils.py:72-95
-            if (p.n_cam > 6) {
-              const float r2 = xn * xn + yn * yn;
-              const float radial = k1 * r2 + k2 * r2 * r2;
-              xd = xn + xn * radial;
-              yd = yn + yn * radial;
-              valid = valid && (!limited || r2 < limit);
-              const float uvn = xn * yn;
-              const float drad = 2.f * k1 + 4.f * k2 * r2;
-              jxx += radial + xn * xn * drad;
-              jyy += radial + yn * yn * drad;
-              jxy += uvn * drad;
-              jyx += uvn * drad;
-              if (p.n_cam > 8) {
-                xd += 2.f * p1 * uvn + p2 * (r2 + 2.f * xn * xn);
-                yd += 2.f * p2 * uvn + p1 * (r2 + 2.f * yn * yn);
-                jxx += 2.f * p1 * yn + 6.f * p2 * xn;
-                jyy += 2.f * p2 * xn + 6.f * p1 * yn;
-                jxy += 2.f * p1 * xn + 2.f * p2 * yn;
-                jyx += 2.f * p2 * yn + 2.f * p1 * xn;
+            for (int d = 1; d < 32; d <<= 1) {
+              const int o = __shfl_up_sync(full, incl, d);
+              if (lane >= d) incl += o;
+            }
+            if (lane < kRounds * kWarps) sOffs[lane] = incl - c;
+            if (lane == 31) sNValid = incl;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int r = 0; r < kRounds; ++r) {
+            if ((myvalid >> r) & 1u) {
+              const int pos = sOffs[r * kWarps + warp] + __popc(sMask[r * kWarps + warp] & ((1u << lane) - 1u));
+              sList[pos] = (unsigned short)(r * kThreads + threadIdx.x);
+            }
+          }
+          __syncthreads();
+          // ---- phase B: gather + fold + reduce, LPP lanes per point ---------------------------
+          const int nv = sNValid;
+          for (int kb = warp * PPW; kb < nv; kb += kWarps * PPW) {
+            const int k = kb + grp;
+            const bool active = k < nv;
+            float sxx = 0.f, sxy = 0.f, syy = 0.f, sxr = 0.f, syr = 0.f, srr = 0.f, cq = 0.f;
+            int li = 0;
+            if (active) {
+              li = sList[k];
+              const float2 uv = sUV[li];
+              const int pt = pass0 + li;
+              const float x0f = floorf(uv.x), y0f = floorf(uv.y);
+              const int x0 = (int)x0f, y0 = (int)y0f;
+              const float ax = uv.x - x0f, ay = uv.y - y0f;
+              const float wa = (1.f - ax) * (1.f - ay), wb = ax * (1.f - ay), wc = (1.f - ax) * ay, wd = ax * ay;
+              const bool xin_ = x0 - 1 >= 0, xin1 = x0 + 1 < p.W, xin2 = x0 + 2 < p.W;
+              const bool yin_ = y0 - 1 >= 0, yin1 = y0 + 1 < p.H, yin2 = y0 + 2 < p.H;
+              const size_t row0 = (size_t)y0 * p.W;
+              for (int c4 = sub; c4 < C4; c4 += LPP) {
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4* base0 = fq4 + (row0 + x0) * C4 + c4;   // texel (y0, x0)
+                const ptrdiff_t dx = C4, dy = (ptrdiff_t)p.W * C4;
+                const float4 m0 = yin_ ? __ldg(base0 - dy) : z4;
+                const float4 m1 = (yin_ && xin1) ? __ldg(base0 - dy + dx) : z4;
+                const float4 a_ = xin_ ? __ldg(base0 - dx) : z4;
+                const float4 a0 = __ldg(base0);
+                const float4 a1 = xin1 ? __ldg(base0 + dx) : z4;
+                const float4 a2 = xin2 ? __ldg(base0 + 2 * dx) : z4;
+                const float4 b_ = (yin1 && xin_) ? __ldg(base0 + dy - dx) : z4;
+                const float4 b0 = yin1 ? __ldg(base0 + dy) : z4;
+                const float4 b1 = (yin1 && xin1) ? __ldg(base0 + dy + dx) : z4;
+                const float4 b2 = (yin1 && xin2) ? __ldg(base0 + dy + 2 * dx) : z4;
+                const float4 q0 = yin2 ? __ldg(base0 + 2 * dy) : z4;
+                const float4 q1 = (yin2 && xin1) ? __ldg(base0 + 2 * dy + dx) : z4;
+                const float4 rf = __ldg(fref4 + (size_t)pt * C4 + c4);
+                fold_channel(m0.x, m1.x, a_.x, a0.x, a1.x, a2.x, b_.x, b0.x, b1.x, b2.x, q0.x, q1.x, rf.x, wa, wb, wc,
+                             wd, sxx, sxy, syy, sxr, syr, srr);
+                fold_channel(m0.y, m1.y, a_.y, a0.y, a1.y, a2.y, b_.y, b0.y, b1.y, b2.y, q0.y, q1.y, rf.y, wa, wb, wc,
+                             wd, sxx, sxy, syy, sxr, syr, srr);
+                fold_channel(m0.z, m1.z, a_.z, a0.z, a1.z, a2.z, b_.z, b0.z, b1.z, b2.z, q0.z, q1.z, rf.z, wa, wb, wc,
+                             wd, sxx, sxy, syy, sxr, syr, srr);
+                fold_channel(m0.w, m1.w, a_.w, a0.w, a1.w, a2.w, b_.w, b0.w, b1.w, b2.w, q0.w, q1.w, rf.w, wa, wb, wc,
+                             wd, sxx, sxy, syy, sxr, syr, srr);
+              }
+              if (wq != nullptr && sub < 4) {   // confidence: 4 texels, one per lane (costs.py:27-32)
+                const int ox = sub & 1, oy = sub >> 1;
+                const bool in = (ox == 0 || xin1) && (oy == 0 || yin1);
+                const float wgt = (sub == 0) ? wa : (sub == 1) ? wb : (sub == 2) ? wc : wd;
+                cq = in ? wgt * __ldg(wq + row0 + (size_t)oy * p.W + x0 + ox) : 0.f;
               }
             }
-            u = xd * fx + cx;
-            v = yd * fy + cy;
-            valid = valid && (u >= 0.f) && (v >= 0.f) && (u <= cw - 1.f) && (v <= ch - 1.f);   // Camera.in_image
-            valid = valid && (u >= padf) && (v >= padf) && (u <= xmax) && (v <= ymax);         // mask_in_image
-            if (mask != nullptr) valid = valid && (mask[pt] != 0);
-            if (valid) {
-              // J_p2D_p3D = diag(f) * J_undist * J_project  (2x3), wrappers.py:316-326,357-362
-              const float iz = 1.f / z;
-              const float jp02 = -px / (z * z), jp12 = -py / (z * z);
-              const float m00 = fx * jxx, m01 = fx * jxy, m10 = fy * jyx, m11 = fy * jyy;
-              const float q00 = m00 * iz, q01 = m01 * iz, q02 = m00 * jp02 + m01 * jp12;
-              const float q10 = m10 * iz, q11 = m11 * iz, q12 = m10 * jp02 + m11 * jp12;
-              // times [I | -skew(p_cam)], wrappers.py:195-203
-              A0[0] = q00; A0[1] = q01; A0[2] = q02;
-              A0[3] = q02 * py - q01 * pz;
-              A0[4] = q00 * pz - q02 * px;
-              A0[5] = q01 * px - q00 * py;
-              A1[0] = q10; A1[1] = q11; A1[2] = q12;
-              A1[3] = q12 * py - q11 * pz;
-              A1[4] = q10 * pz - q12 * px;
-              A1[5] = q11 * px - q10 * py;
-            }
-          }
-          if (__ballot_sync(full, valid) == 0u) continue;
-
-          float sxx = 0.f, sxy = 0.f, syy = 0.f, sxr = 0.f, syr = 0.f, srr = 0.f, cq = 0.f;
-          if (valid) {
-            const float x0f = floorf(u), y0f = floorf(v);
-            const int x0 = (int)x0f, y0 = (int)y0f;
-            const float ax = u - x0f, ay = v - y0f;
-            const float wa = (1.f - ax) * (1.f - ay), wb = ax * (1.f - ay), wc = (1.f - ax) * ay, wd = ax * ay;
-            const bool xin_ = x0 - 1 >= 0, xin0 = true, xin1 = x0 + 1 < p.W, xin2 = x0 + 2 < p.W;
-            const bool yin_ = y0 - 1 >= 0, yin1 = y0 + 1 < p.H, yin2 = y0 + 2 < p.H;
-            (void)xin0;
-            const size_t row0 = (size_t)y0 * p.W;
-            for (int c4 = sub; c4 < C4; c4 += LPP) {
-              const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4* base0 = fq4 + (row0 + x0) * C4 + c4;   // texel (y0, x0)
-              const ptrdiff_t dx = C4, dy = (ptrdiff_t)p.W * C4;
-              const float4 m0 = yin_ ? __ldg(base0 - dy) : z4;
-              const float4 m1 = (yin_ && xin1) ? __ldg(base0 - dy + dx) : z4;
-              const float4 a_ = xin_ ? __ldg(base0 - dx) : z4;
-              const float4 a0 = __ldg(base0);
-              const float4 a1 = xin1 ? __ldg(base0 + dx) : z4;
-              const float4 a2 = xin2 ? __ldg(base0 + 2 * dx) : z4;
-              const float4 b_ = (yin1 && xin_) ? __ldg(base0 + dy - dx) : z4;
-              const float4 b0 = yin1 ? __ldg(base0 + dy) : z4;
-              const float4 b1 = (yin1 && xin1) ? __ldg(base0 + dy + dx) : z4;
-              const float4 b2 = (yin1 && xin2) ? __ldg(base0 + dy + 2 * dx) : z4;
-              const float4 q0 = yin2 ? __ldg(base0 + 2 * dy) : z4;
-              const float4 q1 = (yin2 && xin1) ? __ldg(base0 + 2 * dy + dx) : z4;
-              const float4 rf = __ldg(fref4 + (size_t)pt * C4 + c4);
-              fold_channel(m0.x, m1.x, a_.x, a0.x, a1.x, a2.x, b_.x, b0.x, b1.x, b2.x, q0.x, q1.x, rf.x, wa, wb, wc, wd,
-                           sxx, sxy, syy, sxr, syr, srr);
-              fold_channel(m0.y, m1.y, a_.y, a0.y, a1.y, a2.y, b_.y, b0.y, b1.y, b2.y, q0.y, q1.y, rf.y, wa, wb, wc, wd,
-                           sxx, sxy, syy, sxr, syr, srr);
-              fold_channel(m0.z, m1.z, a_.z, a0.z, a1.z, a2.z, b_.z, b0.z, b1.z, b2.z, q0.z, q1.z, rf.z, wa, wb, wc, wd,
-                           sxx, sxy, syy, sxr, syr, srr);
-              fold_channel(m0.w, m1.w, a_.w, a0.w, a1.w, a2.w, b_.w, b0.w, b1.w, b2.w, q0.w, q1.w, rf.w, wa, wb, wc, wd,
-                           sxx, sxy, syy, sxr, syr, srr);
-            }
-            if (wq != nullptr && sub < 4) {   // confidence: 4 texels, one per lane (costs.py:27-32)
-              const int ox = sub & 1, oy = sub >> 1;
-              const bool in = (ox == 0 || xin1) && (oy == 0 || yin1);
-              const float wgt = (sub == 0) ? wa : (sub == 1) ? wb : (sub == 2) ? wc : wd;
-              cq = in ? wgt * __ldg(wq + row0 + (size_t)oy * p.W + x0 + ox) : 0.f;
-            }
-          }
 #pragma unroll
-          for (int m = LPP >> 1; m >= 1; m >>= 1) {
-            sxx += __shfl_xor_sync(full, sxx, m);
-            sxy += __shfl_xor_sync(full, sxy, m);
-            syy += __shfl_xor_sync(full, syy, m);
-            sxr += __shfl_xor_sync(full, sxr, m);
-            syr += __shfl_xor_sync(full, syr, m);
-            srr += __shfl_xor_sync(full, srr, m);
-            cq += __shfl_xor_sync(full, cq, m);
+            for (int m = LPP >> 1; m >= 1; m >>= 1) {
+              sxx += __shfl_xor_sync(full, sxx, m);
+              sxy += __shfl_xor_sync(full, sxy, m);
+              syy += __shfl_xor_sync(full, syy, m);
+              sxr += __shfl_xor_sync(full, sxr, m);
+              syr += __shfl_xor_sync(full, syr, m);
+              srr += __shfl_xor_sync(full, srr, m);
+              cq += __shfl_xor_sync(full, cq, m);
+            }
+            if (active && sub == 0) {
+              *reinterpret_cast<float4*>(&sSums[li][0]) = make_float4(sxx, sxy, syy, sxr);
+              *reinterpret_cast<float4*>(&sSums[li][4]) = make_float4(syr, srr, cq, 0.f);
+            }
           }
-          if (valid) {
-            const float x = srr / P.a2;                              // losses.py:17-19
-            const float wl = 2.f / (x + 2.f);                        // losses.py:73
-            const float loss = 2.f * log1pf(fminf(0.5f * x, 33e37f)) * P.a2;
-            float w = wl;
-            if (wref != nullptr) w *= __ldg(wref + pt) * (wq != nullptr ? cq : 1.f);
+          __syncthreads();
+          // ---- phase C: weight, Jacobian chain, 29 contributions, one thread per point ---------
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-              float val = 0.f;
-              if (eType[k] == 0) {
-                const float a0r = pick6(A0, eR[k]), a1r = pick6(A1, eR[k]);
-                const float a0c = pick6(A0, eC[k]), a1c = pick6(A1, eC[k]);
-                const float Xv = sxx * a0c + sxy * a1c;
-                const float Yv = sxy * a0c + syy * a1c;
-                val = w * (a0r * Xv + a1r * Yv);
-              } else if (eType[k] == 1) {
-                val = w * (pick6(A0, eR[k]) * sxr + pick6(A1, eR[k]) * syr);
-              } else if (eType[k] == 2) {
-                val = loss;
-              } else if (eType[k] == 3) {
-                val = 1.f;
+          for (int r = 0; r < kRounds; ++r) {
+            if ((myvalid >> r) & 1u) {
+              const int i = r * kThreads + threadIdx.x;
+              const int pt = pass0 + i;
+              float u, v, A0[6], A1[6];
+              point_geometry<true>(ck, T, p3d[3 * pt], p3d[3 * pt + 1], p3d[3 * pt + 2], u, v, A0, A1);
+              const float4 s0 = *reinterpret_cast<const float4*>(&sSums[i][0]);
+              const float4 s1 = *reinterpret_cast<const float4*>(&sSums[i][4]);
+              const float sxx = s0.x, sxy = s0.y, syy = s0.z, sxr = s0.w, syr = s1.x, srr = s1.y, cq = s1.z;
+              const float x = srr / P.a2;                              // losses.py:17-19
+              const float wl = 2.f / (x + 2.f);                        // losses.py:73
+              const float loss = 2.f * log1pf(fminf(0.5f * x, 33e37f)) * P.a2;
+              float w = wl;
+              if (wref != nullptr) w *= __ldg(wref + pt) * (wq != nullptr ? cq : 1.f);
+              float Xv[6], Yv[6];
+#pragma unroll
+              for (int l = 0; l < 6; ++l) {
+                Xv[l] = sxx * A0[l] + sxy * A1[l];
+                Yv[l] = sxy * A0[l] + syy * A1[l];
               }
-              acc[k] += val;
+              int e = 0;
+#pragma unroll
+              for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+                for (int cc = rr; cc < 6; ++cc) {
+                  acc[e] += w * (A0[rr] * Xv[cc] + A1[rr] * Yv[cc]);
+                  ++e;
+                }
+#pragma unroll
+              for (int l = 0; l < 6; ++l) acc[21 + l] += w * (A0[l] * sxr + A1[l] * syr);
+              acc[27] += loss;
+              acc[28] += 1.f;
             }
           }
-        }  // points
+        }  // passes
 
-        // warp: fold the PPW point groups; then warp -> CTA (fixed order)
+        // thread -> warp -> CTA (fixed order)
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
+        for (int e = 0; e < kEntries; ++e) {
 #pragma unroll
-          for (int m = LPP; m < 32; m <<= 1) acc[k] += __shfl_xor_sync(full, acc[k], m);
+          for (int m = 16; m >= 1; m >>= 1) acc[e] += __shfl_xor_sync(full, acc[e], m);
         }
-        if (grp == 0) {
+        if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < K; ++k) {
-            const int e = sub + LPP * k;
-            if (e < 32) sWarp[warp][e] = (e < kEntries) ? acc[k] : 0.f;
-          }
+          for (int e = 0; e < kEntries; ++e) sWarp[warp][e] = acc[e];
+          sWarp[warp][29] = 0.f;
+          sWarp[warp][30] = 0.f;
+          sWarp[warp][31] = 0.f;
         }
         __syncthreads();
         if (warp == 0) {
