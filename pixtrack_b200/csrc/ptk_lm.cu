@@ -286,17 +286,58 @@ __device__ __forceinline__ bool point_geometry(const CamK& c, const float* __res
 constexpr int kPass = 1024;                   // points a CTA stages per pass
 constexpr int kRounds = kPass / kThreads;     // points per thread per pass
 
+// Cross-lane sum of 8 per-lane values inside groups of LPP lanes by recursive halving: each xor
+// step halves the number of values a lane is responsible for (lanes with the mask bit clear keep
+// the lower half, the others the upper half), so 8 values cost 4+2+1(+1+1) shuffles instead of
+// 8 x log2(LPP).  On return vals[0 .. n-1] (n = max(1, 8*2/LPP... see kKeep) hold the group totals
+// of value indices first .. first+n-1.
+template <int LPP>
+struct GroupReduce {
+  static constexpr int kSteps = (LPP == 32) ? 5 : (LPP == 16) ? 4 : (LPP == 8) ? 3 : 2;
+  static constexpr int kHalvings = kSteps < 3 ? kSteps : 3;
+  static constexpr int kKeep = 8 >> kHalvings;   // values left per lane
+  __device__ static __forceinline__ int run(float (&vals)[8], int sub) {
+    const unsigned full = 0xffffffffu;
+    int first = 0;
+    int n = 8;
+    int m = LPP >> 1;
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s) {
+      if (s < kHalvings) {
+        const bool up = (sub & m) != 0;
+        n >>= 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < n) {
+            const float lo = vals[i], hi = vals[i + n];
+            const float send = up ? lo : hi;
+            const float keep = up ? hi : lo;
+            vals[i] = keep + __shfl_xor_sync(full, send, m);
+          }
+        }
+        first += up ? n : 0;
+      } else {
+        vals[0] += __shfl_xor_sync(full, vals[0], m);
+      }
+      m >>= 1;
+    }
+    return first;
+  }
+};
+
 // One LM launch.  Per iteration and per pass of <= kPass points a CTA runs three phases:
 //  A  one THREAD per point: projection + validity, (u,v) to shared memory, deterministic compaction
 //     of the valid points into a list;
 //  B  WARPS walk the list: LPP lanes per point gather the 12-texel footprint (float4 per lane per
-//     texel), fold it into 6 channel sums + the confidence sample, xor-reduce them inside the lane
+//     texel), fold it into 6 channel sums + the confidence sample, reduce them inside the lane
 //     group and park the 7 totals in shared memory;
 //  C  one THREAD per point again: robust weight, Jacobian chain, and the 29 contributions
-//     (21 H, 6 g, cost, count) accumulated in that thread's registers.
-// Only phase B touches the maps, and it carries no per-point scalar math, so the issue slots go to
-// loads and the interpolation FMAs.
-template <int LPP>
+//     (21 H, 6 g, cost, count), warp-reduced and added to the warp's shared-memory accumulator.
+// Only phase B touches the maps, and it carries no per-point scalar math and no state of the other
+// phases in registers, so its issue slots go to loads and the interpolation FMAs.
+// kFast: C == 4*LPP (one float4 per lane per texel, compile-time texel stride) and pad >= 1 (all
+// 12 texels in bounds except the two that carry an exactly-zero weight, which are clamped).
+template <int LPP, bool kFast>
 __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
   constexpr int PPW = 32 / LPP;
   const int lane = threadIdx.x & 31;
@@ -318,11 +359,11 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
   __shared__ float sT[12];
   __shared__ float sCam[12];
   __shared__ float sLam[6];
+  __shared__ CamK sCK;
   __shared__ int sStop, sFailed, sAbort;
   static_assert(kRounds * kWarps <= 32, "prefix scan is done by one warp");
 
   const PtkLmProblem& p = P.p;
-  const int C4 = p.C >> 2;
   const int N = p.N;
   const int per = (N + P.G - 1) / P.G;
   const int start = min(N, rank * per);
@@ -332,10 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
 
   for (int b = group; b < p.B && group < P.n_groups; b += P.n_groups) {
     const float* p3d = p.p3d + (size_t)b * p.p3d_bstride;
-    const float4* fref4 = reinterpret_cast<const float4*>(p.f_ref + (size_t)b * p.f_ref_bstride);
     const float* wref = p.w_ref ? p.w_ref + (size_t)b * p.w_ref_bstride : nullptr;
-    const float4* fq4 = reinterpret_cast<const float4*>(p.fq + (size_t)b * p.fq_bstride);
-    const float* wq = p.wq ? p.wq + (size_t)b * p.wq_bstride : nullptr;
     const uint8_t* mask = p.mask ? p.mask + (size_t)b * p.mask_bstride : nullptr;
 
     __syncthreads();  // previous problem fully retired before smem is rewritten
@@ -350,10 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
       sFailed = 0;
     }
     __syncthreads();
-
-    const bool skipped = p.skip != nullptr && p.skip[b] != 0;
-    int it = 0;
-    if (!skipped) {
+    if (threadIdx.x == 0) {
       CamK ck;
       ck.cw = sCam[0]; ck.ch = sCam[1]; ck.fx = sCam[2]; ck.fy = sCam[3]; ck.cx = sCam[4]; ck.cy = sCam[5];
       ck.k1 = sCam[6]; ck.k2 = sCam[7]; ck.p1 = sCam[8]; ck.p2 = sCam[9];
@@ -368,14 +403,15 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
       ck.xmax = (float)(p.W - 1 - p.pad);
       ck.ymax = (float)(p.H - 1 - p.pad);
       ck.padf = (float)p.pad;
+      sCK = ck;
+    }
+    __syncthreads();
 
+    const bool skipped = p.skip != nullptr && p.skip[b] != 0;
+    int it = 0;
+    if (!skipped) {
       for (it = 0; it < p.num_iters; ++it) {
-        float T[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) T[i] = sT[i];
-        float acc[kEntries];
-#pragma unroll
-        for (int e = 0; e < kEntries; ++e) acc[e] = 0.f;
+        sWarp[warp][lane] = 0.f;   // this warp's accumulator row (only this warp touches it until the CTA sum)
 
         for (int pass0 = start; pass0 < end; pass0 += kPass) {
           const int cnt = min(kPass, end - pass0);
@@ -388,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
             if (i < cnt) {
               const int pt = pass0 + i;
               float u, v, d0[6], d1[6];
-              ok = point_geometry<false>(ck, T, p3d[3 * pt], p3d[3 * pt + 1], p3d[3 * pt + 2], u, v, d0, d1);
+              ok = point_geometry<false>(sCK, sT, p3d[3 * pt], p3d[3 * pt + 1], p3d[3 * pt + 2], u, v, d0, d1);
               if (mask != nullptr) ok = ok && (mask[pt] != 0);
               if (ok) sUV[i] = make_float2(u, v);
             }
@@ -418,123 +454,156 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
           }
           __syncthreads();
           // ---- phase B: gather + fold + reduce, LPP lanes per point ---------------------------
-          const int nv = sNValid;
-          for (int kb = warp * PPW; kb < nv; kb += kWarps * PPW) {
-            const int k = kb + grp;
-            const bool active = k < nv;
-            float sxx = 0.f, sxy = 0.f, syy = 0.f, sxr = 0.f, syr = 0.f, srr = 0.f, cq = 0.f;
-            int li = 0;
-            if (active) {
-              li = sList[k];
-              const float2 uv = sUV[li];
-              const int pt = pass0 + li;
-              const float x0f = floorf(uv.x), y0f = floorf(uv.y);
-              const int x0 = (int)x0f, y0 = (int)y0f;
-              const float ax = uv.x - x0f, ay = uv.y - y0f;
-              const float wa = (1.f - ax) * (1.f - ay), wb = ax * (1.f - ay), wc = (1.f - ax) * ay, wd = ax * ay;
-              const bool xin_ = x0 - 1 >= 0, xin1 = x0 + 1 < p.W, xin2 = x0 + 2 < p.W;
-              const bool yin_ = y0 - 1 >= 0, yin1 = y0 + 1 < p.H, yin2 = y0 + 2 < p.H;
-              const size_t row0 = (size_t)y0 * p.W;
-              for (int c4 = sub; c4 < C4; c4 += LPP) {
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4* base0 = fq4 + (row0 + x0) * C4 + c4;   // texel (y0, x0)
-                const ptrdiff_t dx = C4, dy = (ptrdiff_t)p.W * C4;
-                const float4 m0 = yin_ ? __ldg(base0 - dy) : z4;
-                const float4 m1 = (yin_ && xin1) ? __ldg(base0 - dy + dx) : z4;
-                const float4 a_ = xin_ ? __ldg(base0 - dx) : z4;
-                const float4 a0 = __ldg(base0);
-                const float4 a1 = xin1 ? __ldg(base0 + dx) : z4;
-                const float4 a2 = xin2 ? __ldg(base0 + 2 * dx) : z4;
-                const float4 b_ = (yin1 && xin_) ? __ldg(base0 + dy - dx) : z4;
-                const float4 b0 = yin1 ? __ldg(base0 + dy) : z4;
-                const float4 b1 = (yin1 && xin1) ? __ldg(base0 + dy + dx) : z4;
-                const float4 b2 = (yin1 && xin2) ? __ldg(base0 + dy + 2 * dx) : z4;
-                const float4 q0 = yin2 ? __ldg(base0 + 2 * dy) : z4;
-                const float4 q1 = (yin2 && xin1) ? __ldg(base0 + 2 * dy + dx) : z4;
-                const float4 rf = __ldg(fref4 + (size_t)pt * C4 + c4);
-                fold_channel(m0.x, m1.x, a_.x, a0.x, a1.x, a2.x, b_.x, b0.x, b1.x, b2.x, q0.x, q1.x, rf.x, wa, wb, wc,
-                             wd, sxx, sxy, syy, sxr, syr, srr);
-                fold_channel(m0.y, m1.y, a_.y, a0.y, a1.y, a2.y, b_.y, b0.y, b1.y, b2.y, q0.y, q1.y, rf.y, wa, wb, wc,
-                             wd, sxx, sxy, syy, sxr, syr, srr);
-                fold_channel(m0.z, m1.z, a_.z, a0.z, a1.z, a2.z, b_.z, b0.z, b1.z, b2.z, q0.z, q1.z, rf.z, wa, wb, wc,
-                             wd, sxx, sxy, syy, sxr, syr, srr);
-                fold_channel(m0.w, m1.w, a_.w, a0.w, a1.w, a2.w, b_.w, b0.w, b1.w, b2.w, q0.w, q1.w, rf.w, wa, wb, wc,
-                             wd, sxx, sxy, syy, sxr, syr, srr);
-              }
-              if (wq != nullptr && sub < 4) {   // confidence: 4 texels, one per lane (costs.py:27-32)
-                const int ox = sub & 1, oy = sub >> 1;
-                const bool in = (ox == 0 || xin1) && (oy == 0 || yin1);
-                const float wgt = (sub == 0) ? wa : (sub == 1) ? wb : (sub == 2) ? wc : wd;
-                cq = in ? wgt * __ldg(wq + row0 + (size_t)oy * p.W + x0 + ox) : 0.f;
-              }
-            }
+          {
+            const int nv = sNValid;
+            const int W = p.W, H = p.H;
+            const int C4 = kFast ? LPP : (p.C >> 2);
+            const float4* fq4 = reinterpret_cast<const float4*>(p.fq + (size_t)b * p.fq_bstride);
+            const float4* fref4 = reinterpret_cast<const float4*>(p.f_ref + (size_t)b * p.f_ref_bstride);
+            const float* wq = p.wq ? p.wq + (size_t)b * p.wq_bstride : nullptr;
+            for (int kb = warp * PPW; kb < nv; kb += kWarps * PPW) {
+              const int k = kb + grp;
+              const bool active = k < nv;
+              float s8[8];
 #pragma unroll
-            for (int m = LPP >> 1; m >= 1; m >>= 1) {
-              sxx += __shfl_xor_sync(full, sxx, m);
-              sxy += __shfl_xor_sync(full, sxy, m);
-              syy += __shfl_xor_sync(full, syy, m);
-              sxr += __shfl_xor_sync(full, sxr, m);
-              syr += __shfl_xor_sync(full, syr, m);
-              srr += __shfl_xor_sync(full, srr, m);
-              cq += __shfl_xor_sync(full, cq, m);
-            }
-            if (active && sub == 0) {
-              *reinterpret_cast<float4*>(&sSums[li][0]) = make_float4(sxx, sxy, syy, sxr);
-              *reinterpret_cast<float4*>(&sSums[li][4]) = make_float4(syr, srr, cq, 0.f);
+              for (int i = 0; i < 8; ++i) s8[i] = 0.f;
+              int li = 0;
+              if (active) {
+                li = sList[k];
+                const float2 uv = sUV[li];
+                const int pt = pass0 + li;
+                const float x0f = floorf(uv.x), y0f = floorf(uv.y);
+                const int x0 = (int)x0f, y0 = (int)y0f;
+                const float ax = uv.x - x0f, ay = uv.y - y0f;
+                const float wa = (1.f - ax) * (1.f - ay), wb = ax * (1.f - ay), wc = (1.f - ax) * ay, wd = ax * ay;
+                if (kFast) {
+                  // pad >= 1: x0-1, x0+1, y0-1, y0+1 are in range; x0+2 / y0+2 leave the map only when
+                  // ax / ay is exactly 0, i.e. with zero weight: clamp them onto a valid texel.
+                  constexpr int dx = LPP;   // float4 units between x-neighbours
+                  const int dy = W * LPP;
+                  const float4* r0 = fq4 + ((size_t)y0 * W + x0) * LPP + sub;
+                  const float4* rm = r0 - dy;
+                  const float4* r1 = r0 + dy;
+                  const float4* r2 = (y0 + 2 < H) ? r1 + dy : r1;
+                  const int x2 = (x0 + 2 < W) ? 2 * dx : dx;
+                  const float4 m0 = __ldg(rm), m1 = __ldg(rm + dx);
+                  const float4 a_ = __ldg(r0 - dx), a0 = __ldg(r0), a1 = __ldg(r0 + dx), a2 = __ldg(r0 + x2);
+                  const float4 b_ = __ldg(r1 - dx), b0 = __ldg(r1), b1 = __ldg(r1 + dx), b2 = __ldg(r1 + x2);
+                  const float4 q0 = __ldg(r2), q1 = __ldg(r2 + dx);
+                  const float4 rf = __ldg(fref4 + (size_t)pt * LPP + sub);
+                  fold_channel(m0.x, m1.x, a_.x, a0.x, a1.x, a2.x, b_.x, b0.x, b1.x, b2.x, q0.x, q1.x, rf.x, wa, wb, wc,
+                               wd, s8[0], s8[1], s8[2], s8[3], s8[4], s8[5]);
+                  fold_channel(m0.y, m1.y, a_.y, a0.y, a1.y, a2.y, b_.y, b0.y, b1.y, b2.y, q0.y, q1.y, rf.y, wa, wb, wc,
+                               wd, s8[0], s8[1], s8[2], s8[3], s8[4], s8[5]);
+                  fold_channel(m0.z, m1.z, a_.z, a0.z, a1.z, a2.z, b_.z, b0.z, b1.z, b2.z, q0.z, q1.z, rf.z, wa, wb, wc,
+                               wd, s8[0], s8[1], s8[2], s8[3], s8[4], s8[5]);
+                  fold_channel(m0.w, m1.w, a_.w, a0.w, a1.w, a2.w, b_.w, b0.w, b1.w, b2.w, q0.w, q1.w, rf.w, wa, wb, wc,
+                               wd, s8[0], s8[1], s8[2], s8[3], s8[4], s8[5]);
+                  if (wq != nullptr && sub < 4) {   // confidence: 4 texels, one per lane (costs.py:27-32)
+                    const float wgt = (sub == 0) ? wa : (sub == 1) ? wb : (sub == 2) ? wc : wd;
+                    s8[6] = wgt * __ldg(wq + (size_t)(y0 + (sub >> 1)) * W + x0 + (sub & 1));
+                  }
+                } else {
+                  const bool xin_ = x0 - 1 >= 0, xin1 = x0 + 1 < W, xin2 = x0 + 2 < W;
+                  const bool yin_ = y0 - 1 >= 0, yin1 = y0 + 1 < H, yin2 = y0 + 2 < H;
+                  const size_t row0 = (size_t)y0 * W;
+                  for (int c4 = sub; c4 < C4; c4 += LPP) {
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4* base0 = fq4 + (row0 + x0) * C4 + c4;   // texel (y0, x0)
+                    const ptrdiff_t dx = C4, dy = (ptrdiff_t)W * C4;
+                    const float4 m0 = yin_ ? __ldg(base0 - dy) : z4;
+                    const float4 m1 = (yin_ && xin1) ? __ldg(base0 - dy + dx) : z4;
+                    const float4 a_ = xin_ ? __ldg(base0 - dx) : z4;
+                    const float4 a0 = __ldg(base0);
+                    const float4 a1 = xin1 ? __ldg(base0 + dx) : z4;
+                    const float4 a2 = xin2 ? __ldg(base0 + 2 * dx) : z4;
+                    const float4 b_ = (yin1 && xin_) ? __ldg(base0 + dy - dx) : z4;
+                    const float4 b0 = yin1 ? __ldg(base0 + dy) : z4;
+                    const float4 b1 = (yin1 && xin1) ? __ldg(base0 + dy + dx) : z4;
+                    const float4 b2 = (yin1 && xin2) ? __ldg(base0 + dy + 2 * dx) : z4;
+                    const float4 q0 = yin2 ? __ldg(base0 + 2 * dy) : z4;
+                    const float4 q1 = (yin2 && xin1) ? __ldg(base0 + 2 * dy + dx) : z4;
+                    const float4 rf = __ldg(fref4 + (size_t)pt * C4 + c4);
+                    fold_channel(m0.x, m1.x, a_.x, a0.x, a1.x, a2.x, b_.x, b0.x, b1.x, b2.x, q0.x, q1.x, rf.x, wa, wb,
+                                 wc, wd, s8[0], s8[1], s8[2], s8[3], s8[4], s8[5]);
+                    fold_channel(m0.y, m1.y, a_.y, a0.y, a1.y, a2.y, b_.y, b0.y, b1.y, b2.y, q0.y, q1.y, rf.y, wa, wb,
+                                 wc, wd, s8[0], s8[1], s8[2], s8[3], s8[4], s8[5]);
+                    fold_channel(m0.z, m1.z, a_.z, a0.z, a1.z, a2.z, b_.z, b0.z, b1.z, b2.z, q0.z, q1.z, rf.z, wa, wb,
+                                 wc, wd, s8[0], s8[1], s8[2], s8[3], s8[4], s8[5]);
+                    fold_channel(m0.w, m1.w, a_.w, a0.w, a1.w, a2.w, b_.w, b0.w, b1.w, b2.w, q0.w, q1.w, rf.w, wa, wb,
+                                 wc, wd, s8[0], s8[1], s8[2], s8[3], s8[4], s8[5]);
+                  }
+                  if (wq != nullptr && sub < 4) {
+                    const int ox = sub & 1, oy = sub >> 1;
+                    const bool in = (ox == 0 || xin1) && (oy == 0 || yin1);
+                    const float wgt = (sub == 0) ? wa : (sub == 1) ? wb : (sub == 2) ? wc : wd;
+                    s8[6] = in ? wgt * __ldg(wq + row0 + (size_t)oy * W + x0 + ox) : 0.f;
+                  }
+                }
+              }
+              const int first = GroupReduce<LPP>::run(s8, sub);
+              constexpr int kKeep = GroupReduce<LPP>::kKeep;
+              constexpr int kDup = (LPP * kKeep) / 8;            // lanes holding the same value index
+              if (active && (sub % kDup) == 0) {
+#pragma unroll
+                for (int i = 0; i < kKeep; ++i) sSums[li][first + i] = s8[i];
+              }
             }
           }
           __syncthreads();
           // ---- phase C: weight, Jacobian chain, 29 contributions, one thread per point ---------
+          {
+            float acc[kEntries];
 #pragma unroll
-          for (int r = 0; r < kRounds; ++r) {
-            if ((myvalid >> r) & 1u) {
-              const int i = r * kThreads + threadIdx.x;
-              const int pt = pass0 + i;
-              float u, v, A0[6], A1[6];
-              point_geometry<true>(ck, T, p3d[3 * pt], p3d[3 * pt + 1], p3d[3 * pt + 2], u, v, A0, A1);
-              const float4 s0 = *reinterpret_cast<const float4*>(&sSums[i][0]);
-              const float4 s1 = *reinterpret_cast<const float4*>(&sSums[i][4]);
-              const float sxx = s0.x, sxy = s0.y, syy = s0.z, sxr = s0.w, syr = s1.x, srr = s1.y, cq = s1.z;
-              const float x = srr / P.a2;                              // losses.py:17-19
-              const float wl = 2.f / (x + 2.f);                        // losses.py:73
-              const float loss = 2.f * log1pf(fminf(0.5f * x, 33e37f)) * P.a2;
-              float w = wl;
-              if (wref != nullptr) w *= __ldg(wref + pt) * (wq != nullptr ? cq : 1.f);
-              float Xv[6], Yv[6];
+            for (int e = 0; e < kEntries; ++e) acc[e] = 0.f;
 #pragma unroll
-              for (int l = 0; l < 6; ++l) {
-                Xv[l] = sxx * A0[l] + sxy * A1[l];
-                Yv[l] = sxy * A0[l] + syy * A1[l];
-              }
-              int e = 0;
+            for (int r = 0; r < kRounds; ++r) {
+              if ((myvalid >> r) & 1u) {
+                const int i = r * kThreads + threadIdx.x;
+                const int pt = pass0 + i;
+                float u, v, A0[6], A1[6];
+                point_geometry<true>(sCK, sT, p3d[3 * pt], p3d[3 * pt + 1], p3d[3 * pt + 2], u, v, A0, A1);
+                const float4 s0 = *reinterpret_cast<const float4*>(&sSums[i][0]);
+                const float4 s1 = *reinterpret_cast<const float4*>(&sSums[i][4]);
+                const float sxx = s0.x, sxy = s0.y, syy = s0.z, sxr = s0.w, syr = s1.x, srr = s1.y, cq = s1.z;
+                const float x = srr / P.a2;                              // losses.py:17-19
+                const float wl = 2.f / (x + 2.f);                        // losses.py:73
+                const float loss = 2.f * log1pf(fminf(0.5f * x, 33e37f)) * P.a2;
+                float w = wl;
+                if (wref != nullptr) w *= __ldg(wref + pt) * (p.wq != nullptr ? cq : 1.f);
+                float Xv[6], Yv[6];
 #pragma unroll
-              for (int rr = 0; rr < 6; ++rr)
-#pragma unroll
-                for (int cc = rr; cc < 6; ++cc) {
-                  acc[e] += w * (A0[rr] * Xv[cc] + A1[rr] * Yv[cc]);
-                  ++e;
+                for (int l = 0; l < 6; ++l) {
+                  Xv[l] = sxx * A0[l] + sxy * A1[l];
+                  Yv[l] = sxy * A0[l] + syy * A1[l];
                 }
+                int e = 0;
 #pragma unroll
-              for (int l = 0; l < 6; ++l) acc[21 + l] += w * (A0[l] * sxr + A1[l] * syr);
-              acc[27] += loss;
-              acc[28] += 1.f;
+                for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+                  for (int cc = rr; cc < 6; ++cc) {
+                    acc[e] += w * (A0[rr] * Xv[cc] + A1[rr] * Yv[cc]);
+                    ++e;
+                  }
+#pragma unroll
+                for (int l = 0; l < 6; ++l) acc[21 + l] += w * (A0[l] * sxr + A1[l] * syr);
+                acc[27] += loss;
+                acc[28] += 1.f;
+              }
             }
+            // thread -> warp (fixed order), added to this warp's row
+            float mine = 0.f;
+#pragma unroll
+            for (int e = 0; e < kEntries; ++e) {
+              float v = acc[e];
+#pragma unroll
+              for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(full, v, m);
+              if (lane == e) mine = v;
+            }
+            sWarp[warp][lane] += mine;
           }
         }  // passes
 
-        // thread -> warp -> CTA (fixed order)
-#pragma unroll
-        for (int e = 0; e < kEntries; ++e) {
-#pragma unroll
-          for (int m = 16; m >= 1; m >>= 1) acc[e] += __shfl_xor_sync(full, acc[e], m);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int e = 0; e < kEntries; ++e) sWarp[warp][e] = acc[e];
-          sWarp[warp][29] = 0.f;
-          sWarp[warp][30] = 0.f;
-          sWarp[warp][31] = 0.f;
-        }
         __syncthreads();
         if (warp == 0) {
           float tot = 0.f;
@@ -677,11 +746,13 @@ extern "C" int ptk_lm_run(PtkContext* ctx, const PtkLmProblem* prob, const PtkLm
   const dim3 grid(P.G * P.n_groups), block(kThreads);
   void* args[] = {&P};
   const void* fn = nullptr;
-  switch (pick_lpp(p.C)) {
-    case 4: fn = (const void*)lm_kernel<4>; break;
-    case 8: fn = (const void*)lm_kernel<8>; break;
-    case 16: fn = (const void*)lm_kernel<16>; break;
-    default: fn = (const void*)lm_kernel<32>; break;
+  const int lpp = pick_lpp(p.C);
+  const bool fast = (p.C == 4 * lpp) && (p.pad >= 1);
+  switch (lpp) {
+    case 4: fn = fast ? (const void*)lm_kernel<4, true> : (const void*)lm_kernel<4, false>; break;
+    case 8: fn = fast ? (const void*)lm_kernel<8, true> : (const void*)lm_kernel<8, false>; break;
+    case 16: fn = fast ? (const void*)lm_kernel<16, true> : (const void*)lm_kernel<16, false>; break;
+    default: fn = fast ? (const void*)lm_kernel<32, true> : (const void*)lm_kernel<32, false>; break;
   }
   if (P.G > 1) {
     PTK_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, args, 0, (cudaStream_t)stream));
