@@ -131,6 +131,8 @@ int ptk_lm_plan(const PtkContext* ctx, const PtkLmProblem* prob, int32_t* ctas_p
  * query-side normalisation of BaseRefiner.refine_pose_using_features
  * (pixloc/pixloc/localization/base_refiner.py:92-94).
  * ---------------------------------------------------------------------- */
+/* stream-ordered device-to-device copy (tests snapshot plan-owned activations with it) */
+int ptk_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
 int ptk_chw_to_hwc(PtkContext* ctx, const float* src, float* dst, int32_t C, int32_t H, int32_t W,
                    int32_t normalize, void* stream);
 
@@ -150,6 +152,51 @@ int ptk_chw_to_hwc(PtkContext* ctx, const float* src, float* dst, int32_t C, int
 int ptk_sample_points(PtkContext* ctx, const float* map, int64_t stride_c, int64_t stride_y, int64_t stride_x,
                       int32_t C, int32_t H, int32_t W, const float* pts, int32_t N, int32_t pad, float* vals,
                       uint8_t* mask, float* grads, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Feature extractor (PixLoc UNet, VGG19 encoder) on the tcgen05 tensor cores.
+ *
+ * ptk_conv_f16: one convolution layer on channels-last fp16 activations
+ *   (3x3 pad 1 when taps == 9, 1x1 when taps == 1), fp32 accumulation, + bias,
+ *   optional ReLU, fp16 output [H][W][C_out].  An optional second input continues
+ *   the reduction over channels (the decoder's torch.cat([upsampled, skip], 1)
+ *   is never materialised); inputs larger than the output are cropped to it
+ *   (DecoderBlock.forward, pixloc/pixloc/pixlib/models/unet.py:33-44).
+ *   weights: fp16 [taps][C_out][cin0 + cin1]; bias: fp32 [C_out].
+ *   Replaces the cuDNN convolutions of unet.py:22-31,68-99.
+ *
+ * PtkExtractor: the whole UNet._forward (unet.py:158-190) with the PixLoc
+ *   configuration as a native plan for one input size, including the
+ *   pre-processing of PixTrackFeatureExtractor.__call__
+ *   (pixtrack/localization/feature_extractor.py:34-59): the image
+ *   [img_h][img_w][3] fp32 0..255 is bilinearly resized to the plan's H x W
+ *   (cv2.INTER_LINEAR semantics), scaled to 0..1 and normalised.
+ *   Outputs per level l = 0,1,2 (fine -> coarse): feat[l] fp32 [H_l][W_l][C_l]
+ *   channels-last, conf[l] fp32 [H_l][W_l] = sigmoid(-uncertainty); with
+ *   normalize != 0 the descriptors are L2-normalised over C per pixel
+ *   (base_refiner.py:92-94 fused into the head).
+ * ---------------------------------------------------------------------- */
+int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
+                 int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
+                 int32_t Cout, int32_t taps, int32_t relu, void* out, void* stream);
+
+typedef struct PtkUnetWeights {
+  const void* conv_w[20];   /* [0]: fp32 [64][28] ((ky,kx,c) taps + 1 pad); [1..19]: fp16 [9][C_out][C_in];
+                               16 encoder convs then 4 decoder convs (BatchNorm folded in)              */
+  const float* conv_b[20];  /* fp32 [C_out]                                                             */
+  const float* head_w[3];   /* fp32 [C_l + 1][C_in]: adaptation rows, last row = uncertainty head       */
+  const float* head_b[3];   /* fp32 [C_l + 1]                                                           */
+} PtkUnetWeights;
+
+typedef struct PtkExtractor PtkExtractor;
+int ptk_extractor_create(PtkContext* ctx, const PtkUnetWeights* w, int32_t H, int32_t W, PtkExtractor** out);
+void ptk_extractor_destroy(PtkExtractor* e);
+int ptk_extractor_level_shape(const PtkExtractor* e, int32_t level, int32_t* C, int32_t* H, int32_t* W);
+int ptk_extractor_run(PtkExtractor* e, const float* image, int32_t img_h, int32_t img_w, float* const* feat,
+                      float* const* conf, int32_t normalize, void* stream);
+/* test access to intermediate fp16 NHWC activations: kind 0 = encoder block output, 1 = decoder block output */
+int ptk_extractor_activation(const PtkExtractor* e, int32_t kind, int32_t index, const void** ptr, int32_t* C,
+                             int32_t* H, int32_t* W);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,11 @@ class LmProblem(C.Structure):
     ]
 
 
+class UnetWeights(C.Structure):
+    _fields_ = [('conv_w', C.c_void_p * 20), ('conv_b', C.c_void_p * 20), ('head_w', C.c_void_p * 3),
+                ('head_b', C.c_void_p * 3)]
+
+
 class LmResult(C.Structure):
     _fields_ = [('T', C.c_void_p), ('failed', C.c_void_p), ('n_iters', C.c_void_p), ('log', C.c_void_p)]
 
@@ -57,6 +62,17 @@ SYMBOLS = {
     'ptk_sample_points': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
+    'ptk_conv_f16': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_void_p, C.c_void_p]),
+    'ptk_extractor_create': (C.c_int, [C.c_void_p, C.POINTER(UnetWeights), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    'ptk_extractor_destroy': (None, [C.c_void_p]),
+    'ptk_extractor_level_shape': (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_i32p, c_i32p]),
+    'ptk_extractor_run': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    'ptk_extractor_activation': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_i32p, c_i32p,
+                                           c_i32p]),
+    'ptk_copy_d2d': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'ptk_chw_to_hwc': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p]),
 }

@@ -128,3 +128,10 @@ extern "C" int ptk_chw_to_hwc(PtkContext* ctx, const float* src, float* dst, int
   PTK_CUDA_CHECK(cudaGetLastError());
   return PTK_OK;
 }
+
+// Stream-ordered device-to-device copy (used by tests to snapshot plan-owned activations).
+extern "C" int ptk_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream) {
+  PTK_REQUIRE(dst && src && bytes >= 0, "bad argument");
+  PTK_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return PTK_OK;
+}

@@ -1,0 +1,340 @@
+// 3x3 (and 1x1) convolution on channels-last fp16 activations as an implicit GEMM on the
+// Blackwell tensor cores: tcgen05.mma (kind::f16, fp32 accumulate in TMEM) fed by TMA.
+//
+// Replaces the cuDNN convolutions under UNet._forward (reference
+// pixloc/pixloc/pixlib/models/unet.py:68-99 encoder blocks, :15-44 decoder blocks).
+//
+// GEMM view:  D[128 pixels, BLOCK_N channels] += A[128, 64] * B[BLOCK_N, 64]^T over
+//             K = taps x (C_in / 64) steps.
+//  * A: one TMA 3-D box {64 ch, 16 px wide, 8 px high} of the NHWC input at the tap-shifted
+//    position lands in shared memory as 128 rows x 128 B, 128B-swizzled -- exactly the K-major
+//    UMMA operand layout.  Out-of-bounds box elements are zero-filled by TMA, which IS the
+//    convolution's zero padding (and, with the tensor-map extents set to the cropped size, the
+//    skip-connection crop of DecoderBlock.forward, unet.py:39-43).
+//  * An optional second input tensor continues the K loop: torch.cat([upsampled, skip], 1)
+//    (unet.py:44) is never materialised.
+//  * B: weights pre-packed as [tap][C_out][C_in] fp16, box {64, BLOCK_N, 1}.
+//  * Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer
+//    (one lane), warps 2-5 = epilogue: tcgen05.ld 32 lanes x 32 columns, + bias (conv bias or
+//    folded BatchNorm), ReLU, fp16, 64 B per pixel per store.
+//  * STAGES-deep mbarrier ring between TMA and MMA; tcgen05.commit releases a stage when the
+//    MMAs that read it retire.  Several CTAs are resident per SM (smem permitting) so one CTA's
+//    epilogue overlaps another's main loop.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "ptk_common.cuh"
+
+namespace {
+
+constexpr int kTileW = 16, kTileH = 8;  // 128 output pixels per CTA
+constexpr int kKChunk = 64;             // fp16 channels per k-step = 128 B rows
+constexpr int kABytes = 128 * 128;      // one A stage
+constexpr int kConvThreads = 192;
+
+struct ConvParams {
+  int H, W;            // output (= input) spatial size
+  int Cout;
+  int cin0, cin1;      // channels taken from input 0 / input 1 (0 = absent); multiples of 64
+  int taps;            // 9 (3x3, pad 1) or 1 (1x1)
+  int relu;
+  int tiles_w;
+  const float* bias;   // [Cout] fp32
+  __half* out;         // [H][W][Cout]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  unsigned spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 22)) __trap();   // never hang the GPU on a protocol bug
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row atoms of 1024 B):
+// start>>4 | LBO(=1, ignored for swizzled K-major)<<16 | SBO(1024 B >> 4)<<32 | version 1<<46 | SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                               const __grid_constant__ CUtensorMap tmA1,
+                                                               const __grid_constant__ CUtensorMap tmW,
+                                                               const ConvParams P) {
+  constexpr int kBBytes = BLOCK_N * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;   // power of two >= 32
+  // instruction descriptor: D=F32 (bit 4), A=B=F16, K-major both, N>>3 at bit 17, M>>4 at bit 24
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int th = tile / P.tiles_w, tw = tile - th * P.tiles_w;
+  const int h0 = th * kTileH, w0 = tw * kTileW;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int chunks0 = P.cin0 / kKChunk, chunks1 = P.cin1 / kKChunk;
+  const int steps_per_tap = chunks0 + chunks1;
+  const int num_steps = P.taps * steps_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    if (chunks1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is a warp-wide instruction; this warp also frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      for (int ks = 0; ks < num_steps; ++ks) {
+        const int stage = ks % STAGES;
+        const uint32_t phase = (uint32_t)(ks / STAGES) & 1u;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        const int tap = ks / steps_per_tap, cc = ks - tap * steps_per_tap;
+        const int dy = (P.taps == 9) ? tap / 3 - 1 : 0, dx = (P.taps == 9) ? tap % 3 - 1 : 0;
+        uint8_t* sa = smem + stage * kStageBytes;
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        if (cc < chunks0) tma_load_3d(sa, &tmA0, &full_bar[stage], cc * kKChunk, w0 + dx, h0 + dy);
+        else tma_load_3d(sa, &tmA1, &full_bar[stage], (cc - chunks0) * kKChunk, w0 + dx, h0 + dy);
+        tma_load_3d(sa + kABytes, &tmW, &full_bar[stage], cc * kKChunk, n0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      for (int ks = 0; ks < num_steps; ++ks) {
+        const int stage = ks % STAGES;
+        const uint32_t phase = (uint32_t)(ks / STAGES) & 1u;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+        const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + kABytes);
+#pragma unroll
+        for (int k = 0; k < kKChunk / 16; ++k) {
+          // +32 B per K=16 step inside the 128 B swizzle row = +2 in the (addr >> 4) field
+          tc_mma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (ks | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[stage]);   // stage is free once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);         // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> bias/ReLU -> fp16 -> global ----------------
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;                  // row of the tile = pixel
+    const int h = h0 + m / kTileW, w = w0 + m % kTileW;
+    const bool inside = (h < P.H) && (w < P.W);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t v[32];
+      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (inside) {
+        uint4 pk[4];
+        uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = __uint_as_float(v[2 * j]) + __ldg(P.bias + n0 + c + 2 * j);
+          float b = __uint_as_float(v[2 * j + 1]) + __ldg(P.bias + n0 + c + 2 * j + 1);
+          if (P.relu) {
+            a = fmaxf(a, 0.f);
+            b = fmaxf(b, 0.f);
+          }
+          const __half2 hv = __floats2half2_rn(a, b);
+          pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(orow + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = pk[j];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// fp16 tensor [d2][d1][d0] (d0 innermost, contiguous), box {b0, b1, b2}, 128B swizzle, zero OOB fill
+int make_map_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                uint64_t stride2_elems, uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) {
+    ptk_set_error("cuTensorMapEncodeTiled entry point not available");
+    return PTK_ERR_CUDA;
+  }
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+  const cuuint32_t box[3] = {b0, b1, b2};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ptk_set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu %llu %llu, box %u %u %u)", (int)r,
+                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0, b1, b2);
+    return PTK_ERR_CUDA;
+  }
+  return PTK_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& P,
+                cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles_h = (P.H + kTileH - 1) / kTileH;
+  dim3 grid(P.tiles_w * tiles_h, P.Cout / BLOCK_N);
+  conv_tc_kernel<BLOCK_N, STAGES><<<grid, kConvThreads, smem, stream>>>(a0, a1, w, P);
+  PTK_CUDA_CHECK(cudaGetLastError());
+  return PTK_OK;
+}
+
+}  // namespace
+
+// Picks the N tile so that small maps still fill the machine (>= ~1 CTA per SM when possible).
+static int pick_block_n(int Cout, int m_tiles, int num_sms) {
+  int bn = Cout >= 256 ? 256 : Cout;
+  while (bn > 64 && m_tiles * (Cout / bn) < num_sms) bn >>= 1;
+  return bn;
+}
+
+extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H,
+                            int32_t W, int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights,
+                            const float* bias, int32_t Cout, int32_t taps, int32_t relu, void* out, void* stream) {
+  PTK_REQUIRE(ctx && in0 && weights && bias && out, "null argument");
+  PTK_REQUIRE(taps == 9 || taps == 1, "taps must be 9 (3x3, pad 1) or 1 (1x1)");
+  PTK_REQUIRE(cin0 > 0 && cin0 % kKChunk == 0 && cin1 >= 0 && cin1 % kKChunk == 0, "C_in must be a multiple of 64");
+  PTK_REQUIRE(Cout == 32 || Cout == 64 || Cout == 128 || Cout % 256 == 0, "C_out must be 32, 64, 128 or k*256");
+  PTK_REQUIRE((cin1 == 0) == (in1 == nullptr), "in1 and cin1 must be given together");
+  PTK_REQUIRE(H >= 1 && W >= 1 && in0_H >= H && in0_W >= W, "input 0 smaller than the output");
+  const int ctot = cin0 + cin1;
+  CUtensorMap a0, a1, wm;
+  // extents = the OUTPUT size: anything beyond (incl. a larger skip tensor's extra rows/cols) reads as zero
+  int rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kTileW, kTileH);
+  if (rc != PTK_OK) return rc;
+  if (cin1 > 0) {
+    PTK_REQUIRE(in1_H >= H && in1_W >= W, "input 1 smaller than the output");
+    rc = make_map_3d(&a1, in1, cin1, W, H, cin1, (uint64_t)in1_W * cin1, kKChunk, kTileW, kTileH);
+    if (rc != PTK_OK) return rc;
+  } else {
+    a1 = a0;
+  }
+  ConvParams P;
+  P.H = H; P.W = W; P.Cout = Cout; P.cin0 = cin0; P.cin1 = cin1; P.taps = taps; P.relu = relu;
+  P.tiles_w = (W + kTileW - 1) / kTileW;
+  P.bias = bias;
+  P.out = (__half*)out;
+  const int m_tiles = P.tiles_w * ((H + kTileH - 1) / kTileH);
+  const int bn = pick_block_n(Cout, m_tiles, ctx->num_sms);
+  rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, bn, 1);
+  if (rc != PTK_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (bn) {
+    case 32: return launch_conv<32, 4>(a0, a1, wm, P, s);
+    case 64: return launch_conv<64, 4>(a0, a1, wm, P, s);
+    case 128: return launch_conv<128, 3>(a0, a1, wm, P, s);
+    default: return launch_conv<256, 3>(a0, a1, wm, P, s);
+  }
+}

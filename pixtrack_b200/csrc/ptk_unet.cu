@@ -1,0 +1,398 @@
+// The PixLoc UNet feature extractor as a native plan: small CUDA-core kernels around the
+// tcgen05 convolution (ptk_conv.cu), and the layer schedule.
+//
+// Replaces UNet._forward (reference pixloc/pixloc/pixlib/models/unet.py:158-190) with the PixLoc
+// configuration (pixlib/configs/train_pixloc_megadepth.yaml:22-31: vgg19 encoder, decoder
+// [64,64,64,32], heads at scales 0/2/4 with 32/128/128 channels + uncertainty), and the
+// pre-processing of PixTrackFeatureExtractor.__call__ (pixtrack/localization/feature_extractor.py:34-59).
+// Activations are channels-last fp16 (fp32 accumulation everywhere); outputs are fp32.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "ptk_common.cuh"
+
+extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H,
+                            int32_t W, int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights,
+                            const float* bias, int32_t Cout, int32_t taps, int32_t relu, void* out, void* stream);
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// E0: resize (cv2.INTER_LINEAR semantics for float images: pixel centres aligned, source index
+// clamped, horizontal pass then vertical pass) + /255 + ImageNet mean/std (unet.py:159-161).
+// in: [Hi][Wi][3] fp32 0..255   out: [Ho][Wo][3] fp32 normalised
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_image_kernel(const float* __restrict__ in, int Hi, int Wi, float* __restrict__ out, int Ho, int Wo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Ho * Wo) return;
+  const int y = idx / Wo, x = idx - y * Wo;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  float v[3];
+  if (Hi == Ho && Wi == Wo) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = in[(size_t)idx * 3 + c];
+  } else {
+    const float sx = (float)Wi / (float)Wo, sy = (float)Hi / (float)Ho;
+    float fx = ((float)x + 0.5f) * sx - 0.5f, fy = ((float)y + 0.5f) * sy - 0.5f;
+    int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
+    fx -= (float)x0;
+    fy -= (float)y0;
+    if (x0 < 0) { x0 = 0; fx = 0.f; }
+    if (x0 >= Wi - 1) { x0 = Wi - 1; fx = 0.f; }
+    if (y0 < 0) { y0 = 0; fy = 0.f; }
+    if (y0 >= Hi - 1) { y0 = Hi - 1; fy = 0.f; }
+    const int x1 = min(x0 + 1, Wi - 1), y1 = min(y0 + 1, Hi - 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float a = in[((size_t)y0 * Wi + x0) * 3 + c] * (1.f - fx) + in[((size_t)y0 * Wi + x1) * 3 + c] * fx;
+      const float b = in[((size_t)y1 * Wi + x0) * 3 + c] * (1.f - fx) + in[((size_t)y1 * Wi + x1) * 3 + c] * fx;
+      v[c] = a * (1.f - fy) + b * fy;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[(size_t)idx * 3 + c] = (v[c] / 255.f - mean[c]) / stdv[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// First VGG layer: 3 -> 64 channels, 3x3, pad 1, bias, ReLU.  K = 27 is too thin for the tensor
+// cores; fp32 CUDA-core direct convolution, one pixel x 64 channels per thread.
+// w: [64][28] fp32 (27 taps ordered (ky, kx, c) + 1 pad), out: fp16 [H][W][64]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1_direct_kernel(const float* __restrict__ img, int H, int W,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           __half* __restrict__ out) {
+  __shared__ __align__(16) float sw[64 * 28];
+  __shared__ float sb[64];
+  __shared__ float tile[18][18 * 3];
+  for (int i = threadIdx.x; i < 64 * 28; i += 256) sw[i] = w[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < 18 * 18 * 3; i += 256) {
+    const int ty = i / 54, r = i - ty * 54;
+    const int tx = r / 3, c = r - tx * 3;
+    const int gy = y0 + ty - 1, gx = x0 + tx - 1;
+    tile[ty][r] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[((size_t)gy * W + gx) * 3 + c] : 0.f;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+  const int x = x0 + lx, y = y0 + ly;
+  if (x >= W || y >= H) return;
+  float in[28];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int j = 0; j < 9; ++j) in[ky * 9 + j] = tile[ly + ky][lx * 3 + j];
+  in[27] = 0.f;
+  __half* o = out + ((size_t)y * W + x) * 64;
+#pragma unroll 1
+  for (int c8 = 0; c8 < 64; c8 += 8) {
+    uint4 pk;
+    uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      float acc[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float4* wr = reinterpret_cast<const float4*>(sw + (c8 + j + e) * 28);
+        float a = sb[c8 + j + e];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          const float4 wv = wr[q];
+          a = fmaf(in[4 * q], wv.x, a);
+          a = fmaf(in[4 * q + 1], wv.y, a);
+          a = fmaf(in[4 * q + 2], wv.z, a);
+          a = fmaf(in[4 * q + 3], wv.w, a);
+        }
+        acc[e] = fmaxf(a, 0.f);
+      }
+      const __half2 hv = __floats2half2_rn(acc[0], acc[1]);
+      pw[j >> 1] = *reinterpret_cast<const uint32_t*>(&hv);
+    }
+    *reinterpret_cast<uint4*>(o + c8) = pk;
+  }
+}
+
+// 2x2 / stride 2 max pool (floor mode), NHWC fp16, 8 channels per thread.
+__global__ void maxpool2_kernel(const __half* __restrict__ in, int H, int W, int C, __half* __restrict__ out) {
+  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Ho * Wo * C8) return;
+  const int c8 = (int)(idx % C8);
+  const long long p = idx / C8;
+  const int x = (int)(p % Wo), y = (int)(p / Wo);
+  const uint4* src = reinterpret_cast<const uint4*>(in);
+  const size_t base = ((size_t)(2 * y) * W + 2 * x) * C8 + c8;
+  uint4 a = src[base], b = src[base + C8], c = src[base + (size_t)W * C8], d = src[base + (size_t)W * C8 + C8];
+  __half2* ha = reinterpret_cast<__half2*>(&a);
+  const __half2* hb = reinterpret_cast<const __half2*>(&b);
+  const __half2* hc = reinterpret_cast<const __half2*>(&c);
+  const __half2* hd = reinterpret_cast<const __half2*>(&d);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ha[i] = __hmax2(__hmax2(ha[i], hb[i]), __hmax2(hc[i], hd[i]));
+  reinterpret_cast<uint4*>(out)[idx] = a;
+}
+
+// x2 bilinear upsample, align_corners=False (nn.Upsample in DecoderBlock, unet.py:19-20), NHWC fp16.
+__global__ void upsample2_kernel(const __half* __restrict__ in, int H, int W, int C, __half* __restrict__ out) {
+  const int Ho = 2 * H, Wo = 2 * W, C8 = C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Ho * Wo * C8) return;
+  const int c8 = (int)(idx % C8);
+  const long long p = idx / C8;
+  const int x = (int)(p % Wo), y = (int)(p / Wo);
+  const float sxf = fmaxf(((float)x + 0.5f) * 0.5f - 0.5f, 0.f), syf = fmaxf(((float)y + 0.5f) * 0.5f - 0.5f, 0.f);
+  const int x0 = (int)sxf, y0 = (int)syf;
+  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  const float lx = sxf - (float)x0, ly = syf - (float)y0;
+  const uint4* src = reinterpret_cast<const uint4*>(in);
+  const uint4 v00 = src[((size_t)y0 * W + x0) * C8 + c8], v01 = src[((size_t)y0 * W + x1) * C8 + c8];
+  const uint4 v10 = src[((size_t)y1 * W + x0) * C8 + c8], v11 = src[((size_t)y1 * W + x1) * C8 + c8];
+  const __half2* a = reinterpret_cast<const __half2*>(&v00);
+  const __half2* b = reinterpret_cast<const __half2*>(&v01);
+  const __half2* c = reinterpret_cast<const __half2*>(&v10);
+  const __half2* d = reinterpret_cast<const __half2*>(&v11);
+  uint4 o;
+  __half2* ho = reinterpret_cast<__half2*>(&o);
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __half22float2(a[i]), fb = __half22float2(b[i]), fc = __half22float2(c[i]), fd = __half22float2(d[i]);
+    ho[i] = __floats2half2_rn(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
+                              w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+  }
+  reinterpret_cast<uint4*>(out)[idx] = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Heads (unet.py:47-50,177-188): 1x1 adaptation conv C_in -> C_out plus the 1x1 uncertainty conv
+// (-> 1 channel), confidence = sigmoid(-u); optional per-pixel L2 normalisation of the descriptor
+// (base_refiner.py:92-94) fused in.  fp16 in, fp32 out.
+// w: [C_out + 1][C_in] fp32 (row C_out = uncertainty), b: [C_out + 1].
+// 32 pixels x 8 output-slices per 256-thread block, K in chunks of 64 through shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHeadMaxOut = 136;   // >= C_out + 1, multiple of 8
+__global__ void __launch_bounds__(256) head_kernel(const __half* __restrict__ x, long long npix, int Cin, int Cout,
+                                                   const float* __restrict__ w, const float* __restrict__ b,
+                                                   float* __restrict__ feat, float* __restrict__ conf, int normalize) {
+  __shared__ float sx[32][65];
+  __shared__ float swt[kHeadMaxOut][65];
+  const int j = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int nout = Cout + 1;
+  constexpr int kAcc = kHeadMaxOut / 8;
+  float acc[kAcc];
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < Cin; k0 += 64) {
+    const int kc = min(64, Cin - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int pp = i >> 6, kk = i & 63;
+      sx[pp][kk] = (kk < kc && p0 + pp < npix) ? __half2float(x[(p0 + pp) * Cin + k0 + kk]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < nout * 64; i += 256) {
+      const int co = i >> 6, kk = i & 63;
+      swt[co][kk] = (kk < kc) ? w[(size_t)co * Cin + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kAcc; ++i) {
+      const int co = j + 8 * i;
+      if (co < nout) {
+        float a = acc[i];
+#pragma unroll 16
+        for (int kk = 0; kk < kc; ++kk) a = fmaf(sx[pl][kk], swt[co][kk], a);
+        acc[i] = a;
+      }
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) {
+    const int co = j + 8 * i;
+    if (co < nout) {
+      acc[i] += b[co];
+      if (co < Cout) ss = fmaf(acc[i], acc[i], ss);
+    }
+  }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+  const float inv = normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+  const long long p = p0 + pl;
+  if (p >= npix) return;
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) {
+    const int co = j + 8 * i;
+    if (co < Cout) feat[p * Cout + co] = acc[i] * inv;
+    else if (co == Cout) conf[p] = 1.f / (1.f + expf(acc[i]));   // sigmoid(-u)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layer schedule
+// ---------------------------------------------------------------------------------------------
+constexpr int kNumConv = 20;   // 16 encoder + 4 decoder 3x3 convolutions
+const int kEncBlocks[5][4] = {{64, 64, 0, 0}, {128, 128, 0, 0}, {256, 256, 256, 256}, {512, 512, 512, 512}, {512, 512, 512, 512}};
+const int kEncCount[5] = {2, 2, 4, 4, 4};
+const int kDec[4] = {64, 64, 64, 32};
+const int kHeadScale[3] = {0, 2, 4};
+const int kHeadDim[3] = {32, 128, 128};
+
+}  // namespace
+
+struct PtkExtractor {
+  PtkContext* ctx;
+  int H, W;                       // network input size
+  PtkUnetWeights wts;
+  float* img;                     // [H][W][3] normalised fp32
+  __half* enc[5][4];              // conv outputs per block (the last one of each block is the skip feature)
+  __half* pool[4];                // pooled input of blocks 1..4
+  __half* up[4];                  // upsampled decoder inputs
+  __half* dec[4];
+  int eh[5], ew[5];               // spatial size of encoder block b
+  int dh[4], dw[4];               // spatial size of decoder block i output
+  void* arena;
+};
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int ptk_extractor_create(PtkContext* ctx, const PtkUnetWeights* w, int32_t H, int32_t W,
+                                    PtkExtractor** out) {
+  PTK_REQUIRE(ctx && w && out, "null argument");
+  PTK_REQUIRE(H >= 16 && W >= 16, "image must be at least 16x16");
+  PtkExtractor* e = (PtkExtractor*)calloc(1, sizeof(PtkExtractor));
+  e->ctx = ctx; e->H = H; e->W = W; e->wts = *w;
+  e->eh[0] = H; e->ew[0] = W;
+  for (int b = 1; b < 5; ++b) { e->eh[b] = e->eh[b - 1] / 2; e->ew[b] = e->ew[b - 1] / 2; }
+  for (int i = 0; i < 4; ++i) { e->dh[i] = 2 * (i == 0 ? e->eh[4] : e->dh[i - 1]); e->dw[i] = 2 * (i == 0 ? e->ew[4] : e->dw[i - 1]); }
+  // one arena for all activations
+  size_t total = align_up((size_t)H * W * 3 * 4);
+  for (int b = 0; b < 5; ++b)
+    for (int i = 0; i < kEncCount[b]; ++i) total += align_up((size_t)e->eh[b] * e->ew[b] * kEncBlocks[b][i] * 2);
+  for (int b = 1; b < 5; ++b) total += align_up((size_t)e->eh[b] * e->ew[b] * kEncBlocks[b - 1][kEncCount[b - 1] - 1] * 2);
+  for (int i = 0; i < 4; ++i) {
+    const int cprev = (i == 0) ? 512 : kDec[i - 1];
+    total += align_up((size_t)e->dh[i] * e->dw[i] * cprev * 2) + align_up((size_t)e->dh[i] * e->dw[i] * kDec[i] * 2);
+  }
+  cudaError_t err = cudaMalloc(&e->arena, total);
+  if (err != cudaSuccess) {
+    ptk_set_error("extractor arena of %zu bytes: %s", total, cudaGetErrorString(err));
+    free(e);
+    return PTK_ERR_CUDA;
+  }
+  uint8_t* p = (uint8_t*)e->arena;
+  auto take = [&](size_t bytes) { void* r = p; p += align_up(bytes); return r; };
+  e->img = (float*)take((size_t)H * W * 3 * 4);
+  for (int b = 0; b < 5; ++b)
+    for (int i = 0; i < kEncCount[b]; ++i) e->enc[b][i] = (__half*)take((size_t)e->eh[b] * e->ew[b] * kEncBlocks[b][i] * 2);
+  for (int b = 1; b < 5; ++b)
+    e->pool[b - 1] = (__half*)take((size_t)e->eh[b] * e->ew[b] * kEncBlocks[b - 1][kEncCount[b - 1] - 1] * 2);
+  for (int i = 0; i < 4; ++i) {
+    const int cprev = (i == 0) ? 512 : kDec[i - 1];
+    e->up[i] = (__half*)take((size_t)e->dh[i] * e->dw[i] * cprev * 2);
+    e->dec[i] = (__half*)take((size_t)e->dh[i] * e->dw[i] * kDec[i] * 2);
+  }
+  *out = e;
+  return PTK_OK;
+}
+
+extern "C" void ptk_extractor_destroy(PtkExtractor* e) {
+  if (e == nullptr) return;
+  if (e->arena) cudaFree(e->arena);
+  free(e);
+}
+
+extern "C" int ptk_extractor_level_shape(const PtkExtractor* e, int32_t level, int32_t* C, int32_t* H, int32_t* W) {
+  PTK_REQUIRE(e && level >= 0 && level < 3 && C && H && W, "bad argument");
+  *C = kHeadDim[level];
+  if (level == 0) { *H = e->dh[3]; *W = e->dw[3]; }
+  else if (level == 1) { *H = e->dh[1]; *W = e->dw[1]; }
+  else { *H = e->eh[4]; *W = e->ew[4]; }
+  return PTK_OK;
+}
+
+// Debug / test access to intermediate activations (fp16 NHWC): kind 0 = encoder block output b,
+// kind 1 = decoder block output i.
+extern "C" int ptk_extractor_activation(const PtkExtractor* e, int32_t kind, int32_t index, const void** ptr, int32_t* C,
+                                        int32_t* H, int32_t* W) {
+  PTK_REQUIRE(e && ptr && C && H && W, "null argument");
+  if (kind == 0 && index >= 0 && index < 5) {
+    *ptr = e->enc[index][kEncCount[index] - 1]; *C = kEncBlocks[index][kEncCount[index] - 1]; *H = e->eh[index]; *W = e->ew[index];
+    return PTK_OK;
+  }
+  if (kind == 1 && index >= 0 && index < 4) {
+    *ptr = e->dec[index]; *C = kDec[index]; *H = e->dh[index]; *W = e->dw[index];
+    return PTK_OK;
+  }
+  ptk_set_error("no such activation (%d, %d)", kind, index);
+  return PTK_ERR_INVALID;
+}
+
+extern "C" int ptk_extractor_run(PtkExtractor* e, const float* image, int32_t img_h, int32_t img_w, float* const* feat,
+                                 float* const* conf, int32_t normalize, void* stream) {
+  PTK_REQUIRE(e && image && feat && conf, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int H = e->H, W = e->W;
+  prep_image_kernel<<<(H * W + 255) / 256, 256, 0, s>>>(image, img_h, img_w, e->img, H, W);
+  // ---- encoder (unet.py:163-167) ----
+  int li = 0;
+  conv1_direct_kernel<<<dim3((W + 15) / 16, (H + 15) / 16), 256, 0, s>>>(e->img, H, W, (const float*)e->wts.conv_w[0],
+                                                                       e->wts.conv_b[0], e->enc[0][0]);
+  PTK_CUDA_CHECK(cudaGetLastError());
+  li = 1;
+  for (int b = 0; b < 5; ++b) {
+    const int h = e->eh[b], w = e->ew[b];
+    const __half* cur;
+    int ccur;
+    if (b == 0) {
+      cur = e->enc[0][0];
+      ccur = 64;
+    } else {
+      const int cprev = kEncBlocks[b - 1][kEncCount[b - 1] - 1];
+      const long long n = (long long)h * w * (cprev / 8);
+      maxpool2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(e->enc[b - 1][kEncCount[b - 1] - 1], e->eh[b - 1],
+                                                                  e->ew[b - 1], cprev, e->pool[b - 1]);
+      cur = e->pool[b - 1];
+      ccur = cprev;
+    }
+    for (int i = (b == 0 ? 1 : 0); i < kEncCount[b]; ++i) {
+      const int rc = ptk_conv_f16(e->ctx, cur, ccur, nullptr, 0, h, w, h, w, 0, 0, e->wts.conv_w[li], e->wts.conv_b[li],
+                                  kEncBlocks[b][i], 9, 1, e->enc[b][i], stream);
+      if (rc != PTK_OK) return rc;
+      cur = e->enc[b][i];
+      ccur = kEncBlocks[b][i];
+      ++li;
+    }
+  }
+  // ---- decoder (unet.py:169-173; DecoderBlock.forward :33-44) ----
+  const __half* prev = e->enc[4][3];
+  int cprev = 512, ph = e->eh[4], pw = e->ew[4];
+  for (int i = 0; i < 4; ++i) {
+    const int sb = 3 - i;   // skip feature comes from encoder block 3, 2, 1, 0
+    const int cskip = kEncBlocks[sb][kEncCount[sb] - 1];
+    const long long n = (long long)e->dh[i] * e->dw[i] * (cprev / 8);
+    upsample2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(prev, ph, pw, cprev, e->up[i]);
+    const int rc = ptk_conv_f16(e->ctx, e->up[i], cprev, e->enc[sb][kEncCount[sb] - 1], cskip, e->dh[i], e->dw[i],
+                                e->dh[i], e->dw[i], e->eh[sb], e->ew[sb], e->wts.conv_w[li], e->wts.conv_b[li], kDec[i], 9,
+                                1, e->dec[i], stream);
+    if (rc != PTK_OK) return rc;
+    prev = e->dec[i];
+    cprev = kDec[i];
+    ph = e->dh[i];
+    pw = e->dw[i];
+    ++li;
+  }
+  // ---- heads (unet.py:175-188): pre_features fine -> coarse = dec[3], dec[2], dec[1], dec[0], enc[4] ----
+  for (int l = 0; l < 3; ++l) {
+    const __half* src;
+    int cin, h, w;
+    if (kHeadScale[l] == 4) { src = e->enc[4][3]; cin = 512; h = e->eh[4]; w = e->ew[4]; }
+    else { const int di = 3 - kHeadScale[l]; src = e->dec[di]; cin = kDec[di]; h = e->dh[di]; w = e->dw[di]; }
+    const long long npix = (long long)h * w;
+    head_kernel<<<(unsigned)((npix + 31) / 32), 256, 0, s>>>(src, npix, cin, kHeadDim[l], e->wts.head_w[l],
+                                                           e->wts.head_b[l], feat[l], conf[l], normalize);
+  }
+  PTK_CUDA_CHECK(cudaGetLastError());
+  return PTK_OK;
+}

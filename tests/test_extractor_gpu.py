@@ -1,0 +1,143 @@
+"""GPU: tcgen05 convolution and the native UNet plan against PyTorch fp32 / the oracle / the
+reference goldens.  The tensor-core path multiplies fp16 operands (fp32 accumulate), so the
+comparison with the fp32 reference uses relative-to-scale tolerances; the isolated convolution is
+checked tightly against an fp32 convolution of the SAME fp16-rounded operands."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as tF
+
+import cases
+from pixtrack_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+D = 'cuda:0'
+
+
+def _conv_ref(x_hwc, w, b, relu, x1=None, hw=None):
+    xs = [x_hwc.float().permute(2, 0, 1)[None]]
+    H, W = hw if hw else x_hwc.shape[:2]
+    xs[0] = xs[0][:, :, :H, :W]
+    if x1 is not None:
+        xs.append(x1.float().permute(2, 0, 1)[None][:, :, :H, :W])
+    y = tF.conv2d(torch.cat(xs, 1), w.float(), b, padding=w.shape[-1] // 2)
+    return (tF.relu(y) if relu else y)[0].permute(1, 2, 0)
+
+
+@pytest.mark.parametrize('cin,cout,H,W', [(64, 64, 24, 40), (128, 256, 17, 33), (64, 32, 8, 16), (256, 512, 9, 20),
+                                          (512, 128, 40, 70), (64, 64, 130, 250)])
+def test_conv3x3_against_fp32_conv_of_same_operands(cin, cout, H, W):
+    from pixtrack_b200.extractor import conv_f16, pack_conv3x3
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(H, W, cin, generator=g).half().to(D)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).half().to(D)
+    b = torch.randn(cout, generator=g).to(D)
+    for relu in (True, False):
+        y = conv_f16(x, pack_conv3x3(w), b, relu=relu)
+        torch.cuda.synchronize()
+        ref = _conv_ref(x, w, b, relu)
+        err = (y.float() - ref).abs().max().item()
+        assert err < 4e-3 * max(1.0, ref.abs().max().item()), err      # fp16 output rounding only
+
+
+def test_conv_two_inputs_with_cropped_skip_and_1x1():
+    from pixtrack_b200.extractor import conv_f16, pack_conv3x3
+    g = torch.Generator().manual_seed(3)
+    up = torch.randn(18, 36, 64, generator=g).half().to(D)
+    skip = torch.randn(19, 37, 128, generator=g).half().to(D)          # odd-sized skip: cropped to 18x36
+    w = (torch.randn(64, 192, 3, 3, generator=g) / 40).half().to(D)
+    b = torch.randn(64, generator=g).to(D)
+    y = conv_f16(up, pack_conv3x3(w), b, relu=True, x1=skip, out_hw=(18, 36))
+    ref = _conv_ref(up, w, b, True, x1=skip, hw=(18, 36))
+    assert (y.float() - ref).abs().max().item() < 4e-3 * ref.abs().max().item()
+    w1 = (torch.randn(128, 64, 1, 1, generator=g) / 8).half().to(D)
+    b1 = torch.randn(128, generator=g).to(D)
+    y1 = conv_f16(up, w1.reshape(1, 128, 64).contiguous(), b1, relu=False, taps=1)
+    ref1 = _conv_ref(up, w1, b1, False)
+    assert (y1.float() - ref1).abs().max().item() < 4e-3 * ref1.abs().max().item()
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.parametrize('tag,hw', [('a', (64, 96)), ('b', (80, 112))])
+def test_unet_against_reference_golden(tag, hw):
+    from pixtrack_b200.extractor import B200FeatureExtractor
+    g = cases.gold('unet')
+    ext = B200FeatureExtractor(syn.unet_weights(0), D, dict(resize=None))
+    img = syn.textured_image(hw[0], hw[1], seed=3).to(D)
+    feats, confs, scales = ext.extract_device(img)
+    torch.cuda.synchronize()
+    for lv in range(3):
+        f = feats[lv].permute(2, 0, 1).cpu()
+        assert _rel(f, torch.from_numpy(g[f'{tag}_f{lv}'])) < 2e-2, lv
+        assert float((confs[lv].cpu() - torch.from_numpy(g[f'{tag}_c{lv}'])[0]).abs().max()) < 1e-2, lv
+
+
+def test_unet_layer_by_layer_against_oracle():
+    """Encoder block outputs and decoder block outputs vs the oracle's fp32 activations (odd sizes:
+    exercises floor pooling and the skip crop)."""
+    from oracle import unet as ounet
+    from pixtrack_b200.extractor import B200FeatureExtractor
+    sd = syn.unet_weights(0)
+    H, W = 90, 150
+    ext = B200FeatureExtractor(sd, D, dict(resize=None))
+    img = syn.textured_image(H, W, seed=5)
+    ext.extract_device(img.to(D))
+    torch.cuda.synchronize()
+    x = (img.permute(2, 0, 1) / 255.)[None]
+    mean = x.new_tensor(ounet.IMAGENET_MEAN)[:, None, None]
+    std = x.new_tensor(ounet.IMAGENET_STD)[:, None, None]
+    skips = ounet.encoder(sd, (x - mean) / std)
+    for b in range(5):
+        a = ext.activation(H, W, 0, b).float().permute(2, 0, 1).cpu()
+        assert a.shape == skips[b][0].shape
+        assert _rel(a, skips[b][0]) < 2e-2, f'encoder block {b}'
+    pre = skips[-1]
+    for i, skip in enumerate(skips[:-1][::-1]):
+        pre = ounet.decoder_block(sd, i, pre, skip)
+        a = ext.activation(H, W, 1, i).float().permute(2, 0, 1).cpu()
+        assert a.shape == pre[0].shape
+        assert _rel(a, pre[0]) < 2e-2, f'decoder block {i}'
+
+
+def test_public_call_with_resize_matches_reference_golden():
+    from pixtrack_b200.extractor import B200FeatureExtractor
+    g = cases.gold('unet')
+    ext = B200FeatureExtractor(syn.unet_weights(0), D, dict(resize=128))
+    feats, scales, confs = ext(syn.textured_image(150, 200, seed=4).numpy(), 1)
+    np.testing.assert_allclose(np.array(scales), g['x_scales'])
+    assert ext.model.scales == [1, 4, 16]
+    for lv in range(3):
+        assert tuple(feats[lv].shape) == g[f'x_f{lv}'].shape and tuple(confs[lv].shape) == g[f'x_c{lv}'].shape
+        assert _rel(feats[lv].cpu(), torch.from_numpy(g[f'x_f{lv}'])) < 2e-2
+        assert float((confs[lv].cpu() - torch.from_numpy(g[f'x_c{lv}'])).abs().max()) < 1e-2
+
+
+def test_fused_normalisation_and_channels_last_views():
+    from pixtrack_b200.extractor import B200FeatureExtractor
+    from pixtrack_b200.optimizer import query_map_to_hwc
+    ext = B200FeatureExtractor(syn.unet_weights(0), D, dict(resize=None))
+    img = syn.textured_image(64, 96, seed=3).to(D)
+    raw, _, _ = ext.extract_device(img, normalize=False)
+    nrm, _, _ = ext.extract_device(img, normalize=True)
+    for r, n in zip(raw, nrm):
+        np.testing.assert_allclose(n.cpu().numpy(), tF.normalize(r, dim=2).cpu().numpy(), rtol=1e-5, atol=1e-6)
+    chw = raw[1].permute(2, 0, 1)
+    assert query_map_to_hwc(chw).data_ptr() == raw[1].data_ptr()      # zero-copy hand-off to the LM kernel
+
+
+def test_full_size_plan_runs_and_is_deterministic():
+    from pixtrack_b200.extractor import B200FeatureExtractor
+    ext = B200FeatureExtractor(syn.unet_weights(0), D)
+    img = syn.textured_image(1080, 1920, seed=6).to(D)      # resized to 576 x 1024 on the device
+    a, ca, sc = ext.extract_device(img, normalize=True)
+    b, cb, _ = ext.extract_device(img, normalize=True)
+    torch.cuda.synchronize()
+    assert [tuple(t.shape) for t in a] == [(576, 1024, 32), (144, 256, 128), (36, 64, 128)]
+    np.testing.assert_allclose(np.array(sc), [[1024 / 1920 / s] * 2 for s in (1, 4, 16)])
+    for x, y in zip(a + ca, b + cb):
+        assert torch.equal(x, y) and bool(torch.isfinite(x).all())
+    assert abs(float(a[1].pow(2).sum(-1).mean()) - 1.0) < 1e-4
