@@ -192,8 +192,16 @@ typedef struct PtkExtractor PtkExtractor;
 int ptk_extractor_create(PtkContext* ctx, const PtkUnetWeights* w, int32_t H, int32_t W, PtkExtractor** out);
 void ptk_extractor_destroy(PtkExtractor* e);
 int ptk_extractor_level_shape(const PtkExtractor* e, int32_t level, int32_t* C, int32_t* H, int32_t* W);
-int ptk_extractor_run(PtkExtractor* e, const float* image, int32_t img_h, int32_t img_w, float* const* feat,
-                      float* const* conf, int32_t normalize, void* stream);
+/* image: [img_h][img_w][3] RGB, img_dtype 0 = fp32 in 0..255, 1 = uint8 (converted to float before the
+ * bilinear resize; the reference's cv2 path for uint8 rounds the resized image back to uint8 first). */
+int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
+                      float* const* feat, float* const* conf, int32_t normalize, void* stream);
+/* Benchmark helper (SYNCHRONISES): runs the plan once with a CUDA event after every launch.  ms[i] = device
+ * time of launch i; kinds[i]: 0 prep, 1 first conv (direct), 2 max-pool, 3 tensor-core conv, 4 upsample,
+ * 5 head; flops[i] = 2 x multiply-adds of launch i. */
+int ptk_extractor_profile(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
+                          float* const* feat, float* const* conf, int32_t normalize, void* stream, int32_t max_n,
+                          float* ms, int32_t* kinds, double* flops, int32_t* n_out);
 /* test access to intermediate fp16 NHWC activations: kind 0 = encoder block output, 1 = decoder block output */
 int ptk_extractor_activation(const PtkExtractor* e, int32_t kind, int32_t index, const void** ptr, int32_t* C,
                              int32_t* H, int32_t* W);

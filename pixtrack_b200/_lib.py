@@ -68,8 +68,11 @@ SYMBOLS = {
     'ptk_extractor_create': (C.c_int, [C.c_void_p, C.POINTER(UnetWeights), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     'ptk_extractor_destroy': (None, [C.c_void_p]),
     'ptk_extractor_level_shape': (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_i32p, c_i32p]),
-    'ptk_extractor_run': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p),
+    'ptk_extractor_run': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    'ptk_extractor_profile': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int32, c_f32p, c_i32p,
+                                        C.POINTER(C.c_double), c_i32p]),
     'ptk_extractor_activation': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_i32p, c_i32p,
                                            c_i32p]),
     'ptk_copy_d2d': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

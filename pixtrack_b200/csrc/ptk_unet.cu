@@ -22,7 +22,8 @@ namespace {
 // clamped, horizontal pass then vertical pass) + /255 + ImageNet mean/std (unet.py:159-161).
 // in: [Hi][Wi][3] fp32 0..255   out: [Ho][Wo][3] fp32 normalised
 // ---------------------------------------------------------------------------------------------
-__global__ void prep_image_kernel(const float* __restrict__ in, int Hi, int Wi, float* __restrict__ out, int Ho, int Wo) {
+template <typename TIn>
+__global__ void prep_image_kernel(const TIn* __restrict__ in, int Hi, int Wi, float* __restrict__ out, int Ho, int Wo) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Ho * Wo) return;
   const int y = idx / Wo, x = idx - y * Wo;
@@ -30,7 +31,7 @@ __global__ void prep_image_kernel(const float* __restrict__ in, int Hi, int Wi, 
   float v[3];
   if (Hi == Ho && Wi == Wo) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = in[(size_t)idx * 3 + c];
+    for (int c = 0; c < 3; ++c) v[c] = (float)in[(size_t)idx * 3 + c];
   } else {
     const float sx = (float)Wi / (float)Wo, sy = (float)Hi / (float)Ho;
     float fx = ((float)x + 0.5f) * sx - 0.5f, fy = ((float)y + 0.5f) * sy - 0.5f;
@@ -44,8 +45,8 @@ __global__ void prep_image_kernel(const float* __restrict__ in, int Hi, int Wi, 
     const int x1 = min(x0 + 1, Wi - 1), y1 = min(y0 + 1, Hi - 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float a = in[((size_t)y0 * Wi + x0) * 3 + c] * (1.f - fx) + in[((size_t)y0 * Wi + x1) * 3 + c] * fx;
-      const float b = in[((size_t)y1 * Wi + x0) * 3 + c] * (1.f - fx) + in[((size_t)y1 * Wi + x1) * 3 + c] * fx;
+      const float a = (float)in[((size_t)y0 * Wi + x0) * 3 + c] * (1.f - fx) + (float)in[((size_t)y0 * Wi + x1) * 3 + c] * fx;
+      const float b = (float)in[((size_t)y1 * Wi + x0) * 3 + c] * (1.f - fx) + (float)in[((size_t)y1 * Wi + x1) * 3 + c] * fx;
       v[c] = a * (1.f - fy) + b * fy;
     }
   }
@@ -253,7 +254,11 @@ struct PtkExtractor {
   int eh[5], ew[5];               // spatial size of encoder block b
   int dh[4], dw[4];               // spatial size of decoder block i output
   void* arena;
+  // optional per-launch timing (ptk_extractor_profile): events recorded after every launch
+  cudaEvent_t* prof_ev;
+  int prof_n;
 };
+#define PTK_MAX_LAUNCHES 48
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -329,17 +334,24 @@ extern "C" int ptk_extractor_activation(const PtkExtractor* e, int32_t kind, int
   return PTK_ERR_INVALID;
 }
 
-extern "C" int ptk_extractor_run(PtkExtractor* e, const float* image, int32_t img_h, int32_t img_w, float* const* feat,
-                                 float* const* conf, int32_t normalize, void* stream) {
+extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
+                                 float* const* feat, float* const* conf, int32_t normalize, void* stream) {
   PTK_REQUIRE(e && image && feat && conf, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int H = e->H, W = e->W;
-  prep_image_kernel<<<(H * W + 255) / 256, 256, 0, s>>>(image, img_h, img_w, e->img, H, W);
+  e->prof_n = 0;
+  auto mark = [&]() { if (e->prof_ev != nullptr && e->prof_n < PTK_MAX_LAUNCHES) cudaEventRecord(e->prof_ev[e->prof_n++], s); };
+  mark();
+  PTK_REQUIRE(img_dtype == 0 || img_dtype == 1, "img_dtype must be 0 (fp32) or 1 (uint8)");
+  if (img_dtype == 0) prep_image_kernel<float><<<(H * W + 255) / 256, 256, 0, s>>>((const float*)image, img_h, img_w, e->img, H, W);
+  else prep_image_kernel<uint8_t><<<(H * W + 255) / 256, 256, 0, s>>>((const uint8_t*)image, img_h, img_w, e->img, H, W);
+  mark();
   // ---- encoder (unet.py:163-167) ----
   int li = 0;
   conv1_direct_kernel<<<dim3((W + 15) / 16, (H + 15) / 16), 256, 0, s>>>(e->img, H, W, (const float*)e->wts.conv_w[0],
                                                                        e->wts.conv_b[0], e->enc[0][0]);
   PTK_CUDA_CHECK(cudaGetLastError());
+  mark();
   li = 1;
   for (int b = 0; b < 5; ++b) {
     const int h = e->eh[b], w = e->ew[b];
@@ -355,11 +367,13 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const float* image, int32_t im
                                                                   e->ew[b - 1], cprev, e->pool[b - 1]);
       cur = e->pool[b - 1];
       ccur = cprev;
+      mark();
     }
     for (int i = (b == 0 ? 1 : 0); i < kEncCount[b]; ++i) {
       const int rc = ptk_conv_f16(e->ctx, cur, ccur, nullptr, 0, h, w, h, w, 0, 0, e->wts.conv_w[li], e->wts.conv_b[li],
                                   kEncBlocks[b][i], 9, 1, e->enc[b][i], stream);
       if (rc != PTK_OK) return rc;
+      mark();
       cur = e->enc[b][i];
       ccur = kEncBlocks[b][i];
       ++li;
@@ -373,10 +387,12 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const float* image, int32_t im
     const int cskip = kEncBlocks[sb][kEncCount[sb] - 1];
     const long long n = (long long)e->dh[i] * e->dw[i] * (cprev / 8);
     upsample2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(prev, ph, pw, cprev, e->up[i]);
+    mark();
     const int rc = ptk_conv_f16(e->ctx, e->up[i], cprev, e->enc[sb][kEncCount[sb] - 1], cskip, e->dh[i], e->dw[i],
                                 e->dh[i], e->dw[i], e->eh[sb], e->ew[sb], e->wts.conv_w[li], e->wts.conv_b[li], kDec[i], 9,
                                 1, e->dec[i], stream);
     if (rc != PTK_OK) return rc;
+    mark();
     prev = e->dec[i];
     cprev = kDec[i];
     ph = e->dh[i];
@@ -392,7 +408,56 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const float* image, int32_t im
     const long long npix = (long long)h * w;
     head_kernel<<<(unsigned)((npix + 31) / 32), 256, 0, s>>>(src, npix, cin, kHeadDim[l], e->wts.head_w[l],
                                                            e->wts.head_b[l], feat[l], conf[l], normalize);
+    mark();
   }
   PTK_CUDA_CHECK(cudaGetLastError());
+  return PTK_OK;
+}
+
+// Runs the plan once with a CUDA event after every launch and returns the per-launch durations
+// (SYNCHRONISES; for benchmarks).  Launch order: prep, conv1, then per encoder block
+// [pool] conv..., per decoder block upsample conv, 3 heads.  kinds[i]: 0 prep, 1 conv1 (direct),
+// 2 pool, 3 tensor-core conv, 4 upsample, 5 head.  flops[i]: multiply-add count x 2 of launch i.
+extern "C" int ptk_extractor_profile(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
+                                     float* const* feat, float* const* conf, int32_t normalize, void* stream,
+                                     int32_t max_n, float* ms, int32_t* kinds, double* flops, int32_t* n_out) {
+  PTK_REQUIRE(e && ms && kinds && flops && n_out, "null argument");
+  cudaEvent_t ev[PTK_MAX_LAUNCHES];
+  for (int i = 0; i < PTK_MAX_LAUNCHES; ++i) PTK_CUDA_CHECK(cudaEventCreate(&ev[i]));
+  e->prof_ev = ev;
+  const int rc = ptk_extractor_run(e, image, img_dtype, img_h, img_w, feat, conf, normalize, stream);
+  e->prof_ev = nullptr;
+  if (rc != PTK_OK) return rc;
+  PTK_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  const int n = e->prof_n - 1;
+  // rebuild the launch list (same order as ptk_extractor_run)
+  int k = 0;
+  auto put = [&](int kind, double f) { if (k < max_n) { kinds[k] = kind; flops[k] = f; } ++k; };
+  put(0, 0.0);
+  put(1, 2.0 * e->H * e->W * 27.0 * 64.0);
+  for (int b = 0; b < 5; ++b) {
+    int ccur = (b == 0) ? 64 : kEncBlocks[b - 1][kEncCount[b - 1] - 1];
+    if (b > 0) put(2, 0.0);
+    for (int i = (b == 0 ? 1 : 0); i < kEncCount[b]; ++i) {
+      put(3, 2.0 * e->eh[b] * e->ew[b] * 9.0 * ccur * kEncBlocks[b][i]);
+      ccur = kEncBlocks[b][i];
+    }
+  }
+  int cprev = 512;
+  for (int i = 0; i < 4; ++i) {
+    const int sb = 3 - i;
+    put(4, 0.0);
+    put(3, 2.0 * e->dh[i] * e->dw[i] * 9.0 * (cprev + kEncBlocks[sb][kEncCount[sb] - 1]) * kDec[i]);
+    cprev = kDec[i];
+  }
+  for (int l = 0; l < 3; ++l) {
+    const int cin = (kHeadScale[l] == 4) ? 512 : kDec[3 - kHeadScale[l]];
+    const int h = (kHeadScale[l] == 4) ? e->eh[4] : e->dh[3 - kHeadScale[l]];
+    const int w = (kHeadScale[l] == 4) ? e->ew[4] : e->dw[3 - kHeadScale[l]];
+    put(5, 2.0 * h * w * (double)cin * (kHeadDim[l] + 1));
+  }
+  for (int i = 0; i < n && i < max_n; ++i) PTK_CUDA_CHECK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  *n_out = n < k ? n : k;
+  for (int i = 0; i < PTK_MAX_LAUNCHES; ++i) cudaEventDestroy(ev[i]);
   return PTK_OK;
 }

@@ -143,21 +143,48 @@ class B200FeatureExtractor(torch.nn.Module):
             self._plans[(H, W)] = _Plan(self._lib, self._ctx, self._wts, H, W)
         return self._plans[(H, W)]
 
-    def extract_device(self, image: Tensor, scale_image: int = 1, normalize: bool = False):
-        """image: CUDA fp32 [H,W,3] in 0..255.  Returns (feats_hwc list [H_l,W_l,C_l], confs list [H_l,W_l],
-        scales); nothing is synchronised."""
-        assert image.is_cuda and image.dtype == torch.float32 and image.is_contiguous() and image.shape[2] == 3
+    def level_shapes(self, ih: int, iw: int, scale_image: int = 1):
+        H, W, _ = self.network_size(ih, iw, scale_image)
+        return self.plan(H, W).shapes
+
+    def extract_device(self, image: Tensor, scale_image: int = 1, normalize: bool = False, out=None):
+        """image: CUDA [H,W,3] RGB, fp32 in 0..255 or uint8.  Returns (feats_hwc list [H_l,W_l,C_l], confs list
+        [H_l,W_l], scales); nothing is synchronised.  `out=(feats, confs)` writes into caller-owned buffers
+        (static addresses for prepared LM launches / CUDA graphs)."""
+        assert image.is_cuda and image.dtype in (torch.float32, torch.uint8) and image.is_contiguous()
+        assert image.shape[2] == 3
         ih, iw = image.shape[:2]
         H, W, sr = self.network_size(ih, iw, scale_image)
+        plan = self.plan(H, W)
+        if out is None:
+            feats = [torch.empty((h, w, c), dtype=torch.float32, device=self.device) for c, h, w in plan.shapes]
+            confs = [torch.empty((h, w), dtype=torch.float32, device=self.device) for c, h, w in plan.shapes]
+        else:
+            feats, confs = out
+        fp = (C.c_void_p * 3)(*[t.data_ptr() for t in feats])
+        cp = (C.c_void_p * 3)(*[t.data_ptr() for t in confs])
+        _lib.check(self._lib.ptk_extractor_run(plan.h, image.data_ptr(), 0 if image.dtype == torch.float32 else 1, ih,
+                                               iw, fp, cp, 1 if normalize else 0,
+                                               _lib.current_stream_ptr(self.device)))
+        scales = [(sr[0] / s, sr[1] / s) for s in self.model.scales]
+        return feats, confs, scales
+
+    def profile(self, image: Tensor, scale_image: int = 1, normalize: bool = True):
+        """Per-launch device times of one extraction (synchronises): list of (kind, ms, flops)."""
+        ih, iw = image.shape[:2]
+        H, W, _ = self.network_size(ih, iw, scale_image)
         plan = self.plan(H, W)
         feats = [torch.empty((h, w, c), dtype=torch.float32, device=self.device) for c, h, w in plan.shapes]
         confs = [torch.empty((h, w), dtype=torch.float32, device=self.device) for c, h, w in plan.shapes]
         fp = (C.c_void_p * 3)(*[t.data_ptr() for t in feats])
         cp = (C.c_void_p * 3)(*[t.data_ptr() for t in confs])
-        _lib.check(self._lib.ptk_extractor_run(plan.h, image.data_ptr(), ih, iw, fp, cp, 1 if normalize else 0,
-                                               _lib.current_stream_ptr(self.device)))
-        scales = [(sr[0] / s, sr[1] / s) for s in self.model.scales]
-        return feats, confs, scales
+        ms, kinds, flops, n = (C.c_float * 48)(), (C.c_int32 * 48)(), (C.c_double * 48)(), C.c_int32()
+        _lib.check(self._lib.ptk_extractor_profile(plan.h, image.data_ptr(), 0 if image.dtype == torch.float32 else 1,
+                                                   ih, iw, fp, cp, 1 if normalize else 0,
+                                                   _lib.current_stream_ptr(self.device), 48, ms, kinds, flops,
+                                                   C.byref(n)))
+        names = {0: 'prep', 1: 'conv1_direct', 2: 'maxpool', 3: 'conv_tc', 4: 'upsample', 5: 'head'}
+        return [(names[kinds[i]], ms[i], flops[i]) for i in range(n.value)]
 
     def activation(self, H: int, W: int, kind: int, index: int) -> Tensor:
         """Copy of an intermediate fp16 activation of the (H, W) plan (tests)."""
@@ -171,6 +198,9 @@ class B200FeatureExtractor(torch.nn.Module):
 
     @torch.no_grad()
     def __call__(self, image: np.ndarray, scale_image: int = 1):
-        img = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(self.device, non_blocking=True)
+        image = np.ascontiguousarray(image)
+        if image.dtype != np.uint8:
+            image = image.astype(np.float32, copy=False)
+        img = torch.from_numpy(image).to(self.device, non_blocking=True)
         feats, confs, scales = self.extract_device(img, scale_image, normalize=False)
         return [f.permute(2, 0, 1) for f in feats], scales, [c[None] for c in confs]
