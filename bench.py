@@ -3,13 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1] restated on synthetic data, SURVEY 8d "C2"):
-one step = one tracked frame = coarse-to-fine LM-to-convergence (reference
-stop criteria, num_iters=150) over the 3-level feature pyramid of a 1024x576
-query (32x576x1024 / 128x144x256 / 128x36x64), N=5000 3D points, B=8
-reference views solved together.  N>1: one process per GPU, independent
-frames sharded over ranks (weak scaling), one NCCL all_gather of the poses at
-the end.  Prints ONE JSON line (rank 0).
+Workload (BASELINE.json configs[1] restated on synthetic data, SURVEY 8d "C2"): one step = one
+tracked frame of pixloc_tracker_r9.py's refine() minus the NeRF render:
+  1. reference refresh: UNet extraction of the re-rendered reference view (1008x756 image) and
+     sparse sampling of its 3-level pyramid at the N=5000 model points into one of the B=8 view slots
+     (r9.py:154-160 -> extract_reference_features);
+  2. query: UNet extraction of the 1920x1080 frame (resized to 1024x576 on the device) and the
+     coarse-to-fine LM to convergence (reference stop criteria, num_iters=150) over the 3-level
+     pyramid against the B=8 cached reference views (refine_query_pose).
+N>1: one process per GPU, independent sequences sharded over ranks (weak scaling), one NCCL
+all_gather of the poses at the end.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -19,6 +22,7 @@ import sys
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -26,9 +30,11 @@ sys.path.insert(0, ROOT)
 
 from pixtrack_b200 import synthetic as syn  # noqa: E402
 
-N_POINTS, N_VIEWS, RING = 5000, 8, 3
-WORKLOAD = ('C2: 1024x576 query pyramid (32x576x1024,128x144x256,128x36x64 fp32), N=5000 points, B=8 reference '
-            'views, 3 levels coarse-to-fine, LM to convergence (num_iters=150, stop 1e-4/5e-3/5e-2), damping const=0')
+N_POINTS, N_VIEWS, RING = 5000, 8, 4
+WORKLOAD = ('C2 frame: 1920x1080 query + 1008x756 re-rendered reference view of one textured object; per frame '
+            '2 UNet(VGG19) extractions (1024x576 and 1008x756 nets, random-init weights), reference sparse sampling '
+            'at N=5000 points into 1 of B=8 view slots, 3-level coarse-to-fine LM to convergence against the 8 views '
+            '(num_iters=150, stop 1e-4/5e-3/5e-2, damping const=0); NeRF render excluded (no CPU path in the reference)')
 STOP = dict(num_iters=150, grad_stop=1e-4, dt_stop=5e-3, dR_stop=5e-2)
 
 
@@ -74,27 +80,40 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def host_frames(rank):
-    return [syn.frame_problem(seed=100 + 17 * rank + i, N=N_POINTS, B=N_VIEWS) for i in range(RING)]
-
-
 # ------------------------------------------------------------------------------------------------
-# reference arm: the oracle port of the reference's CPU path (the reference is Python and is not
-# present on the GPU box; oracle/lm.py restates it with the same torch CPU primitives)
+# CPU arm: the oracle port of the reference's CPU path (the reference is Python and is not present
+# on the GPU box; oracle/ restates it with the same torch CPU primitives: conv2d, grid_sample,
+# einsum, linalg.cholesky)
 # ------------------------------------------------------------------------------------------------
-def cpu_refine_view(fr, view, threads):
-    from oracle import lm
-    torch.set_num_threads(threads)
-    R, t = fr['T_init'][view, :9].reshape(3, 3), fr['T_init'][view, 9:]
-    iters = []
-    for lv in (2, 1, 0):
-        out = lm.lm_run(fr['p3d'], fr['F_ref'][lv][view], fr['F_q'][lv], R, t, fr['cam'][lv],
-                        fr['W_ref'][lv][view][:, None], fr['W_q'][lv], lam=lam0(), **STOP)
-        iters.append(out['n_iters'])
-        if out['failed']:
-            break
-        R, t = out['R'], out['t']
-    return iters
+class CpuFrame:
+    def __init__(self, seq, threads):
+        from oracle import lm
+        torch.set_num_threads(threads)
+        self.seq, self.sd, self.lams = seq, syn.unet_weights(0), [lm.damping_lambda(torch.zeros(6))] * 3
+        self.obs = {}
+
+    def step(self, i):
+        """One frame: reference extraction + sampling, query extraction, B view refinements.  The
+        reference keeps B observation sets; only slot i % B is refreshed per frame, the others reuse
+        the observations of the frame that filled them (first use fills every slot)."""
+        from oracle import lm, unet
+        fr = self.seq['frames'][i % len(self.seq['frames'])]
+        fr_f, sc_r, cf_r = unet.extract(self.sd, fr['img_r'].numpy().astype(np.float32))
+        maps_r = [torch.cat([f, c], 0) for f, c in zip(fr_f, cf_r)]
+        obs, keep = lm.sample_reference(maps_r, sc_r, self.seq['cam_r'], fr['R_r'], fr['t_r'], self.seq['p3d'])
+        new = ([o[keep] for o in obs], self.seq['p3d'][keep].float())
+        for v in range(N_VIEWS):
+            if v == i % N_VIEWS or v not in self.obs:
+                self.obs[v] = new
+        fq, sc_q, cf_q = unet.extract(self.sd, fr['img_q'].numpy().astype(np.float32))
+        maps_q = [torch.cat([f, c], 0) for f, c in zip(fq, cf_q)]
+        T = []
+        for v in range(N_VIEWS):
+            T0 = fr['T_init'][v]
+            out = lm.refine_levels(maps_q, sc_q, self.seq['cam_q'].float(), T0[:9].reshape(3, 3), T0[9:], self.obs[v][0],
+                                   self.obs[v][1], self.lams, **STOP)
+            T.append(torch.cat([out['R'].reshape(-1), out['t']]))
+        return torch.stack(T)
 
 
 def run_reference(args, rank, world):
@@ -102,22 +121,28 @@ def run_reference(args, rank, world):
         return
     torch.set_grad_enabled(False)
     threads = os.cpu_count() or 1
-    frames = [syn.frame_problem(seed=100 + i, N=N_POINTS, B=N_VIEWS) for i in range(1)]
-    for _ in range(min(args.warmup, 1)):
-        cpu_refine_view(frames[0], 0, threads)
+    cpu = CpuFrame(syn.tracked_sequence(100, n_frames=RING, N=N_POINTS, n_views=N_VIEWS), threads)
+    budget = 240.0
+    t_start = time.perf_counter()
+    for i in range(min(args.warmup, 1)):
+        cpu.step(i)
     t0 = time.perf_counter()
+    done = 0
     for i in range(args.steps):
-        cpu_refine_view(frames[0], i % N_VIEWS, threads)
+        cpu.step(i)
+        done += 1
+        if time.perf_counter() - t_start > budget:
+            break
     dt = time.perf_counter() - t0
-    fps = args.steps / dt / N_VIEWS          # a frame is 8 views
+    fps = done / dt
     line = {
         'impl': 'reference', 'metric': 'tracked frames/sec (LM-to-convergence)', 'value': fps, 'unit': 'frames/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps * N_VIEWS,
+        'n_gpus': args.gpus, 'steps': done, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * dt / done,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD},
         'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{args.steps} steps, each = 1 of the 8 views of one frame (3 levels, to convergence); '
-                                   'frames/s = views/s / 8'},
+                         'sample': f'{done} full frames (of {args.steps} requested; 240 s budget) through oracle/: 2 UNet '
+                                   'extractions + reference sampling + 8 view refinements each'},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -147,16 +172,19 @@ def lm_stress(dev, lam, peak):
     nv = float(L.log[:, :, 1].sum())
     byts = nv * (52 * 128 + 32)
     g, ng = L.plan()
-    return {'workload': 'C4 level 1: C=128 144x256, N=20000, B=16, 30 fixed iterations', 'ms_per_launch': ms,
-            'us_per_iteration': 1e3 * ms / 30, 'achieved': byts / (ms * 1e-3) / 1e9, 'unit': 'GB/s',
+    return {'kernel': 'lm_kernel', 'bound': 'hbm',
+            'workload': 'C4 level 1: C=128 144x256, N=20000, B=16, 30 fixed iterations', 'ms_per_launch': ms,
+            'us_per_iteration': 1e3 * ms / 30, 'achieved': byts / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
             'frac': byts / (ms * 1e-3) / 1e9 / peak, 'ctas_per_problem': g, 'problems_in_flight': ng,
-            'note': 'algorithmic bytes (52C+32 per valid point per iteration); the 19 MB map stays L2-resident'}
+            'note': 'algorithmic bytes (52C+32 per valid point per iteration); the 19 MB map stays L2-resident, so '
+                    'this is L2-served traffic measured against the HBM copy peak'}
 
 
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from pixtrack_b200 import _lib
-    from pixtrack_b200.refiner import FramePlan
+    from pixtrack_b200.extractor import B200FeatureExtractor
+    from pixtrack_b200.pipeline import FrameTracker
 
     torch.set_grad_enabled(False)
     dev = torch.device('cuda', local_rank)
@@ -164,24 +192,23 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lam = lam0().to(dev)
-    frames = host_frames(rank)
+    seq = syn.tracked_sequence(100 + rank, n_frames=RING, N=N_POINTS, n_views=N_VIEWS)
+    frames = seq['frames']
+    ext = B200FeatureExtractor(syn.unet_weights(0), dev)
+    trk = FrameTracker(ext, frames[0]['img_q'].shape[:2], seq['cam_q'], seq['p3d'], [lam] * 3, N_VIEWS, **STOP)
 
-    # per ring slot: pinned host copies of the per-frame inputs (query pyramid, channels-last),
-    # device-resident copies, a device staging area for the end-to-end leg, and prepared launch chains
-    host, plans, plans_e2e, staging = [], [], [], []
-    for fr in frames:
-        h = dict(fq=[f.permute(1, 2, 0).contiguous().pin_memory() for f in fr['F_q']],
-                 wq=[w[0].contiguous().pin_memory() for w in fr['W_q']])
-        ref = dict(cams=[c.to(dev) for c in fr['cam']], F_ref=[x.to(dev) for x in fr['F_ref']],
-                   W_ref=[x.to(dev) for x in fr['W_ref']], p3d=fr['p3d'].to(dev), T_init=fr['T_init'].to(dev))
-        fq, wq = [x.to(dev) for x in h['fq']], [x.to(dev) for x in h['wq']]
-        st = dict(fq=[torch.empty_like(x) for x in fq], wq=[torch.empty_like(x) for x in wq])
-        host.append(h)
-        staging.append(st)
-        plans.append(FramePlan(fq, wq, lams=[lam] * 3, **ref, **STOP).capture())
-        plans_e2e.append(FramePlan(st['fq'], st['wq'], lams=[lam] * 3, **ref, **STOP).capture())
-    ring_bytes = sum(x.numel() * 4 for x in host[0]['fq'] + host[0]['wq']) * RING
-    graphs = plans[0].graph is not None
+    host = [dict(q=f['img_q'].pin_memory(), r=f['img_r'].pin_memory()) for f in frames]
+    devi = [dict(q=h['q'].to(dev), r=h['r'].to(dev)) for h in host]
+    stage = dict(q=torch.empty_like(devi[0]['q']), r=torch.empty_like(devi[0]['r']))
+    T_ref = [torch.cat([f['R_r'].reshape(-1), f['t_r']]) for f in frames]
+    T_init = [f['T_init'].to(dev) for f in frames]
+    for v in range(N_VIEWS):            # fill every view slot once (untimed set-up)
+        trk.refresh_reference(v, devi[0]['r'], seq['cam_r'], T_ref[0])
+
+    def step(i, imgs):
+        k = i % RING
+        trk.refresh_reference(i % N_VIEWS, imgs['r'], seq['cam_r'], T_ref[k])
+        return trk.track(imgs['q'], T_init[k])
 
     def barrier():
         torch.cuda.synchronize()
@@ -189,9 +216,9 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: K frames, inputs already in HBM ---------------------------------
+    # ---- device-resident timing: K frames, images already in HBM ---------------------------------
     for i in range(args.warmup):
-        plans[i % RING].run()
+        step(i, devi[i % RING])
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -200,59 +227,69 @@ def run_ours(args, rank, world, local_rank):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
-        plans[i % RING].run()
+        step(i, devi[i % RING])
     ev1.record()
     barrier()
-    n_launch = 3 * args.steps
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
     _lib.device_status(local_rank)
-
-    # ---- per-launch timing of the LM kernel for the roofline (events around each bare launch) ------
-    per_level = {}
-    for i in range(min(args.steps, 4 * RING)):
-        pl = plans[i % RING]
-        for k, L in enumerate(pl.launches):
-            lv = 2 - k
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            L.launch()
-            b.record()
-            torch.cuda.synchronize()
-            Cc = L.shape[2]
-            n_it = L.n_iters.cpu()
-            lg = L.log[:, :, 1].cpu()
-            nv = sum(float(lg[v, :int(n_it[v])].sum()) for v in range(N_VIEWS))
-            rec = per_level.setdefault(lv, dict(ms=0.0, bytes=0.0, n=0, iters=0))
-            rec['ms'] += a.elapsed_time(b)
-            rec['bytes'] += nv * (52 * Cc + 32)
-            rec['n'] += 1
-            rec['iters'] += int(n_it.max())
     clk = clocks.stop() if rank == 0 else None
-    dom = max(per_level, key=lambda k: per_level[k]['ms'])
+    launches_per_step = 2 * 32 + 1 + 3          # 2 extractor plans, 1 sampling launch, 3 LM launches (one graph)
+
+    # ---- results of the last ring pass: LM iteration counts, failures, pose error vs ground truth ------
+    iters, errs, ok = [], [], True
+    for k in range(RING):
+        T, failed = step(k, devi[k])
+        n_it = [int(x.max()) for x in trk.plan.n_iters]
+        torch.cuda.synchronize()
+        iters.append(n_it)
+        ok = ok and not bool(failed.any())
+        Tc = T.double().cpu()
+        dR = Tc[:, :9].reshape(-1, 3, 3) @ frames[k]['R_q'].t()
+        ang = torch.rad2deg(torch.acos(((dR.diagonal(dim1=1, dim2=2).sum(-1) - 1) / 2).clamp(-1, 1)))
+        errs.append([float(ang.median()), float((Tc[:, 9:] - frames[k]['t_q']).norm(dim=1).median())])
+
+    # ---- rooflines (rank 0): per-launch CUDA-event timing of the extractor plan; LM stress ---------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except OSError:
         pass
-    peak = float(peaks.get('hbm_gbs', 6650.0))
-    ach = per_level[dom]['bytes'] / (per_level[dom]['ms'] * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': f'lm_kernel (pyramid level {dom} launch)', 'achieved': ach, 'peak': peak,
-                'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
-                'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
-                'per_level': {str(k): {'us_per_launch': 1e3 * v['ms'] / v['n'], 'GBps': v['bytes'] / (v['ms'] * 1e-3) / 1e9,
-                                       'max_iters_per_launch': v['iters'] / v['n']} for k, v in per_level.items()}}
-    stress = lm_stress(dev, lam, peak) if rank == 0 else None
+    roofline = stress = plan_prof = None
+    if rank == 0:
+        rows = None
+        for _ in range(3):
+            r = ext.profile(devi[0]['q'])
+            rows = r if rows is None else [(a[0], min(a[1], b[1]), a[2]) for a, b in zip(rows, r)]
+        tc_ms = sum(r[1] for r in rows if r[0] == 'conv_tc')
+        tc_fl = sum(r[2] for r in rows if r[0] == 'conv_tc')
+        n_tc = sum(1 for r in rows if r[0] == 'conv_tc')
+        peak_tf = float(peaks.get('bf16_tflops', 1590.0))
+        ach = tc_fl / (tc_ms * 1e-3) / 1e12
+        by_kind = {}
+        for k, m, f in rows:
+            d = by_kind.setdefault(k, [0.0, 0.0, 0])
+            d[0] += m
+            d[1] += f
+            d[2] += 1
+        plan_prof = {k: {'launches': v[2], 'ms': v[0], 'gflop': v[1] / 1e9} for k, v in by_kind.items()}
+        roofline = {'bound': 'tensor', 'kernel': f'conv_tc_kernel (tcgen05 implicit-GEMM conv; {n_tc} launches of the '
+                    '1024x576 plan, 549 of its 561 GFLOP)', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                    'frac': ach / peak_tf, 'traffic': None,
+                    'peak_source': ('MEASURED_PEAKS.json bf16_tflops (burst; kernels timed one by one with CUDA events)'
+                                    if peaks else 'fallback 1590 TFLOP/s'),
+                    'avg_launch_us': 1e3 * tc_ms / n_tc, 'share_of_plan_time': tc_ms / sum(r[1] for r in rows)}
+        stress = lm_stress(dev, lam, float(peaks.get('hbm_gbs', 6650.0)))
 
-    # ---- end to end: host buffers in (pinned -> staging), poses out ---------------------------------
+    # ---- end to end: host images in (pinned -> staging), poses out -----------------------------------
     def e2e_step(i):
-        h, st, pl = host[i % RING], staging[i % RING], plans_e2e[i % RING]
-        for dst, src in zip(st['fq'] + st['wq'], h['fq'] + h['wq']):
-            dst.copy_(src, non_blocking=True)
-        pl.run()
-        return pl.T.cpu(), pl.failed.cpu()
+        h = host[i % RING]
+        stage['q'].copy_(h['q'], non_blocking=True)
+        stage['r'].copy_(h['r'], non_blocking=True)
+        T, failed = step(i, stage)
+        return T.cpu(), failed.cpu()
     for i in range(max(1, args.warmup // 2)):
         e2e_step(i)
     barrier()
@@ -263,43 +300,44 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    h2d = sum(x.numel() * 4 for x in host[0]['fq'] + host[0]['wq'])
+    h2d = host[0]['q'].numel() + host[0]['r'].numel()
     d2h = N_VIEWS * 13
 
     # ---- final gather of per-frame results (the only collective on this path) -----------------------
-    res = torch.stack([torch.cat([pl.T, pl.failed.float()[:, None]], 1) for pl in plans])
+    res = torch.cat([trk.plan.T, trk.plan.failed.float()[:, None]], 1)
     if world > 1:
         gathered = [torch.empty_like(res) for _ in range(world)]
         dist.all_gather(gathered, res)
-    iters = [[int(x.max()) for x in pl.n_iters] for pl in plans]
-    ok = all(not bool(pl.failed.any()) for pl in plans)
 
     if rank == 0:
         cpu = None
         if world == 1:
             th = os.cpu_count() or 1
-            cpu_refine_view(frames[0], 0, th)
+            cf = CpuFrame(seq, th)
             t0 = time.perf_counter()
-            n_v = 0
-            while n_v < 40 and time.perf_counter() - t0 < 15:
-                cpu_refine_view(frames[n_v // N_VIEWS % RING], n_v % N_VIEWS, th)
-                n_v += 1
+            n_f = 0
+            while n_f < 2 and (n_f == 0 or time.perf_counter() - t0 < 15):
+                cf.step(n_f)
+                n_f += 1
             dt = time.perf_counter() - t0
-            cpu = {'value': n_v / dt / N_VIEWS, 'unit': 'frames/s', 'cores': th, 'kind': 'port',
-                   'sample': f'{n_v} view refinements (each 3 levels to convergence) of the same C2 frames via '
-                             f'oracle/lm.py in {dt:.1f} s; frames/s = views/s / 8'}
+            cpu = {'value': n_f / dt, 'unit': 'frames/s', 'cores': th, 'kind': 'port',
+                   'sample': f'{n_f} full frame(s) of the same sequence through oracle/ (2 UNet extractions + reference '
+                             f'sampling + 8 view refinements each) in {dt:.1f} s'}
         fps = args.steps * world / (ms_total * 1e-3)
         line = {
             'metric': 'tracked frames/sec (LM-to-convergence)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16 tensor-core convs (f32 '
+            'accumulate) + f32 LM', 'data': 'synthetic',
             'config': {'workload': WORKLOAD,
-                       'l2': f'inputs larger than L2: ring of {RING} frames, {ring_bytes / 1e6:.0f} MB of maps',
-                       'stage': 'LM only (pyramids synthetic; extractor and NeRF render not in the timed step yet)',
-                       'cuda_graph': graphs, 'lm_iters_coarse_to_fine': iters, 'no_failures': ok},
+                       'l2': f'inputs larger than L2: ring of {RING} distinct frames; one frame streams >600 MB of '
+                             'activations and maps through the 126 MB L2',
+                       'cuda_graph': trk.plan.graph is not None, 'lm_iters_coarse_to_fine': iters, 'no_failures': ok,
+                       'median_pose_error_deg_m_vs_gt': errs},
             'e2e': {'value': args.steps * world / float(e2e_s), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h},
-            'gpu_launches': n_launch, 'clocks': clk, 'roofline': roofline, 'lm_stress': stress, 'cpu_baseline': cpu,
+            'gpu_launches': launches_per_step * args.steps, 'clocks': clk, 'roofline': roofline,
+            'roofline_lm': stress, 'extractor_plan': plan_prof, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -154,6 +154,40 @@ int ptk_sample_points(PtkContext* ctx, const float* map, int64_t stride_c, int64
                       uint8_t* mask, float* grads, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Reference-view observations of the model points, all pyramid levels in one
+ * launch.
+ *
+ * Replaces PoseTrackerRefiner.interp_sparse_observations
+ *   pixtrack/localization/pixloc_pose_refiners.py:327-368
+ * (per level: camera.scale(sc).world2image(T * p3d) in float64, interpolator at
+ * the float pixel position, mask & valid; validity = AND over levels) and the
+ * reference-side half of BaseRefiner.refine_pose_using_features
+ *   pixloc/pixloc/localization/base_refiner.py:74-84
+ * (stack per level, split descriptor / confidence, F.normalize(F_ref, dim=1)).
+ * Level l reads feat [H][W][C] channels-last (NOT normalised) and conf [H][W],
+ * and writes f_out [N][C] (L2-normalised when normalize != 0) and w_out [N].
+ * p3d: DEVICE float64 [N][3].  host_cam: HOST float64 [n_cam] camera of the
+ * reference image; level l uses Camera.scale((sx, sy)).  host_T: HOST float64
+ * [12] world-to-camera pose (R row-major, t).  valid [N]: 1 when the point
+ * projects inside every level (the reference drops the others from its lists;
+ * pass `valid` as PtkLmProblem.mask for the same sums).
+ * ---------------------------------------------------------------------- */
+#define PTK_MAX_LEVELS 4
+typedef struct PtkRefLevel {
+  const float* feat;
+  const float* conf;     /* NULL together with w_out: descriptors only            */
+  float* f_out;
+  float* w_out;
+  double sx, sy;
+  int32_t C, H, W;
+  int32_t normalize;
+} PtkRefLevel;
+
+int ptk_sample_reference(PtkContext* ctx, const PtkRefLevel* levels, int32_t n_levels, const double* p3d, int32_t N,
+                         const double* host_cam, int32_t n_cam, const double* host_T, int32_t pad, uint8_t* valid,
+                         void* stream);
+
+/* ------------------------------------------------------------------------
  * Feature extractor (PixLoc UNet, VGG19 encoder) on the tcgen05 tensor cores.
  *
  * ptk_conv_f16: one convolution layer on channels-last fp16 activations

@@ -45,6 +45,12 @@ class UnetWeights(C.Structure):
                 ('head_b', C.c_void_p * 3)]
 
 
+class RefLevel(C.Structure):
+    _fields_ = [('feat', C.c_void_p), ('conf', C.c_void_p), ('f_out', C.c_void_p), ('w_out', C.c_void_p),
+                ('sx', C.c_double), ('sy', C.c_double), ('C', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('normalize', C.c_int32)]
+
+
 class LmResult(C.Structure):
     _fields_ = [('T', C.c_void_p), ('failed', C.c_void_p), ('n_iters', C.c_void_p), ('log', C.c_void_p)]
 
@@ -62,6 +68,9 @@ SYMBOLS = {
     'ptk_sample_points': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
+    'ptk_sample_reference': (C.c_int, [C.c_void_p, C.POINTER(RefLevel), C.c_int32, C.c_void_p, C.c_int32,
+                                       C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p,
+                                       C.c_void_p]),
     'ptk_conv_f16': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_void_p, C.c_void_p]),

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(HERE, '_build')
 LIB = os.path.join(HERE, 'libpixtrack_b200.so')
-SOURCES = ('ptk_api.cu', 'ptk_lm.cu', 'ptk_sample.cu', 'ptk_conv.cu', 'ptk_unet.cu')
+SOURCES = ('ptk_api.cu', 'ptk_lm.cu', 'ptk_sample.cu', 'ptk_sample_ref.cu', 'ptk_conv.cu', 'ptk_unet.cu')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 

@@ -167,67 +167,136 @@ __global__ void upsample2_kernel(const __half* __restrict__ in, int H, int W, in
 // ---------------------------------------------------------------------------------------------
 // Heads (unet.py:47-50,177-188): 1x1 adaptation conv C_in -> C_out plus the 1x1 uncertainty conv
 // (-> 1 channel), confidence = sigmoid(-u); optional per-pixel L2 normalisation of the descriptor
-// (base_refiner.py:92-94) fused in.  fp16 in, fp32 out.
+// (base_refiner.py:92-94) fused in.  fp16 activations in, fp32 weights, fp32 out.
 // w: [C_out + 1][C_in] fp32 (row C_out = uncertainty), b: [C_out + 1].
-// 32 pixels x 8 output-slices per 256-thread block, K in chunks of 64 through shared memory.
+// Register-tiled fp32 GEMM on the CUDA cores (the op is 1 GMAC in total and bound by the 78 MB it
+// writes at level 0): 256 threads = NTM x NTN, a thread owns PT pixels x 9 outputs; K advances in
+// chunks of 32 through shared memory with both operands k-contiguous (one LDS.128 feeds 4 k of one
+// row: 13 loads per 144 FMAs at PT = 4); results are staged in shared memory and leave as fully
+// coalesced rows of the channels-last output.
 // ---------------------------------------------------------------------------------------------
-constexpr int kHeadMaxOut = 136;   // >= C_out + 1, multiple of 8
+constexpr int kHeadKC = 32, kHeadLd = kHeadKC + 4, kHeadOut = 9;
+template <int PT, int NTN>
+struct HeadCfg {
+  static constexpr int NTM = 256 / NTN, TM = NTM * PT, TN = kHeadOut * NTN;
+  static constexpr int kOperandFloats = (TM + TN) * kHeadLd;
+  static constexpr int kStageFloats = TM * (TN + 1);
+  static constexpr int kSmemFloats = kOperandFloats > kStageFloats ? kOperandFloats : kStageFloats;
+};
+
+template <int PT, int NTN>
 __global__ void __launch_bounds__(256) head_kernel(const __half* __restrict__ x, long long npix, int Cin, int Cout,
                                                    const float* __restrict__ w, const float* __restrict__ b,
                                                    float* __restrict__ feat, float* __restrict__ conf, int normalize) {
-  __shared__ float sx[32][65];
-  __shared__ float swt[kHeadMaxOut][65];
-  const int j = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  const long long p0 = (long long)blockIdx.x * 32;
+  using Cfg = HeadCfg<PT, NTN>;
+  constexpr int TM = Cfg::TM, TN = Cfg::TN;
+  __shared__ __align__(16) float smem[Cfg::kSmemFloats];
+  float* As = smem;                     // [TM][kHeadLd]
+  float* Ws = smem + TM * kHeadLd;      // [TN][kHeadLd]
+  const int tn = threadIdx.x % NTN, tm = threadIdx.x / NTN;
+  const long long p0 = (long long)blockIdx.x * TM;
   const int nout = Cout + 1;
-  constexpr int kAcc = kHeadMaxOut / 8;
-  float acc[kAcc];
+  float acc[PT][kHeadOut];
 #pragma unroll
-  for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
-  for (int k0 = 0; k0 < Cin; k0 += 64) {
-    const int kc = min(64, Cin - k0);
+  for (int i = 0; i < PT; ++i)
+#pragma unroll
+    for (int j = 0; j < kHeadOut; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < Cin; k0 += kHeadKC) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
-      const int pp = i >> 6, kk = i & 63;
-      sx[pp][kk] = (kk < kc && p0 + pp < npix) ? __half2float(x[(p0 + pp) * Cin + k0 + kk]) : 0.f;
+    for (int idx = threadIdx.x; idx < TM * 4; idx += 256) {        // activations: 8 halfs per thread
+      const int p = idx >> 2, q = idx & 3;
+      float v[8];
+      if (p0 + p < npix) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + (p0 + p) * Cin + k0 + q * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          v[2 * e] = f.x;
+          v[2 * e + 1] = f.y;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      }
+      float4* dst = reinterpret_cast<float4*>(As + p * kHeadLd + q * 8);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
-    for (int i = threadIdx.x; i < nout * 64; i += 256) {
-      const int co = i >> 6, kk = i & 63;
-      swt[co][kk] = (kk < kc) ? w[(size_t)co * Cin + k0 + kk] : 0.f;
+    for (int idx = threadIdx.x; idx < TN * 8; idx += 256) {        // weights: one float4 per thread
+      const int n = idx >> 3, q = idx & 7;
+      const float4 v = (n < nout) ? __ldg(reinterpret_cast<const float4*>(w + (size_t)n * Cin + k0 + q * 4))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(Ws + n * kHeadLd + q * 4) = v;
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < kAcc; ++i) {
-      const int co = j + 8 * i;
-      if (co < nout) {
-        float a = acc[i];
-#pragma unroll 16
-        for (int kk = 0; kk < kc; ++kk) a = fmaf(sx[pl][kk], swt[co][kk], a);
-        acc[i] = a;
+    for (int k = 0; k < kHeadKC; k += 4) {
+      float4 a[PT];
+#pragma unroll
+      for (int i = 0; i < PT; ++i) a[i] = *reinterpret_cast<const float4*>(As + (tm * PT + i) * kHeadLd + k);
+#pragma unroll
+      for (int j = 0; j < kHeadOut; ++j) {
+        const float4 wv = *reinterpret_cast<const float4*>(Ws + (tn + NTN * j) * kHeadLd + k);
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+          acc[i][j] = fmaf(a[i].x, wv.x, acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, wv.y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, wv.z, acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, wv.w, acc[i][j]);
+        }
       }
     }
   }
-  float ss = 0.f;
+  // bias, squared norm of the descriptor part (the NTN threads of a pixel are adjacent lanes)
+  float ss[PT];
 #pragma unroll
-  for (int i = 0; i < kAcc; ++i) {
-    const int co = j + 8 * i;
-    if (co < nout) {
-      acc[i] += b[co];
-      if (co < Cout) ss = fmaf(acc[i], acc[i], ss);
+  for (int i = 0; i < PT; ++i) ss[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kHeadOut; ++j) {
+    const int n = tn + NTN * j;
+    const float bias = (n < nout) ? __ldg(b + n) : 0.f;
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+      acc[i][j] += bias;
+      if (n < Cout) ss[i] = fmaf(acc[i][j], acc[i][j], ss[i]);
     }
   }
-  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-  ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-  const float inv = normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
-  const long long p = p0 + pl;
-  if (p >= npix) return;
 #pragma unroll
-  for (int i = 0; i < kAcc; ++i) {
-    const int co = j + 8 * i;
-    if (co < Cout) feat[p * Cout + co] = acc[i] * inv;
-    else if (co == Cout) conf[p] = 1.f / (1.f + expf(acc[i]));   // sigmoid(-u)
+  for (int i = 0; i < PT; ++i) {
+#pragma unroll
+    for (int m = NTN >> 1; m >= 1; m >>= 1) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], m);
   }
+  __syncthreads();                      // operands dead: reuse the buffer as the output stage
+  float* Os = smem;                     // [TM][Cout + 1 (pad)]
+  const int ldo = Cout + 1;
+#pragma unroll
+  for (int i = 0; i < PT; ++i) {
+    const int pl = tm * PT + i;
+    const float inv = normalize ? 1.f / fmaxf(sqrtf(ss[i]), 1e-12f) : 1.f;
+#pragma unroll
+    for (int j = 0; j < kHeadOut; ++j) {
+      const int n = tn + NTN * j;
+      if (n < Cout) Os[pl * ldo + n] = acc[i][j] * inv;
+      else if (n == Cout && p0 + pl < npix) conf[p0 + pl] = 1.f / (1.f + expf(acc[i][j]));   // sigmoid(-u)
+    }
+  }
+  __syncthreads();
+  const long long rem = npix - p0;
+  const int rows = rem < TM ? (int)rem : TM;
+  float* dst = feat + p0 * Cout;
+  for (int idx = threadIdx.x; idx < rows * Cout; idx += 256) {
+    const int pl = idx / Cout, c = idx - pl * Cout;
+    dst[idx] = Os[pl * ldo + c];
+  }
+}
+
+template <int PT, int NTN>
+void launch_head(const __half* x, long long npix, int Cin, int Cout, const float* w, const float* b, float* feat,
+                 float* conf, int normalize, cudaStream_t s) {
+  constexpr int TM = HeadCfg<PT, NTN>::TM;
+  head_kernel<PT, NTN><<<(unsigned)((npix + TM - 1) / TM), 256, 0, s>>>(x, npix, Cin, Cout, w, b, feat, conf, normalize);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -406,8 +475,12 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
     if (kHeadScale[l] == 4) { src = e->enc[4][3]; cin = 512; h = e->eh[4]; w = e->ew[4]; }
     else { const int di = 3 - kHeadScale[l]; src = e->dec[di]; cin = kDec[di]; h = e->dh[di]; w = e->dw[di]; }
     const long long npix = (long long)h * w;
-    head_kernel<<<(unsigned)((npix + 31) / 32), 256, 0, s>>>(src, npix, cin, kHeadDim[l], e->wts.head_w[l],
-                                                           e->wts.head_b[l], feat[l], conf[l], normalize);
+    if (kHeadDim[l] + 1 <= HeadCfg<4, 4>::TN)          // 32 (+1) outputs: 256 pixels per block
+      launch_head<4, 4>(src, npix, cin, kHeadDim[l], e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
+    else if (npix >= 64LL * 2 * e->ctx->num_sms)       // 128 (+1) outputs: 64 pixels per block
+      launch_head<4, 16>(src, npix, cin, kHeadDim[l], e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
+    else                                               // small maps: 16 pixels per block to fill the SMs
+      launch_head<1, 16>(src, npix, cin, kHeadDim[l], e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
     mark();
   }
   PTK_CUDA_CHECK(cudaGetLastError());

@@ -1,49 +1,86 @@
-"""FrameTracker: the per-frame hot path on one GPU -- query feature extraction followed by the
-coarse-to-fine LM refinement against B cached reference views -- over static device buffers.
+"""FrameTracker: the per-frame hot path on one GPU over static device buffers.
 
 This is the B200 form of one `PixLocPoseTrackerR9.refine` call restricted to the hot path
-(reference pixtrack/pose_trackers/pixloc_tracker_r9.py:216-266 ->
-PoseTrackerRefiner.refine_query_pose, pixtrack/localization/pixloc_pose_refiners.py:200-271 ->
-dense_feature_extraction + refine_pose_using_features): the query pyramid is written by the native
-UNet plan straight into the buffers the prepared LM launches read (descriptors already
-L2-normalised by the fused head), so a frame is: one image upload, ~35 extractor launches, one
-CUDA-graph launch of the 3-level LM chain, one 13-float-per-view read-back.
+(reference pixtrack/pose_trackers/pixloc_tracker_r9.py:216-266):
+
+  refresh_reference(view, image, camera, pose)
+      = create_dynamic_reference_image's feature half (r9.py:154-160 ->
+        PoseTrackerRefiner.extract_reference_features, pixtrack/localization/pixloc_pose_refiners.py:273-325):
+        dense extraction of the rendered reference view + interp_sparse_observations (:327-368).
+        Here: the native UNet plan, then ONE ptk_sample_reference launch that writes the
+        normalised descriptors / confidences / validity of all levels straight into the view's slot
+        of the observation cache the LM launches read.
+  track(image, T_init)
+      = PoseTrackerRefiner.refine_query_pose (:200-271): dense_feature_extraction of the query +
+        refine_pose_using_features (pixloc/pixloc/localization/base_refiner.py:64-137) against the B
+        cached views.  Here: the UNet plan writes the L2-normalised query pyramid into the buffers
+        the prepared LM launches read; the 3-level coarse-to-fine chain is one CUDA-graph launch.
+
+A frame is: image upload(s), ~35 extractor launches per image, one sampling launch, one graph
+launch, one 13-float-per-view read-back; nothing synchronises inside.
 """
-from typing import Dict, List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 
 from .extractor import B200FeatureExtractor
 from .geometry import Camera
 from .refiner import FramePlan
+from .sampling import sample_reference
 
 Tensor = torch.Tensor
 
 
 class FrameTracker:
-    def __init__(self, extractor: B200FeatureExtractor, image_hw, camera: Tensor, p3d: Tensor,
-                 F_ref: Sequence[Tensor], W_ref: Sequence[Tensor], lams: Sequence[Tensor], n_views: int,
-                 scale_image: int = 1, use_graph: bool = True, **lm_conf):
-        """camera: [n_cam] at the IMAGE resolution; p3d [N,3]; F_ref[l] [B,N,C_l] (normalised),
-        W_ref[l] [B,N]; lams[l] [6]; lm_conf -> LmLaunch (num_iters, stop criteria, pad)."""
+    def __init__(self, extractor: B200FeatureExtractor, image_hw, camera: Tensor, p3d: Tensor, lams: Sequence[Tensor],
+                 n_views: int, scale_image: int = 1, use_graph: bool = True, pad: int = 1, **lm_conf):
+        """camera: [n_cam] query camera at the IMAGE resolution; p3d [N,3] model points (float64 kept for
+        the reference-side projection, float32 copy for the LM); lams[l] [6] damping per level;
+        lm_conf -> LmLaunch (num_iters, stop criteria)."""
         dev = extractor.device
-        self.extractor, self.scale_image, self.B = extractor, scale_image, n_views
+        self.extractor, self.scale_image, self.B, self.pad = extractor, scale_image, n_views, pad
         ih, iw = image_hw
         H, W, sr = extractor.network_size(ih, iw, scale_image)
         shapes = extractor.plan(H, W).shapes
+        N = p3d.shape[0]
+        self.p3d64 = p3d.to(dev, torch.float64).contiguous()
+        self.p3d32 = self.p3d64.float()
+        # query pyramid (channels-last, L2-normalised by the fused head) + confidences
         self.feats = [torch.zeros((h, w, c), dtype=torch.float32, device=dev) for c, h, w in shapes]
         self.confs = [torch.zeros((h, w), dtype=torch.float32, device=dev) for c, h, w in shapes]
+        # reference observation cache: F_ref[l] [B,N,C_l], W_ref[l] [B,N], valid [B,N]
+        self.F_ref = [torch.zeros((n_views, N, c), dtype=torch.float32, device=dev) for c, _, _ in shapes]
+        self.W_ref = [torch.zeros((n_views, N), dtype=torch.float32, device=dev) for _ in shapes]
+        self.valid = torch.zeros((n_views, N), dtype=torch.uint8, device=dev)
         cam = Camera(camera.detach().cpu().double())
         self.cams = [cam.scale((sr[0] / s, sr[1] / s))._data.float().to(dev) for s in extractor.model.scales]
         self.T_init = torch.zeros((n_views, 12), dtype=torch.float32, device=dev)
-        self.plan = FramePlan(self.feats, self.confs, self.cams, [f.to(dev) for f in F_ref],
-                              [w.to(dev) for w in W_ref], p3d.to(dev), self.T_init, [l.to(dev) for l in lams], **lm_conf)
-        if use_graph:
-            self.plan.capture()
+        self.plan = FramePlan(self.feats, self.confs, self.cams, self.F_ref, self.W_ref, self.p3d32, self.T_init,
+                              [l.to(dev) for l in lams], mask=self.valid, pad=pad, **lm_conf)
+        self._use_graph, self._captured = use_graph, False
+        self._ref_bufs = {}
+
+    def refresh_reference(self, view: int, image: Tensor, camera, T_w2cam, scale_image: int = 1):
+        """image: CUDA [H,W,3] uint8/fp32 render of reference view `view`; camera / T_w2cam: its camera at the
+        image resolution and its world-to-camera pose (host, float64).  Stream-ordered."""
+        ih, iw = image.shape[:2]
+        key = (ih, iw, scale_image)
+        if key not in self._ref_bufs:
+            shapes = self.extractor.level_shapes(ih, iw, scale_image)
+            dev = self.extractor.device
+            self._ref_bufs[key] = ([torch.empty((h, w, c), dtype=torch.float32, device=dev) for c, h, w in shapes],
+                                   [torch.empty((h, w), dtype=torch.float32, device=dev) for c, h, w in shapes])
+        bufs = self._ref_bufs[key]
+        feats, confs, scales = self.extractor.extract_device(image, scale_image, normalize=False, out=bufs)
+        sample_reference(feats, confs, scales, camera, T_w2cam, self.p3d64, pad=self.pad, normalize=True,
+                         out=([f[view] for f in self.F_ref], [w[view] for w in self.W_ref], self.valid[view]))
 
     def track(self, image: Tensor, T_init: Optional[Tensor] = None):
-        """image: CUDA [H,W,3] uint8/fp32.  Returns (T [B,12], failed [B]) device tensors; stream-ordered,
-        no synchronisation."""
+        """image: CUDA [H,W,3] uint8/fp32 query frame.  Returns (T [B,12], failed [B]) device tensors;
+        stream-ordered, no synchronisation."""
+        if self._use_graph and not self._captured:
+            self.plan.capture()
+            self._captured = True
         if T_init is not None:
             self.T_init.copy_(T_init, non_blocking=True)
         self.extractor.extract_device(image, self.scale_image, normalize=True, out=(self.feats, self.confs))

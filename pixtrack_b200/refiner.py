@@ -22,19 +22,20 @@ def refine_levels_batched(fq_hwc: Sequence[Tensor], wq: Sequence[Optional[Tensor
                           F_ref: Sequence[Tensor], W_ref: Sequence[Optional[Tensor]], p3d: Tensor, T_init: Tensor,
                           lams: Sequence[Tensor], *, num_iters: int = 150, pad: int = 1, loss_scale: float = 0.1,
                           grad_stop: float = 1e-4, dt_stop: float = 5e-3, dR_stop: float = 5e-2,
-                          want_log: bool = True):
+                          want_log: bool = True, mask: Optional[Tensor] = None):
     """All sequences are indexed by pyramid level, fine (0) to coarse (L-1);
     the levels are visited coarse to fine.
       fq_hwc[l] [B|1,H_l,W_l,C_l] (already L2-normalised over C), wq[l] [B|1,H_l,W_l],
       cams[l] [B|1,n_cam] (camera already scaled to the level), F_ref[l] [B,N,C_l]
-      (already normalised), W_ref[l] [B,N], p3d [B|1,N,3], T_init [B,12], lams[l] [6].
+      (already normalised), W_ref[l] [B,N], p3d [B|1,N,3], T_init [B,12], lams[l] [6];
+      mask [B,N] uint8: points to use (the `valid` flags of sample_reference).
     Returns dict(T [B,12], failed [B] uint8, n_iters [L][B], logs [L]) -- levels
     in visiting order (coarse first), like DebugTracker.costs."""
     T, skip = T_init, None
     n_all, logs = [], []
     for lv in reversed(range(len(fq_hwc))):
         T, failed, n_it, log = lm_run_batched(
-            p3d, F_ref[lv], fq_hwc[lv], T, cams[lv], lams[lv], W_ref[lv], wq[lv], None, skip,
+            p3d, F_ref[lv], fq_hwc[lv], T, cams[lv], lams[lv], W_ref[lv], wq[lv], mask, skip,
             num_iters=num_iters, pad=pad, loss_scale=loss_scale, grad_stop=grad_stop, dt_stop=dt_stop,
             dR_stop=dR_stop, want_log=want_log)
         skip = failed
@@ -52,11 +53,11 @@ class FramePlan:
     device.  `capture()` records the chain into a CUDA graph so a frame costs
     one graph launch."""
 
-    def __init__(self, fq_hwc, wq, cams, F_ref, W_ref, p3d, T_init, lams, **kw):
+    def __init__(self, fq_hwc, wq, cams, F_ref, W_ref, p3d, T_init, lams, mask=None, **kw):
         self.launches = []
         T, skip = T_init, None
         for lv in reversed(range(len(fq_hwc))):
-            L = LmLaunch(p3d, F_ref[lv], fq_hwc[lv], T, cams[lv], lams[lv], W_ref[lv], wq[lv], None, skip, **kw)
+            L = LmLaunch(p3d, F_ref[lv], fq_hwc[lv], T, cams[lv], lams[lv], W_ref[lv], wq[lv], mask, skip, **kw)
             self.launches.append(L)
             T, skip = L.T, L.failed
         self.T, self.failed = T, skip

@@ -259,3 +259,69 @@ def frame_problem(seed: int, N: int = 5000, B: int = 8, size: Tuple[int, int] = 
         T0.append(torch.cat([Rb.reshape(-1), tb]))
     out['T_init'] = torch.stack(T0)
     return out
+
+
+# ---------------------------------------------------------------------------
+# geometrically consistent image pairs: a textured plane seen by two cameras
+# ---------------------------------------------------------------------------
+def plane_texture(seed: int, size: int = 1536) -> Tensor:
+    """[3, size, size] in 0..255: multi-octave smooth noise, the 'object' texture on the plane z = 0."""
+    g = _gen(seed)
+    tex = torch.zeros(3, size, size)
+    for cells, amp in ((6, 1.0), (24, 0.7), (96, 0.45), (384, 0.25)):
+        n = torch.randn(1, 3, cells, cells, generator=g)
+        tex += amp * tF.interpolate(n, size=(size, size), mode='bicubic', align_corners=False)[0]
+    tex = (tex - tex.mean()) / tex.std()
+    return (torch.sigmoid(1.2 * tex) * 255.0).contiguous()
+
+
+def render_plane(tex: Tensor, cam: Tensor, R: Tensor, t: Tensor, half_extent: float = 0.6) -> Tensor:
+    """Pinhole view (cam = [w,h,fx,fy,cx,cy,...], distortion ignored; world -> camera p_c = R p + t) of the
+    plane z = 0 whose square [-half_extent, half_extent]^2 carries `tex`.  Returns uint8 [h, w, 3] (outside
+    the square: mid grey), i.e. what the NeRF render / the camera frame would hand to the extractor."""
+    w, h = int(cam[0]), int(cam[1])
+    R, t = R.double(), t.double()
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float64), torch.arange(w, dtype=torch.float64), indexing='ij')
+    d = torch.stack([(xs - float(cam[4])) / float(cam[2]), (ys - float(cam[5])) / float(cam[3]), torch.ones_like(xs)], -1)
+    dw = d @ R                      # R^T d for every pixel (row vectors)
+    c = -(R.t() @ t)                # camera centre in world
+    lam = -c[2] / dw[..., 2]
+    P = c + lam[..., None] * dw     # intersection with z = 0
+    g = (P[..., :2] / half_extent).float()
+    img = tF.grid_sample(tex[None], g[None], mode='bilinear', padding_mode='zeros', align_corners=False)[0]
+    inside = ((g.abs() <= 1).all(-1) & (lam > 0))[None]
+    img = torch.where(inside, img, torch.full_like(img, 127.0))
+    return img.permute(1, 2, 0).round().clamp(0, 255).to(torch.uint8).contiguous()
+
+
+def tracked_sequence(seed: int, n_frames: int = 4, N: int = 5000, n_views: int = 8, query_wh=(1920, 1080),
+                     ref_wh=(1008, 756), rot_deg: float = 1.0, trans: float = 0.005) -> Dict:
+    """A short tracked sequence with REAL pixels (BASELINE config 2 restated): one textured
+    plane carrying N model points, and per frame a query image (1920x1080 camera frame) plus the
+    reference-view render r9 makes at the previous pose estimate with the SfM camera x 0.5 (1008x756;
+    reference pixtrack/pose_trackers/pixloc_tracker_r9.py:145-160), and n_views perturbed initial poses.
+    Everything the per-frame hot path consumes: images (uint8 HWC), cameras at image resolution,
+    world->camera poses (float64), points (float64)."""
+    tex = plane_texture(seed * 3 + 1)
+    g = _gen(seed * 3 + 2)
+    p = torch.zeros(N, 3, dtype=torch.float64)
+    p[:, :2] = (torch.rand(N, 2, generator=g, dtype=torch.float64) - 0.5) * 0.5       # central 0.5 m square
+    cam_q, cam_r = pixtrack_camera(*query_wh), pixtrack_camera(*ref_wh)
+    cam_q[6:] = 0
+    cam_r[6:] = 0
+    base = torch.rand(6, generator=g, dtype=torch.float64) - 0.5
+    frames = []
+    for f in range(n_frames):
+        d = (torch.rand(12, generator=g, dtype=torch.float64) - 0.5)
+        aq = torch.stack([0.25 * base[0] + 0.03 * d[0], 0.25 * base[1] + 0.03 * d[1], 0.3 * base[2] + 0.03 * d[2]])
+        R_q = axis_angle_to_R(aq)
+        t_q = torch.stack([0.05 * base[3] + 0.01 * d[3], 0.05 * base[4] + 0.01 * d[4], 1.25 + 0.1 * base[5] + 0.01 * d[5]])
+        R_r = axis_angle_to_R(aq + 0.02 * d[6:9])                # render pose = a nearby earlier estimate
+        t_r = t_q + 0.01 * d[9:12]
+        T0 = []
+        for b in range(n_views):
+            Rb, tb = perturb_pose(R_q.float(), t_q.float(), seed * 1000 + f * 37 + b, rot_deg, trans)
+            T0.append(torch.cat([Rb.reshape(-1), tb]))
+        frames.append(dict(img_q=render_plane(tex, cam_q, R_q, t_q), img_r=render_plane(tex, cam_r, R_r, t_r),
+                           R_q=R_q, t_q=t_q, R_r=R_r, t_r=t_r, T_init=torch.stack(T0)))
+    return dict(frames=frames, cam_q=cam_q.double(), cam_r=cam_r.double(), p3d=p)
