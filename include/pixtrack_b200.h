@@ -240,6 +240,61 @@ int ptk_extractor_profile(PtkExtractor* e, const void* image, int32_t img_dtype,
 int ptk_extractor_activation(const PtkExtractor* e, int32_t kind, int32_t index, const void** ptr, int32_t* C,
                              int32_t* H, int32_t* W);
 
+/* ------------------------------------------------------------------------
+ * NeRF reference-view render (instant-ngp hash grid + fused MLPs + occupancy
+ * marching + compositing) as one persistent launch.
+ *
+ * Replaces pyngp Testbed.render(width, height, spp, linear=True)
+ *   instant-ngp/src/python_api.cu:127-173,352 -> Testbed::render_frame
+ *   (src/testbed.cu:2591-2749) -> render_nerf / NerfTracer
+ *   (src/testbed_nerf.cu:606-955,1721-2146,2228-2330) and
+ *   NerfNetwork::inference_mixed_precision_impl (nerf_network.h:101-136) with
+ *   tiny-cuda-nn's kernel_grid / kernel_sh / kernel_mlp_fused,
+ * as called by get_nerf_image (pixtrack/visualization/run_vis_on_poses.py:28-57)
+ * with the testbed settings of pixtrack/utils/ingp_utils.py:22-44
+ * (snap_to_pixel_centers, fov_axis 0, exposure 0, identity tone curve).
+ *
+ * PtkNerfModel: an unpacked snapshot for the configs/nerf/base.json network
+ *   (16-level hash grid F=2 T=2^19 base 16, density MLP 32-64-16, rgb MLP
+ *   32-64-64-3, ReLU, SH degree 4).  grid: fp16 [n_grid_entries][2]; weights:
+ *   fp16 row-major [out][in]: density [64][32], [16][64]; rgb [64][32],
+ *   [64][64], [16][64]; bitfield: uint8 [8 * 128^3 / 8] occupancy bits, Morton
+ *   order per cascade (density_grid_bitfield).  The arrays must stay alive.
+ * PtkNerfView: camera = 3x4 row-major camera-to-world in NGP convention
+ *   (NerfDataset::nerf_matrix_to_ngp applied); focal in pixels (both axes);
+ *   background already in linear colour; depth_mode 0 = Shade, 1 = Depth.
+ * Outputs (any may be NULL except that one of rgba/u8 is required):
+ *   rgba float [H][W][4] (what Testbed.render returns), u8 [H][W][3] =
+ *   (rgb * 255).astype(uint8) (what get_nerf_image returns), depth [H][W].
+ * ---------------------------------------------------------------------- */
+typedef struct PtkNerfModel {
+  const void* grid;
+  int64_t n_grid_entries;
+  const void* weights[5];
+  const uint8_t* bitfield;
+  int32_t aabb_scale;
+  int32_t reserved0;
+} PtkNerfModel;
+
+typedef struct PtkNerfView {
+  float camera[12];
+  float render_aabb_min[3];
+  float render_aabb_max[3];
+  float focal;
+  float depth_scale;        /* 1 / dataset scale */
+  float min_transmittance;  /* testbed.nerf.rendering_min_transmittance */
+  float background[4];
+  int32_t width, height, spp, depth_mode;
+} PtkNerfView;
+
+typedef struct PtkNerf PtkNerf;
+int ptk_nerf_create(PtkContext* ctx, const PtkNerfModel* model, PtkNerf** out);
+void ptk_nerf_destroy(PtkNerf* n);
+/* hash-grid entries (of 2 fp16 features) the base.json encoding has at this aabb_scale (host only) */
+int64_t ptk_nerf_grid_entries(int32_t aabb_scale);
+int ptk_nerf_render(PtkNerf* n, const PtkNerfView* view, float* out_rgba, uint8_t* out_u8, float* out_depth,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

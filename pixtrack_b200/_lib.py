@@ -51,6 +51,18 @@ class RefLevel(C.Structure):
                 ('normalize', C.c_int32)]
 
 
+class NerfModelStruct(C.Structure):
+    _fields_ = [('grid', C.c_void_p), ('n_grid_entries', C.c_int64), ('weights', C.c_void_p * 5),
+                ('bitfield', C.c_void_p), ('aabb_scale', C.c_int32), ('reserved0', C.c_int32)]
+
+
+class NerfView(C.Structure):
+    _fields_ = [('camera', C.c_float * 12), ('render_aabb_min', C.c_float * 3), ('render_aabb_max', C.c_float * 3),
+                ('focal', C.c_float), ('depth_scale', C.c_float), ('min_transmittance', C.c_float),
+                ('background', C.c_float * 4), ('width', C.c_int32), ('height', C.c_int32), ('spp', C.c_int32),
+                ('depth_mode', C.c_int32)]
+
+
 class LmResult(C.Structure):
     _fields_ = [('T', C.c_void_p), ('failed', C.c_void_p), ('n_iters', C.c_void_p), ('log', C.c_void_p)]
 
@@ -84,6 +96,10 @@ SYMBOLS = {
                                         C.POINTER(C.c_double), c_i32p]),
     'ptk_extractor_activation': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_i32p, c_i32p,
                                            c_i32p]),
+    'ptk_nerf_create': (C.c_int, [C.c_void_p, C.POINTER(NerfModelStruct), C.POINTER(C.c_void_p)]),
+    'ptk_nerf_destroy': (None, [C.c_void_p]),
+    'ptk_nerf_grid_entries': (C.c_int64, [C.c_int32]),
+    'ptk_nerf_render': (C.c_int, [C.c_void_p, C.POINTER(NerfView), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ptk_copy_d2d': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'ptk_chw_to_hwc': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p]),

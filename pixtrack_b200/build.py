@@ -18,7 +18,10 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(HERE, '_build')
 LIB = os.path.join(HERE, 'libpixtrack_b200.so')
-SOURCES = ('ptk_api.cu', 'ptk_lm.cu', 'ptk_sample.cu', 'ptk_sample_ref.cu', 'ptk_conv.cu', 'ptk_unet.cu')
+SOURCES = ('ptk_api.cu', 'ptk_lm.cu', 'ptk_sample.cu', 'ptk_sample_ref.cu', 'ptk_conv.cu', 'ptk_unet.cu', 'ptk_nerf.cu')
+# per-file extra flags: the NeRF marcher is compiled without FMA contraction so that its geometric decisions
+# (voxel stepping, occupancy tests) are the same IEEE operation sequence as the numpy oracle
+EXTRA_FLAGS = {'ptk_nerf.cu': ['-fmad=false']}
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 
@@ -31,7 +34,7 @@ def _nvcc() -> str:
 
 
 def _digest() -> str:
-    h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    h = hashlib.sha256((' '.join(NVCC_FLAGS) + repr(sorted(EXTRA_FLAGS.items()))).encode())
     names = sorted(os.listdir(CSRC)) + ['../../include/pixtrack_b200.h']
     for n in names:
         with open(os.path.join(CSRC, n), 'rb') as f:
@@ -50,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     log = []
     for src in SOURCES:
         obj = os.path.join(BUILD, src.replace('.cu', '.o'))
-        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), '-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)
         if r.returncode != 0:

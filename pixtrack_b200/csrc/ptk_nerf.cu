@@ -1,0 +1,708 @@
+// Instant-NGP reference-view render for sm_100a: ONE persistent launch per image does ray
+// generation, occupancy-grid marching, the 16-level hash-grid lookup, the two tiny MLPs, alpha
+// compositing, the spp accumulation and the tone-map epilogue -- no host round trip per march
+// round (the reference reads `n_alive` back after every compaction, testbed_nerf.cu:2085-2086).
+//
+// Replaces (paths relative to /root/reference/instant-ngp):
+//   Testbed::render_to_cpu                     src/python_api.cu:127-173
+//   Testbed::render_frame / render_nerf        src/testbed.cu:2591-2749, src/testbed_nerf.cu:2228-2330
+//   init_rays_with_payload_kernel_nerf         src/testbed_nerf.cu:1781-1890  (+ pixel_to_ray,
+//                                              include/neural-graphics-primitives/common_device.cuh:260-307)
+//   advance_pos_nerf                           :606-657
+//   generate_next_nerf_network_inputs          :693-752
+//   NerfNetwork::inference_mixed_precision_impl include/neural-graphics-primitives/nerf_network.h:101-136
+//     kernel_grid          dependencies/tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:81-116,139-275
+//     kernel_sh            .../encodings/spherical_harmonics.h:47-93
+//     kernel_mlp_fused     dependencies/tiny-cuda-nn/src/fully_fused_mlp.cu:55-140,501-557
+//   composite_kernel_nerf                      :754-955
+//   compact_kernel_nerf / shade_kernel_nerf    :1721-1779
+//   accumulate_kernel / tonemap_kernel         src/render_buffer.cu:236-275,542-570
+// as driven by pixtrack/visualization/run_vis_on_poses.py:28-57 with the settings of
+// pixtrack/utils/ingp_utils.py:22-44 (snap_to_pixel_centers, linear output, Shade or Depth mode).
+//
+// Mapping to the machine
+//  * Every (pixel, sample) ray is independent; the reference's march rounds + stream compaction
+//    only exist to keep its separate kernels busy.  Here a LANE owns a pixel and walks its spp rays
+//    one after the other; a lane whose pixel is finished takes the next pixel from a global atomic
+//    counter (warp-aggregated), so warps stay full without compaction and without the host.
+//  * One warp evaluates the network for its 32 current samples: each lane gathers the 16 x 8 hash
+//    grid corners of its own sample (4-byte random gathers; the 24-49 MB table is L2-resident on
+//    B200's 126 MB L2), the 32 x 32 feature tile goes through shared memory into mma.sync
+//    m16n8k16 fragments, and the five layers are chained in registers (the accumulator fragment of
+//    one layer is the A fragment of the next).  Weights (20 KB fp16) sit in shared memory.
+//    The layers are 32/64 wide: too thin for a 128-row tcgen05 tile per warp, and the kernel is
+//    bound by the gathers and the marching, not by the MMAs.
+//  * fp16 operands, fp32 accumulation, one rounding to fp16 per layer (tiny-cuda-nn accumulates in
+//    fp16 inside wmma fragments; see oracle/nerf.py header).  Hash-grid interpolation accumulates in
+//    fp16 exactly like kernel_grid.
+//  * The marching / compositing arithmetic is compiled with -fmad=false (see build.py) so that it
+//    is the same sequence of IEEE operations as the numpy oracle.
+#include <cuda_fp16.h>
+
+#include "ptk_common.cuh"
+
+namespace {
+
+constexpr int kGrid = 128;                 // NERF_GRIDSIZE
+constexpr int kCascades = 8;               // NERF_CASCADES
+constexpr float kNear = 0.05f;             // NERF_RENDERING_NEAR_DISTANCE
+constexpr float kSqrt3 = 1.73205080757f;
+constexpr float kMinStep = kSqrt3 / 1024.f;                                   // MIN_CONE_STEPSIZE
+constexpr float kMaxStep = kMinStep * (1 << (kCascades - 1)) * 1024.f / kGrid;  // MAX_CONE_STEPSIZE
+constexpr float kWarpDtSpan = kMinStep * (1 << (kCascades - 1)) - kMinStep;   // warp_dt / unwarp_dt
+constexpr int kMaxSteps = 10000;           // MARCH_ITER
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+
+// padded shared-memory strides (halfs): conflict-free 32-bit fragment loads
+constexpr int kS32 = 40, kS64 = 72, kSsh = 24;
+constexpr int kOffWd1 = 0;                         // [64][kS32]
+constexpr int kOffWd2 = kOffWd1 + 64 * kS32;       // [16][kS64]
+constexpr int kOffWc1 = kOffWd2 + 16 * kS64;       // [64][kS32]
+constexpr int kOffWc2 = kOffWc1 + 64 * kS32;       // [64][kS64]
+constexpr int kOffWc3 = kOffWc2 + 64 * kS64;       // [8][kS64]   (rows 0..2 = r, g, b)
+constexpr int kWeightHalfs = kOffWc3 + 8 * kS64;
+constexpr int kWarpHalfs = 32 * kS32 + 32 * kSsh;  // feature tile + SH tile
+constexpr int kSmemBytes = kWeightHalfs * 2 + kWarpsPerCta * (kWarpHalfs * 2 + 32 * 4 * 4);
+
+struct NerfLevel {
+  float scale;
+  uint32_t res;
+  uint32_t offset;
+  uint32_t size;
+  uint32_t hashed;
+};
+
+struct NerfParams {
+  const __half2* grid;
+  const uint8_t* bitfield;
+  const __half* w[5];            // density [64][32], [16][64]; rgb [64][32], [64][64], [16][64]
+  NerfLevel lv[16];
+  float cam[12];                 // 3x4 row-major, NGP convention
+  float tmin[3], tmax[3];        // training box (m_aabb)
+  float rmin[3], rmax[3];        // render box
+  float cone, focal, depth_scale, one_minus_min_T;
+  float bg[4];                   // background, already linear
+  int W, H, spp, depth_mode;
+  float4* out_rgba;              // [H][W] or null
+  uint8_t* out_u8;               // [H][W][3] or null
+  float* out_depth;              // [H][W] or null
+  unsigned* counter;             // pixel queue
+};
+
+struct V3 {
+  float x, y, z;
+};
+
+__device__ __forceinline__ uint32_t rev32(uint32_t x) { return __brev(x); }
+__device__ __forceinline__ uint32_t laine_karras(uint32_t x, uint32_t seed) {
+  x += seed;
+  x ^= x * 0x6c50b47cu;
+  x ^= x * 0xb82f1e52u;
+  x ^= x * 0xc7afe638u;
+  x ^= x * 0x8d22f6e6u;
+  return x;
+}
+__device__ __forceinline__ uint32_t owen(uint32_t x, uint32_t seed) { return rev32(laine_karras(rev32(x), seed)); }
+// random_val.cuh:284-288 with dim 0, where sobol(i, 0) is the base-2 radical inverse.
+__device__ __forceinline__ float ld_random_val(uint32_t index, uint32_t seed) {
+  index = owen(index, seed);
+  const uint32_t hc = seed ^ (0u + (seed << 6) + (seed >> 2));
+  return (float)owen(rev32(index), hc) * (1.0f / 4294967296.0f);
+}
+
+__device__ __forceinline__ float calc_dt(float t, float cone) { return fmaxf(kMinStep, fminf(kMaxStep, t * cone)); }
+
+__device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+
+__device__ __forceinline__ int mip_from_pos(const V3& p) {
+  const float mx = fmaxf(fmaxf(fabsf(p.x - 0.5f), fabsf(p.y - 0.5f)), fabsf(p.z - 0.5f));
+  int e;
+  frexpf(mx, &e);
+  return min(kCascades - 1, max(0, e + 1));
+}
+
+__device__ __forceinline__ int mip_from_dt(float dt, const V3& p) {
+  const int mip = mip_from_pos(p);
+  dt *= 2 * kGrid;
+  if (dt < 1.f) return mip;
+  int e;
+  frexpf(dt, &e);
+  return min(kCascades - 1, max(e, mip));
+}
+
+__device__ __forceinline__ bool occupied(const uint8_t* __restrict__ bits, const V3& p, int mip) {
+  const float s = scalbnf(1.0f, -mip);
+  const int ix = (int)(((p.x - 0.5f) * s + 0.5f) * kGrid);
+  const int iy = (int)(((p.y - 0.5f) * s + 0.5f) * kGrid);
+  const int iz = (int)(((p.z - 0.5f) * s + 0.5f) * kGrid);
+  const uint32_t idx = expand_bits(min(max(ix, 0), kGrid - 1)) | (expand_bits(min(max(iy, 0), kGrid - 1)) << 1) |
+                       (expand_bits(min(max(iz, 0), kGrid - 1)) << 2);
+  return (__ldg(bits + idx / 8 + (size_t)mip * (kGrid * kGrid * kGrid / 8)) >> (idx & 7)) & 1;
+}
+
+__device__ __forceinline__ bool inside(const float* lo, const float* hi, const V3& p) {
+  return p.x >= lo[0] && p.x <= hi[0] && p.y >= lo[1] && p.y <= hi[1] && p.z >= lo[2] && p.z <= hi[2];
+}
+
+// Advance t to the next sample position in an occupied cell (common loop of advance_pos_nerf and
+// generate_next_nerf_network_inputs).  Returns false when the ray left the render box.
+__device__ __forceinline__ bool skip_empty(const NerfParams& P, const V3& o, const V3& d, const V3& id, float& t, V3& pos,
+                                           float& dt) {
+  while (true) {
+    pos.x = o.x + d.x * t;
+    pos.y = o.y + d.y * t;
+    pos.z = o.z + d.z * t;
+    if (!inside(P.rmin, P.rmax, pos)) return false;
+    dt = calc_dt(t, P.cone);
+    const int mip = mip_from_dt(dt, pos);
+    if (occupied(P.bitfield, pos, mip)) return true;
+    const float res = (float)(kGrid >> mip);
+    const float px = res * pos.x, py = res * pos.y, pz = res * pos.z;
+    const float tx = (floorf(px + 0.5f + 0.5f * copysignf(1.f, d.x)) - px) * id.x;
+    const float ty = (floorf(py + 0.5f + 0.5f * copysignf(1.f, d.y)) - py) * id.y;
+    const float tz = (floorf(pz + 0.5f + 0.5f * copysignf(1.f, d.z)) - pz) * id.z;
+    const float target = t + fmaxf(fminf(fminf(tx, ty), tz) / res, 0.f);
+    do {
+      t += calc_dt(t, P.cone);
+    } while (t < target);
+  }
+}
+
+__device__ __forceinline__ float srgb_to_linear(float s) {
+  return s <= 0.04045f ? s / 12.92f : powf((s + 0.055f) / 1.055f, 2.4f);
+}
+
+// ---- network ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// C[32 x N] = A[32 x K] * W[N x K]^T for one warp: A as two m16 tiles of K/16 fragments,
+// W in shared memory with row stride WS halfs.
+template <int K, int N, int WS>
+__device__ __forceinline__ void layer(const uint32_t (&a)[2][K / 16][4], const __half* __restrict__ w, int lane,
+                                      float (&c)[2][N / 8][4]) {
+  const int n_in = lane >> 2, k_in = (lane & 3) * 2;
+#pragma unroll
+  for (int nt = 0; nt < N / 8; ++nt) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < K / 16; ++kk) {
+      const __half* wr = w + (nt * 8 + n_in) * WS + kk * 16 + k_in;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+      mma16816(c[0][nt], a[0][kk], b0, b1);
+      mma16816(c[1][nt], a[1][kk], b0, b1);
+    }
+  }
+}
+
+// accumulator fragments of a layer (fp32) -> A fragments of the next one (fp16), optional ReLU
+template <int N, bool kRelu>
+__device__ __forceinline__ void to_a(const float (&c)[2][N / 8][4], uint32_t (&a)[2][N / 16][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int kk = 0; kk < N / 16; ++kk)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v0 = c[mt][2 * kk + h][0], v1 = c[mt][2 * kk + h][1], v2 = c[mt][2 * kk + h][2], v3 = c[mt][2 * kk + h][3];
+        if (kRelu) {
+          v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+        }
+        a[mt][kk][2 * h] = pack_h2(v0, v1);
+        a[mt][kk][2 * h + 1] = pack_h2(v2, v3);
+      }
+}
+
+template <int KS, int STRIDE>
+__device__ __forceinline__ void load_a(const __half* __restrict__ tile, int lane, int k0, uint32_t (&a)[4], int mt) {
+  const int r = mt * 16 + (lane >> 2), c = k0 + (lane & 3) * 2;
+  a[0] = *reinterpret_cast<const uint32_t*>(tile + r * STRIDE + c);
+  a[1] = *reinterpret_cast<const uint32_t*>(tile + (r + 8) * STRIDE + c);
+  a[2] = *reinterpret_cast<const uint32_t*>(tile + r * STRIDE + c + 8);
+  a[3] = *reinterpret_cast<const uint32_t*>(tile + (r + 8) * STRIDE + c + 8);
+}
+
+// hash-grid features of one sample -> 32 halfs in the warp's feature tile row (kernel_grid)
+__device__ __forceinline__ void hash_encode(const NerfParams& P, float x, float y, float z, __half* __restrict__ row) {
+#pragma unroll 4
+  for (int l = 0; l < 16; ++l) {
+    const NerfLevel lv = P.lv[l];
+    const float fx = x * lv.scale + 0.5f, fy = y * lv.scale + 0.5f, fz = z * lv.scale + 0.5f;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const uint32_t gx = (uint32_t)(int)flx, gy = (uint32_t)(int)fly, gz = (uint32_t)(int)flz;
+    const float wx = fx - flx, wy = fy - fly, wz = fz - flz;
+    const __half2* g = P.grid + lv.offset;
+    __half2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t cx = gx + (c & 1), cy = gy + ((c >> 1) & 1), cz = gz + (c >> 2);
+      uint32_t idx;
+      if (lv.hashed) idx = (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) % lv.size;
+      else idx = (cx + cy * lv.res + cz * lv.res * lv.res) % lv.size;
+      v[c] = __ldg(g + idx);
+    }
+    __half ax = __float2half(0.f), ay = __float2half(0.f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float w = 1.f;
+      w *= (c & 1) ? wx : 1.f - wx;
+      w *= (c & 2) ? wy : 1.f - wy;
+      w *= (c & 4) ? wz : 1.f - wz;
+      const float2 f = __half22float2(v[c]);
+      ax = __hadd(ax, __float2half_rn(w * f.x));
+      ay = __hadd(ay, __float2half_rn(w * f.y));
+    }
+    *reinterpret_cast<__half2*>(row + 2 * l) = __halves2half2(ax, ay);
+  }
+}
+
+// degree-4 spherical harmonics of the direction (kernel_sh); the direction goes through
+// warp_direction / the "* 2 - 1" of the encoder like in the reference
+__device__ __forceinline__ void sh_encode(const V3& d, __half* __restrict__ row) {
+  const float x = ((d.x + 1.f) * 0.5f) * 2.f - 1.f, y = ((d.y + 1.f) * 0.5f) * 2.f - 1.f, z = ((d.z + 1.f) * 0.5f) * 2.f - 1.f;
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  float o[16];
+  o[0] = 0.28209479177387814f;
+  o[1] = -0.48860251190291987f * y;
+  o[2] = 0.48860251190291987f * z;
+  o[3] = -0.48860251190291987f * x;
+  o[4] = 1.0925484305920792f * xy;
+  o[5] = -1.0925484305920792f * yz;
+  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  o[7] = -1.0925484305920792f * xz;
+  o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+  o[10] = 2.8906114426405538f * xy * z;
+  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+  o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+  o[14] = 1.4453057213202769f * z * (x2 - y2);
+  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) *reinterpret_cast<__half2*>(row + i) = __floats2half2_rn(o[i], o[i + 1]);
+}
+
+__device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+
+// Network for the warp's 32 samples.  feat / sh tiles are filled by the lanes; out[lane] =
+// (raw r, raw g, raw b, raw density), each rounded to fp16 like the reference's network output.
+__device__ __forceinline__ void run_network(const __half* __restrict__ wts, const __half* __restrict__ feat,
+                                            const __half* __restrict__ sh, float4* __restrict__ out, int lane,
+                                            bool want_rgb) {
+  uint32_t a32[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) load_a<32, kS32>(feat, lane, kk * 16, a32[mt][kk], mt);
+  uint32_t a64[2][4][4];
+  {
+    float c[2][8][4];
+    layer<32, 64, kS32>(a32, wts + kOffWd1, lane, c);
+    to_a<64, true>(c, a64);
+  }
+  float cd[2][2][4];
+  layer<64, 16, kS64>(a64, wts + kOffWd2, lane, cd);
+  const int r = lane >> 2, q = lane & 3;
+  if (q == 0) {
+    out[r].w = round_h(cd[0][0][0]);
+    out[r + 8].w = round_h(cd[0][0][2]);
+    out[r + 16].w = round_h(cd[1][0][0]);
+    out[r + 24].w = round_h(cd[1][0][2]);
+  }
+  if (!want_rgb) return;
+  {
+    uint32_t ad[2][1][4];
+    to_a<16, false>(cd, ad);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a32[mt][0][i] = ad[mt][0][i];
+      load_a<16, kSsh>(sh, lane, 0, a32[mt][1], mt);
+    }
+  }
+  {
+    float c[2][8][4];
+    layer<32, 64, kS32>(a32, wts + kOffWc1, lane, c);
+    to_a<64, true>(c, a64);
+  }
+  {
+    float c[2][8][4];
+    layer<64, 64, kS64>(a64, wts + kOffWc2, lane, c);
+    to_a<64, true>(c, a64);
+  }
+  float c3[2][1][4];
+  layer<64, 8, kS64>(a64, wts + kOffWc3, lane, c3);
+  if (q == 0) {
+    out[r].x = round_h(c3[0][0][0]); out[r].y = round_h(c3[0][0][1]);
+    out[r + 8].x = round_h(c3[0][0][2]); out[r + 8].y = round_h(c3[0][0][3]);
+    out[r + 16].x = round_h(c3[1][0][0]); out[r + 16].y = round_h(c3[1][0][1]);
+    out[r + 24].x = round_h(c3[1][0][2]); out[r + 24].y = round_h(c3[1][0][3]);
+  } else if (q == 1) {
+    out[r].z = round_h(c3[0][0][0]);
+    out[r + 8].z = round_h(c3[0][0][2]);
+    out[r + 16].z = round_h(c3[1][0][0]);
+    out[r + 24].z = round_h(c3[1][0][2]);
+  }
+}
+
+// ---- the render kernel ---------------------------------------------------------------------------
+struct Ray {
+  int pix;          // -1: no pixel
+  int s;            // current sample-per-pixel index
+  int steps;
+  bool alive;
+  V3 d, id;
+  float t, tentry;
+  float r, g, b, a; // this sample's compositing state
+  float maxw, dep;
+  float ar, ag, ab, aa, adep;   // running mean over spp
+};
+
+__device__ __forceinline__ void start_spp(const NerfParams& P, const V3& o, Ray& ry) {
+  ry.r = ry.g = ry.b = ry.a = 0.f;
+  ry.maxw = 0.f;
+  ry.dep = 0.f;
+  ry.steps = 1;
+  float t = fmaxf(ry.tentry, kNear) + 1e-6f;
+  V3 p;
+  p.x = o.x + ry.d.x * t;
+  p.y = o.y + ry.d.y * t;
+  p.z = o.z + ry.d.z * t;
+  ry.alive = inside(P.rmin, P.rmax, p);
+  if (ry.alive) {   // advance_pos_nerf: jittered start, then on to the first occupied cell
+    t += ld_random_val((uint32_t)ry.s, (uint32_t)ry.pix * 786433u) * calc_dt(t, P.cone);
+    float dt;
+    ry.alive = skip_empty(P, o, ry.d, ry.id, t, p, dt);
+  }
+  ry.t = t;
+}
+
+__device__ __forceinline__ void finish_spp(const NerfParams& P, Ray& ry) {
+  float fr = 0.f, fg = 0.f, fb = 0.f, fa = 0.f, fd = 0.f;
+  if (ry.a > 0.001f) {   // compact_kernel_nerf keeps a finished ray only above this alpha
+    fr = ry.r; fg = ry.g; fb = ry.b; fa = ry.a;
+    if (!P.depth_mode) {   // shade_kernel_nerf: accumulate in linear colours
+      fr = srgb_to_linear(fr); fg = srgb_to_linear(fg); fb = srgb_to_linear(fb);
+    }
+    if (ry.a > 0.2f) fd = ry.dep;
+  }
+  const float n = (float)ry.s;
+  ry.ar = (ry.ar * n + fr) / (n + 1.f);   // accumulate_kernel
+  ry.ag = (ry.ag * n + fg) / (n + 1.f);
+  ry.ab = (ry.ab * n + fb) / (n + 1.f);
+  ry.aa = (ry.aa * n + fa) / (n + 1.f);
+  ry.adep = fd;
+}
+
+__device__ __forceinline__ void write_pixel(const NerfParams& P, const Ray& ry) {
+  const float w = (1.f - ry.aa) * P.bg[3];   // tonemap_kernel, linear in / linear out, identity curve
+  const float r = ry.ar + P.bg[0] * w, g = ry.ag + P.bg[1] * w, b = ry.ab + P.bg[2] * w, a = ry.aa + w;
+  if (P.out_rgba) P.out_rgba[ry.pix] = make_float4(r, g, b, a);
+  if (P.out_u8) {   // run_vis_on_poses.py:52-54: (rgb * 255).astype(uint8)
+    uint8_t* o = P.out_u8 + (size_t)ry.pix * 3;
+    o[0] = (uint8_t)((int)(r * 255.f) & 0xFF);
+    o[1] = (uint8_t)((int)(g * 255.f) & 0xFF);
+    o[2] = (uint8_t)((int)(b * 255.f) & 0xFF);
+  }
+  if (P.out_depth) P.out_depth[ry.pix] = ry.adep;
+}
+
+// Runs dead samples to completion: finish the sample, start the next one, until a live ray or the
+// end of the pixel (which is then written and released).
+__device__ __forceinline__ void drain(const NerfParams& P, const V3& o, Ray& ry) {
+  while (ry.pix >= 0 && !ry.alive) {
+    finish_spp(P, ry);
+    ++ry.s;
+    if (ry.s < P.spp) {
+      start_spp(P, o, ry);
+    } else {
+      write_pixel(P, ry);
+      ry.pix = -1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) nerf_render_kernel(const __grid_constant__ NerfParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __half* wts = reinterpret_cast<__half*>(smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* wbase = smem + kWeightHalfs * 2 + warp * (kWarpHalfs * 2 + 32 * 16);
+  __half* feat = reinterpret_cast<__half*>(wbase);
+  __half* sh = feat + 32 * kS32;
+  float4* outv = reinterpret_cast<float4*>(wbase + kWarpHalfs * 2);
+
+  // weights -> padded shared memory
+  for (int i = threadIdx.x; i < 64 * 32; i += kThreads) {
+    wts[kOffWd1 + (i >> 5) * kS32 + (i & 31)] = P.w[0][i];
+    wts[kOffWc1 + (i >> 5) * kS32 + (i & 31)] = P.w[2][i];
+  }
+  for (int i = threadIdx.x; i < 16 * 64; i += kThreads) wts[kOffWd2 + (i >> 6) * kS64 + (i & 63)] = P.w[1][i];
+  for (int i = threadIdx.x; i < 64 * 64; i += kThreads) wts[kOffWc2 + (i >> 6) * kS64 + (i & 63)] = P.w[3][i];
+  for (int i = threadIdx.x; i < 8 * 64; i += kThreads) wts[kOffWc3 + (i >> 6) * kS64 + (i & 63)] = P.w[4][i];
+  __syncthreads();
+
+  const unsigned full = 0xffffffffu;
+  const int npix = P.W * P.H;
+  const V3 o = {P.cam[3], P.cam[7], P.cam[11]};
+  const V3 fwd = {P.cam[2], P.cam[6], P.cam[10]};
+  Ray ry;
+  ry.pix = -1;
+  ry.alive = false;
+  bool exhausted = false;
+
+  while (true) {
+    // ---- take new pixels until every lane has a live ray or the queue is empty (pixels whose rays
+    //      all miss are finished right here) -------------------------------------------------------
+#pragma unroll 1
+    while (true) {
+      const bool need = ry.pix < 0 && !exhausted;
+      const unsigned m = __ballot_sync(full, need);
+      if (m == 0) break;
+      unsigned base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(P.counter, (unsigned)__popc(m));
+      base = __shfl_sync(full, base, __ffs(m) - 1);
+      if (need) {
+        const unsigned mine = base + __popc(m & ((1u << lane) - 1u));
+        if (mine < (unsigned)npix) {
+          ry.pix = (int)mine;
+          ry.s = 0;
+          ry.ar = ry.ag = ry.ab = ry.aa = ry.adep = 0.f;
+          const int px = ry.pix % P.W, py = ry.pix / P.W;
+          // pixel_to_ray with snap_to_pixel_centers (offset 0.5), screen centre 0.5, no parallax
+          const float u = ((float)px + 0.5f) / (float)P.W, v = ((float)py + 0.5f) / (float)P.H;
+          const float cx = (u - 0.5f) * (float)P.W / P.focal, cy = (v - 0.5f) * (float)P.H / P.focal;
+          V3 d;
+          d.x = (cx * P.cam[0] + cy * P.cam[1]) + P.cam[2];
+          d.y = (cx * P.cam[4] + cy * P.cam[5]) + P.cam[6];
+          d.z = (cx * P.cam[8] + cy * P.cam[9]) + P.cam[10];
+          const float nrm = sqrtf((d.x * d.x + d.y * d.y) + d.z * d.z);
+          d.x /= nrm; d.y /= nrm; d.z /= nrm;
+          ry.d = d;
+          ry.id.x = 1.f / d.x; ry.id.y = 1.f / d.y; ry.id.z = 1.f / d.z;
+          // BoundingBox::ray_intersect, entry distance
+          float t0 = (P.rmin[0] - o.x) / d.x, t1 = (P.rmax[0] - o.x) / d.x;
+          float tmin = fminf(t0, t1), tmax = fmaxf(t0, t1);
+          bool miss = false;
+          t0 = (P.rmin[1] - o.y) / d.y; t1 = (P.rmax[1] - o.y) / d.y;
+          float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
+          miss = miss || (tmin > hi) || (lo > tmax);
+          tmin = lo > tmin ? lo : tmin; tmax = hi < tmax ? hi : tmax;
+          t0 = (P.rmin[2] - o.z) / d.z; t1 = (P.rmax[2] - o.z) / d.z;
+          lo = fminf(t0, t1); hi = fmaxf(t0, t1);
+          miss = miss || (tmin > hi) || (lo > tmax);
+          tmin = lo > tmin ? lo : tmin;
+          ry.tentry = miss ? 3.402823466e+38f : tmin;
+          start_spp(P, o, ry);
+          drain(P, o, ry);
+        } else {
+          exhausted = true;
+        }
+      }
+    }
+    if (__ballot_sync(full, ry.pix >= 0) == 0) break;
+
+    // ---- next sample of every live ray ------------------------------------------------------------
+    bool sample = false;
+    V3 pos = {0.f, 0.f, 0.f};
+    float dt = 0.f;
+    if (ry.pix >= 0 && ry.alive) {
+      sample = skip_empty(P, o, ry.d, ry.id, ry.t, pos, dt);
+      if (!sample) ry.alive = false;
+    }
+    const unsigned sm = __ballot_sync(full, sample);
+    if (sm != 0) {
+      // warp_position -> network input in the unit cube of the training box
+      const float wx = (pos.x - P.tmin[0]) / (P.tmax[0] - P.tmin[0]);
+      const float wy = (pos.y - P.tmin[1]) / (P.tmax[1] - P.tmin[1]);
+      const float wz = (pos.z - P.tmin[2]) / (P.tmax[2] - P.tmin[2]);
+      if (sample) {
+        hash_encode(P, wx, wy, wz, feat + lane * kS32);
+        if (!P.depth_mode) sh_encode(ry.d, sh + lane * kSsh);
+      } else {
+        uint4* z = reinterpret_cast<uint4*>(feat + lane * kS32);
+        z[0] = z[1] = z[2] = z[3] = make_uint4(0, 0, 0, 0);
+        uint4* zs = reinterpret_cast<uint4*>(sh + lane * kSsh);
+        zs[0] = zs[1] = make_uint4(0, 0, 0, 0);
+      }
+      __syncwarp();
+      run_network(wts, feat, sh, outv, lane, P.depth_mode == 0);
+      __syncwarp();
+      if (sample) {   // composite_kernel_nerf
+        const float4 raw = outv[lane];
+        ry.t += dt;
+        const float ux = P.tmin[0] + wx * (P.tmax[0] - P.tmin[0]);     // unwarp_position
+        const float uy = P.tmin[1] + wy * (P.tmax[1] - P.tmin[1]);
+        const float uz = P.tmin[2] + wz * (P.tmax[2] - P.tmin[2]);
+        const float udt = ((dt - kMinStep) / kWarpDtSpan) * kWarpDtSpan + kMinStep;   // unwarp_dt(warp_dt(dt))
+        const float T = 1.f - ry.a;
+        const float alpha = 1.f - __expf(-__expf(raw.w) * udt);
+        const float weight = alpha * T;
+        float cr, cg, cb;
+        if (P.depth_mode) {
+          cr = cg = cb = ((fwd.x * (ux - o.x) + fwd.y * (uy - o.y)) + fwd.z * (uz - o.z)) * P.depth_scale;
+        } else {
+          cr = 1.f / (1.f + expf(-raw.x));
+          cg = 1.f / (1.f + expf(-raw.y));
+          cb = 1.f / (1.f + expf(-raw.z));
+        }
+        ry.r += cr * weight;
+        ry.g += cg * weight;
+        ry.b += cb * weight;
+        ry.a += weight;
+        if (weight > ry.maxw) {
+          ry.maxw = weight;
+          ry.dep = (fwd.x * (ux - o.x) + fwd.y * (uy - o.y)) + fwd.z * (uz - o.z);
+        }
+        if (ry.a > P.one_minus_min_T) {
+          ry.r /= ry.a; ry.g /= ry.a; ry.b /= ry.a; ry.a /= ry.a;
+          ry.alive = false;
+        }
+        if (++ry.steps >= kMaxSteps) ry.alive = false;
+      }
+      __syncwarp();
+    }
+    drain(P, o, ry);
+  }
+}
+
+}  // namespace
+
+struct PtkNerf {
+  PtkContext* ctx;
+  NerfParams base;
+  unsigned* counter;
+  int aabb_scale;
+};
+
+extern "C" int ptk_nerf_create(PtkContext* ctx, const PtkNerfModel* m, PtkNerf** out) {
+  PTK_REQUIRE(ctx && m && out, "null argument");
+  PTK_REQUIRE(m->grid && m->bitfield, "null grid / bitfield");
+  for (int i = 0; i < 5; ++i) PTK_REQUIRE(m->weights[i] != nullptr, "null weight matrix");
+  PTK_REQUIRE(m->aabb_scale >= 1 && m->aabb_scale <= 128 && (m->aabb_scale & (m->aabb_scale - 1)) == 0,
+              "aabb_scale must be a power of two in [1, 128]");
+  PtkNerf* n = (PtkNerf*)calloc(1, sizeof(PtkNerf));
+  n->ctx = ctx;
+  n->aabb_scale = m->aabb_scale;
+  NerfParams& P = n->base;
+  P.grid = (const __half2*)m->grid;
+  P.bitfield = m->bitfield;
+  for (int i = 0; i < 5; ++i) P.w[i] = (const __half*)m->weights[i];
+  // hash-grid layout: testbed.cu:2233-2244 (per_level_scale), grid.h:898-930 (offsets)
+  const float pls = expf(logf(2048.0f * (float)m->aabb_scale / 16.0f) / 15.0f);
+  const float log2pls = log2f(pls);
+  uint32_t off = 0;
+  for (int l = 0; l < 16; ++l) {
+    const float scale = exp2f((float)l * log2pls) * 16.0f - 1.0f;
+    const uint32_t res = (uint32_t)ceilf(scale) + 1u;
+    const double cube = (double)res * res * res;
+    uint64_t cnt = cube > 2147483647.0 ? 2147483647ull : (uint64_t)cube;
+    cnt = (cnt + 7) / 8 * 8;
+    if (cnt > (1u << 19)) cnt = 1u << 19;
+    P.lv[l].scale = scale;
+    P.lv[l].res = res;
+    P.lv[l].offset = off;
+    P.lv[l].size = (uint32_t)cnt;
+    P.lv[l].hashed = cube > (double)cnt ? 1u : 0u;
+    off += (uint32_t)cnt;
+  }
+  if (m->n_grid_entries != (int64_t)off) {
+    ptk_set_error("hash grid has %lld entries, aabb_scale %d needs %u", (long long)m->n_grid_entries, m->aabb_scale, off);
+    free(n);
+    return PTK_ERR_INVALID;
+  }
+  const float half = 0.5f * (float)(m->aabb_scale < 128 ? m->aabb_scale : 128);
+  for (int i = 0; i < 3; ++i) {
+    P.tmin[i] = 0.5f - half;
+    P.tmax[i] = 0.5f + half;
+  }
+  P.cone = m->aabb_scale <= 1 ? 0.f : 1.f / 256.f;   // testbed_nerf.cu:2596
+  cudaError_t e = cudaMalloc(&n->counter, sizeof(unsigned));
+  if (e != cudaSuccess) {
+    ptk_set_error("cudaMalloc: %s", cudaGetErrorString(e));
+    free(n);
+    return PTK_ERR_CUDA;
+  }
+  PTK_CUDA_CHECK(cudaFuncSetAttribute(nerf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  *out = n;
+  return PTK_OK;
+}
+
+extern "C" void ptk_nerf_destroy(PtkNerf* n) {
+  if (n == nullptr) return;
+  if (n->counter) cudaFree(n->counter);
+  free(n);
+}
+
+extern "C" int64_t ptk_nerf_grid_entries(int32_t aabb_scale) {
+  const float pls = expf(logf(2048.0f * (float)aabb_scale / 16.0f) / 15.0f);
+  const float log2pls = log2f(pls);
+  uint64_t off = 0;
+  for (int l = 0; l < 16; ++l) {
+    const float scale = exp2f((float)l * log2pls) * 16.0f - 1.0f;
+    const uint32_t res = (uint32_t)ceilf(scale) + 1u;
+    const double cube = (double)res * res * res;
+    uint64_t cnt = cube > 2147483647.0 ? 2147483647ull : (uint64_t)cube;
+    cnt = (cnt + 7) / 8 * 8;
+    if (cnt > (1u << 19)) cnt = 1u << 19;
+    off += cnt;
+  }
+  return (int64_t)off;
+}
+
+extern "C" int ptk_nerf_render(PtkNerf* n, const PtkNerfView* v, float* out_rgba, uint8_t* out_u8, float* out_depth,
+                               void* stream) {
+  PTK_REQUIRE(n && v, "null argument");
+  PTK_REQUIRE(v->width >= 1 && v->height >= 1 && v->spp >= 1, "width, height, spp must be >= 1");
+  PTK_REQUIRE(v->focal > 0.f, "focal must be positive");
+  PTK_REQUIRE(out_rgba || out_u8, "no output buffer");
+  NerfParams P = n->base;
+  for (int i = 0; i < 12; ++i) P.cam[i] = v->camera[i];
+  for (int i = 0; i < 3; ++i) {
+    P.rmin[i] = v->render_aabb_min[i];
+    P.rmax[i] = v->render_aabb_max[i];
+  }
+  P.focal = v->focal;
+  P.depth_scale = v->depth_scale;
+  P.one_minus_min_T = 1.0f - v->min_transmittance;
+  for (int i = 0; i < 4; ++i) P.bg[i] = v->background[i];
+  P.W = v->width;
+  P.H = v->height;
+  P.spp = v->spp;
+  P.depth_mode = v->depth_mode;
+  P.out_rgba = (float4*)out_rgba;
+  P.out_u8 = out_u8;
+  P.out_depth = out_depth;
+  P.counter = n->counter;
+  cudaStream_t s = (cudaStream_t)stream;
+  PTK_CUDA_CHECK(cudaMemsetAsync(n->counter, 0, sizeof(unsigned), s));
+  int per_sm = 1;
+  PTK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nerf_render_kernel, kThreads, kSmemBytes));
+  if (per_sm < 1) per_sm = 1;
+  const long long warps_needed = ((long long)v->width * v->height + 31) / 32;
+  long long ctas = (warps_needed + kWarpsPerCta - 1) / kWarpsPerCta;
+  const long long cap = (long long)n->ctx->num_sms * per_sm;
+  if (ctas > cap) ctas = cap;
+  nerf_render_kernel<<<(unsigned)ctas, kThreads, kSmemBytes, s>>>(P);
+  PTK_CUDA_CHECK(cudaGetLastError());
+  return PTK_OK;
+}

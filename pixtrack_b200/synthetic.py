@@ -325,3 +325,85 @@ def tracked_sequence(seed: int, n_frames: int = 4, N: int = 5000, n_views: int =
         frames.append(dict(img_q=render_plane(tex, cam_q, R_q, t_q), img_r=render_plane(tex, cam_r, R_r, t_r),
                            R_q=R_q, t_q=t_q, R_r=R_r, t_r=t_r, T_init=torch.stack(T0)))
     return dict(frames=frames, cam_q=cam_q.double(), cam_r=cam_r.double(), p3d=p)
+
+
+# ---------------------------------------------------------------------------
+# NeRF scenes (SURVEY config C5): random hash grid / MLPs, procedural occupancy
+# ---------------------------------------------------------------------------
+NERF_GRID = 128
+NERF_CASCADES = 8
+
+
+def nerf_grid_size(aabb_scale: int) -> int:
+    """Number of hash-grid entries (x2 features) for the base.json encoding at this aabb_scale:
+    16 levels, T = 2^19, base resolution 16, finest resolution 2048 * aabb_scale
+    (instant-ngp/src/testbed.cu:2233-2244, tiny-cuda-nn encodings/grid.h:898-930)."""
+    import numpy as np
+    pls = np.float32(math.exp(math.log(2048.0 * aabb_scale / 16) / 15))
+    log2 = np.float32(np.log2(pls))
+    total = 0
+    for lv in range(16):
+        scale = np.float32(np.exp2(np.float32(lv) * log2) * np.float32(16) - np.float32(1))
+        res = int(np.ceil(scale)) + 1
+        total += min((min(res ** 3, 2 ** 31 - 1) + 7) // 8 * 8, 1 << 19)
+    return total
+
+
+def _morton_cell_centers(level: int):
+    import numpy as np
+
+    def compact(x):
+        x = x & 0x49249249
+        x = (x | (x >> 2)) & 0xc30c30c3
+        x = (x | (x >> 4)) & 0x0f00f00f
+        x = (x | (x >> 8)) & 0xff0000ff
+        x = (x | (x >> 16)) & 0x0000ffff
+        return x
+    i = np.arange(NERF_GRID ** 3, dtype=np.int64)
+    xyz = np.stack([compact(i), compact(i >> 1), compact(i >> 2)], 1).astype(np.float64)
+    return ((xyz + 0.5) / NERF_GRID - 0.5) * (2.0 ** level) + 0.5
+
+
+def nerf_scene(seed: int = 0, aabb_scale: int = 1, radius: float = 0.28, density_gain: float = 8.0,
+               zero_network: bool = False) -> Dict[str, object]:
+    """A random-weight instant-ngp model with a procedurally filled occupancy grid (a ball of
+    `radius` around the cube centre, in every cascade).  Returns numpy arrays shaped like an
+    unpacked snapshot: grid fp16 [n,2], w_density ([64,32],[16,64]), w_rgb ([64,32],[64,64],[16,64]),
+    density_grid float32 [(max_cascade+1) * 128^3] (Morton order), aabb_scale."""
+    import numpy as np
+    g = _gen(seed)
+    n = nerf_grid_size(aabb_scale)
+
+    def rnd(*shape, scale=1.0):
+        return (torch.randn(*shape, generator=g) * scale).numpy().astype(np.float16)
+    if zero_network:
+        grid = np.zeros((n, 2), np.float16)
+    else:
+        grid = ((torch.rand(n, 2, generator=g) * 2 - 1) * 0.6).numpy().astype(np.float16)
+    w_density = (rnd(64, 32, scale=math.sqrt(2.0 / 32)), rnd(16, 64, scale=density_gain * math.sqrt(1.0 / 64)))
+    w_density[1][0] = np.abs(w_density[1][0])      # density row: positive weights on ReLU outputs -> dense medium
+    w_rgb = (rnd(64, 32, scale=math.sqrt(2.0 / 32)), rnd(64, 64, scale=math.sqrt(2.0 / 64)),
+             rnd(16, 64, scale=2.0 * math.sqrt(1.0 / 64)))
+    max_cascade = 0
+    while (1 << max_cascade) < aabb_scale:
+        max_cascade += 1
+    dens = []
+    for lv in range(max_cascade + 1):
+        c = _morton_cell_centers(lv)
+        inside = ((c - 0.5) ** 2).sum(1) < (radius + 0.87 * (2.0 ** lv) / NERF_GRID) ** 2
+        dens.append(np.where(inside, 1.0, -1.0).astype(np.float32))
+    return dict(aabb_scale=aabb_scale, grid=grid, w_density=w_density, w_rgb=w_rgb,
+                density_grid=np.concatenate(dens), max_cascade=max_cascade)
+
+
+def nerf_look_at(eye, target=(0.5, 0.5, 0.5), up=(0.0, 0.0, 1.0)):
+    """3x4 camera-to-world matrix in the NGP convention used by the renderer (columns: right, down,
+    forward, origin), looking from `eye` at `target`."""
+    import numpy as np
+    eye, target, up = (np.asarray(v, np.float64) for v in (eye, target, up))
+    f = target - eye
+    f /= np.linalg.norm(f)
+    r = np.cross(f, up)
+    r /= np.linalg.norm(r)
+    d = np.cross(f, r)
+    return np.stack([r, d, f, eye], 1).astype(np.float32)
