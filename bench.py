@@ -180,9 +180,44 @@ def lm_stress(dev, lam, peak):
                     'this is L2-served traffic measured against the HBM copy peak'}
 
 
+def nerf_leg(dev, frame_step, steps):
+    """Reference-view re-render (1008x756, spp 8: r9.py:81,150 + run_vis_on_poses.py:29) of a random-weight
+    instant-ngp model with a ball-shaped occupancy, alone and in front of the tracked frame."""
+    from pixtrack_b200.nerf import NerfTestbed, occupancy_bitfield
+    sc = syn.nerf_scene(11, 2)
+    tb = NerfTestbed(sc['grid'], sc['w_density'], sc['w_rgb'], occupancy_bitfield(sc['density_grid'], sc['max_cascade']),
+                     2, dev)
+    tb.nerf.rendering_min_transmittance = 1e-7
+    tb.fov = 40.0
+    tb.set_ngp_camera_matrix(syn.nerf_look_at((0.4, -1.3, 0.8)))
+    W, H, spp = 1008, 756, 8
+    for _ in range(3):
+        rgba, u8, _ = tb.render_device(W, H, spp, want_u8=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    a.record()
+    for _ in range(reps):
+        tb.render_device(W, H, spp, want_rgba=False, want_u8=True)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    a.record()
+    for i in range(steps):
+        tb.render_device(W, H, spp, want_rgba=False, want_u8=True)
+        frame_step(i)
+    b.record()
+    torch.cuda.synchronize()
+    ms_frame = a.elapsed_time(b) / steps
+    cover = float((rgba[..., 3] > 0.5).float().mean())
+    return {'workload': f'{W}x{H} spp {spp}, aabb_scale 2, ball occupancy covering {cover:.0%} of the image, random weights',
+            'ms_per_render': ms, 'mrays_per_s': W * H * spp / ms / 1e3, 'frames_per_s_with_render': 1e3 / ms_frame,
+            'ms_per_frame_with_render': ms_frame}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from pixtrack_b200 import _lib
+    from pixtrack_b200 import _lib, shard
     from pixtrack_b200.extractor import B200FeatureExtractor
     from pixtrack_b200.pipeline import FrameTracker
 
@@ -230,10 +265,7 @@ def run_ours(args, rank, world, local_rank):
         step(i, devi[i % RING])
     ev1.record()
     barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
+    ms_total = shard.max_over_ranks(ev0.elapsed_time(ev1), dev)
     _lib.device_status(local_rank)
     clk = clocks.stop() if rank == 0 else None
     launches_per_step = 2 * 32 + 1 + 3          # 2 extractor plans, 1 sampling launch, 3 LM launches (one graph)
@@ -297,17 +329,20 @@ def run_ours(args, rank, world, local_rank):
     for i in range(args.steps):
         e2e_step(i)
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = shard.max_over_ranks(time.perf_counter() - t0, dev)
+
+    # ---- the same frame with the NeRF re-render of the reference view in front (r9.py:145-160 renders it
+    #      every frame; reported separately because the reference has no CPU path for it) ---------------
+    nerf = nerf_leg(dev, lambda i: step(i, devi[i % RING]), args.steps) if rank == 0 else None
     h2d = host[0]['q'].numel() + host[0]['r'].numel()
     d2h = N_VIEWS * 13
 
-    # ---- final gather of per-frame results (the only collective on this path) -----------------------
-    res = torch.cat([trk.plan.T, trk.plan.failed.float()[:, None]], 1)
-    if world > 1:
-        gathered = [torch.empty_like(res) for _ in range(world)]
-        dist.all_gather(gathered, res)
+    # ---- final gather of per-unit results (the only collective on this path): unit = this rank's sequence,
+    #      its result = the pose of the best view --------------------------------------------------------
+    best = 0
+    table = shard.gather_results(shard.pack_results([rank], trk.plan.T[best:best + 1], trk.plan.failed[best:best + 1],
+                                                    trk.plan.n_iters[-1][best:best + 1]), world)
+    assert table.shape[0] == world
 
     if rank == 0:
         cpu = None
@@ -337,7 +372,7 @@ def run_ours(args, rank, world, local_rank):
             'e2e': {'value': args.steps * world / float(e2e_s), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h},
             'gpu_launches': launches_per_step * args.steps, 'clocks': clk, 'roofline': roofline,
-            'roofline_lm': stress, 'extractor_plan': plan_prof, 'cpu_baseline': cpu,
+            'roofline_lm': stress, 'extractor_plan': plan_prof, 'nerf_render': nerf, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -81,6 +81,8 @@ struct NerfParams {
   float cam[12];                 // 3x4 row-major, NGP convention
   float tmin[3], tmax[3];        // training box (m_aabb)
   float rmin[3], rmax[3];        // render box
+  float occ[kCascades][6];       // U_m: bounds of the occupied cells of cascades 0..m, padded (see ptk_nerf_create)
+  int corner_mip;                // mip_from_pos of the farthest render-box corner
   float cone, focal, depth_scale, one_minus_min_T;
   float bg[4];                   // background, already linear
   int W, H, spp, depth_mode;
@@ -153,9 +155,16 @@ __device__ __forceinline__ bool inside(const float* lo, const float* hi, const V
 
 // Advance t to the next sample position in an occupied cell (common loop of advance_pos_nerf and
 // generate_next_nerf_network_inputs).  Returns false when the ray left the render box.
-__device__ __forceinline__ bool skip_empty(const NerfParams& P, const V3& o, const V3& d, const V3& id, float& t, V3& pos,
-                                           float& dt) {
+//
+// [tu0, tu1] is the part of the ray inside the padded bounds of everything occupied (U_m, see
+// ptk_nerf_create).  Outside it no probe can find an occupied cell, so before tu0 the ray only needs
+// its t sequence advanced (t += dt(t), the same additions the voxel stepping performs) and after tu1
+// it can be retired at once -- same result as marching on to the box exit.
+__device__ __forceinline__ bool skip_empty(const NerfParams& P, const V3& o, const V3& d, const V3& id, float tu0,
+                                           float tu1, float& t, V3& pos, float& dt) {
+  while (t < tu0) t += calc_dt(t, P.cone);
   while (true) {
+    if (t > tu1) return false;
     pos.x = o.x + d.x * t;
     pos.y = o.y + d.y * t;
     pos.z = o.z + d.z * t;
@@ -257,7 +266,7 @@ __device__ __forceinline__ void hash_encode(const NerfParams& P, float x, float 
     for (int c = 0; c < 8; ++c) {
       const uint32_t cx = gx + (c & 1), cy = gy + ((c >> 1) & 1), cz = gz + (c >> 2);
       uint32_t idx;
-      if (lv.hashed) idx = (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) % lv.size;
+      if (lv.hashed) idx = (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (lv.size - 1u);   // hashed levels hold 2^19
       else idx = (cx + cy * lv.res + cz * lv.res * lv.res) % lv.size;
       v[c] = __ldg(g + idx);
     }
@@ -372,7 +381,7 @@ struct Ray {
   int steps;
   bool alive;
   V3 d, id;
-  float t, tentry;
+  float t, tentry, tu0, tu1;
   float r, g, b, a; // this sample's compositing state
   float maxw, dep;
   float ar, ag, ab, aa, adep;   // running mean over spp
@@ -392,7 +401,7 @@ __device__ __forceinline__ void start_spp(const NerfParams& P, const V3& o, Ray&
   if (ry.alive) {   // advance_pos_nerf: jittered start, then on to the first occupied cell
     t += ld_random_val((uint32_t)ry.s, (uint32_t)ry.pix * 786433u) * calc_dt(t, P.cone);
     float dt;
-    ry.alive = skip_empty(P, o, ry.d, ry.id, t, p, dt);
+    ry.alive = skip_empty(P, o, ry.d, ry.id, ry.tu0, ry.tu1, t, p, dt);
   }
   ry.t = t;
 }
@@ -442,7 +451,7 @@ __device__ __forceinline__ void drain(const NerfParams& P, const V3& o, Ray& ry)
   }
 }
 
-__global__ void __launch_bounds__(kThreads) nerf_render_kernel(const __grid_constant__ NerfParams P) {
+__global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_constant__ NerfParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __half* wts = reinterpret_cast<__half*>(smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -499,7 +508,7 @@ __global__ void __launch_bounds__(kThreads) nerf_render_kernel(const __grid_cons
           d.x /= nrm; d.y /= nrm; d.z /= nrm;
           ry.d = d;
           ry.id.x = 1.f / d.x; ry.id.y = 1.f / d.y; ry.id.z = 1.f / d.z;
-          // BoundingBox::ray_intersect, entry distance
+          // BoundingBox::ray_intersect
           float t0 = (P.rmin[0] - o.x) / d.x, t1 = (P.rmax[0] - o.x) / d.x;
           float tmin = fminf(t0, t1), tmax = fmaxf(t0, t1);
           bool miss = false;
@@ -510,9 +519,40 @@ __global__ void __launch_bounds__(kThreads) nerf_render_kernel(const __grid_cons
           t0 = (P.rmin[2] - o.z) / d.z; t1 = (P.rmax[2] - o.z) / d.z;
           lo = fminf(t0, t1); hi = fmaxf(t0, t1);
           miss = miss || (tmin > hi) || (lo > tmax);
-          tmin = lo > tmin ? lo : tmin;
+          tmin = lo > tmin ? lo : tmin; tmax = hi < tmax ? hi : tmax;
           ry.tentry = miss ? 3.402823466e+38f : tmin;
-          start_spp(P, o, ry);
+          // part of the ray inside the occupied bounds of every cascade it can probe
+          ry.tu0 = 3.402823466e+38f;
+          ry.tu1 = -3.402823466e+38f;
+          if (!miss) {
+            const float far = fmaxf(tmax, kNear) + 1.f;
+            int mh = P.corner_mip;
+            {
+              const float dtf = calc_dt(far, P.cone) * (2 * kGrid);
+              int e = 0;
+              if (dtf >= 1.f) frexpf(dtf, &e);
+              mh = min(kCascades - 1, max(mh, e));
+            }
+            const float* U = P.occ[mh];
+            float a0 = (U[0] - o.x) / d.x, a1 = (U[3] - o.x) / d.x;
+            float un = fminf(a0, a1), ux = fmaxf(a0, a1);
+            a0 = (U[1] - o.y) / d.y; a1 = (U[4] - o.y) / d.y;
+            un = fmaxf(un, fminf(a0, a1)); ux = fminf(ux, fmaxf(a0, a1));
+            a0 = (U[2] - o.z) / d.z; a1 = (U[5] - o.z) / d.z;
+            un = fmaxf(un, fminf(a0, a1)); ux = fminf(ux, fmaxf(a0, a1));
+            if (un <= ux && U[0] <= U[3]) {   // NaN-free hit (fminf/fmaxf drop NaNs of axis-parallel rays)
+              ry.tu0 = un;
+              ry.tu1 = ux;
+            }
+          }
+          if (!(ry.tu0 <= ry.tu1)) {   // nothing occupied along this ray: every sample-per-pixel is empty
+            ry.s = P.spp - 1;
+            ry.alive = false;
+            ry.r = ry.g = ry.b = ry.a = 0.f;
+            ry.maxw = ry.dep = 0.f;
+          } else {
+            start_spp(P, o, ry);
+          }
           drain(P, o, ry);
         } else {
           exhausted = true;
@@ -526,7 +566,7 @@ __global__ void __launch_bounds__(kThreads) nerf_render_kernel(const __grid_cons
     V3 pos = {0.f, 0.f, 0.f};
     float dt = 0.f;
     if (ry.pix >= 0 && ry.alive) {
-      sample = skip_empty(P, o, ry.d, ry.id, ry.t, pos, dt);
+      sample = skip_empty(P, o, ry.d, ry.id, ry.tu0, ry.tu1, ry.t, pos, dt);
       if (!sample) ry.alive = false;
     }
     const unsigned sm = __ballot_sync(full, sample);
@@ -636,6 +676,48 @@ extern "C" int ptk_nerf_create(PtkContext* ctx, const PtkNerfModel* m, PtkNerf**
     P.tmax[i] = 0.5f + half;
   }
   P.cone = m->aabb_scale <= 1 ? 0.f : 1.f / 256.f;   // testbed_nerf.cu:2596
+  {
+    // Bounds of the occupied cells (load-time, host): B_m = box of the set cells of cascade m in world
+    // coordinates; U_m = box of B_0..B_m padded by two cells of cascade m.  A probe at cascade <= m outside U_m
+    // cannot be occupied, which lets the marcher skip the voxel walk there (skip_empty).
+    const size_t bytes = (size_t)kCascades * kGrid * kGrid * kGrid / 8;
+    uint8_t* host = (uint8_t*)malloc(bytes);
+    cudaError_t ce = cudaMemcpy(host, m->bitfield, bytes, cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) {
+      ptk_set_error("reading the occupancy bitfield: %s", cudaGetErrorString(ce));
+      free(host);
+      free(n);
+      return PTK_ERR_CUDA;
+    }
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+    const size_t per = (size_t)kGrid * kGrid * kGrid;
+    for (int mip = 0; mip < kCascades; ++mip) {
+      const float cs = ldexpf(1.f, mip) / kGrid;
+      for (size_t i = 0; i < per; ++i) {
+        if (((host[(mip * per + i) >> 3] >> (i & 7)) & 1) == 0) continue;
+        uint32_t c[3];
+        for (int a = 0; a < 3; ++a) {   // Morton decode
+          uint32_t x = ((uint32_t)i >> a) & 0x49249249u;
+          x = (x | (x >> 2)) & 0xc30c30c3u;
+          x = (x | (x >> 4)) & 0x0f00f00fu;
+          x = (x | (x >> 8)) & 0xff0000ffu;
+          x = (x | (x >> 16)) & 0x0000ffffu;
+          c[a] = x;
+        }
+        for (int a = 0; a < 3; ++a) {
+          const float w0 = ((float)c[a] / kGrid - 0.5f) * ldexpf(1.f, mip) + 0.5f;
+          if (w0 < lo[a]) lo[a] = w0;
+          if (w0 + cs > hi[a]) hi[a] = w0 + cs;
+        }
+      }
+      const float pad = 2.f * cs + 1e-4f;
+      for (int a = 0; a < 3; ++a) {
+        P.occ[mip][a] = lo[a] - pad;
+        P.occ[mip][3 + a] = hi[a] + pad;
+      }
+    }
+    free(host);
+  }
   cudaError_t e = cudaMalloc(&n->counter, sizeof(unsigned));
   if (e != cudaSuccess) {
     ptk_set_error("cudaMalloc: %s", cudaGetErrorString(e));
@@ -680,6 +762,13 @@ extern "C" int ptk_nerf_render(PtkNerf* n, const PtkNerfView* v, float* out_rgba
   for (int i = 0; i < 3; ++i) {
     P.rmin[i] = v->render_aabb_min[i];
     P.rmax[i] = v->render_aabb_max[i];
+  }
+  {
+    float mx = 0.f;
+    for (int i = 0; i < 3; ++i) mx = fmaxf(mx, fmaxf(fabsf(P.rmin[i] - 0.5f), fabsf(P.rmax[i] - 0.5f)));
+    int e = 0;
+    frexpf(mx, &e);
+    P.corner_mip = e + 1 < 0 ? 0 : (e + 1 > kCascades - 1 ? kCascades - 1 : e + 1);
   }
   P.focal = v->focal;
   P.depth_scale = v->depth_scale;

@@ -8,7 +8,7 @@ tb = NerfTestbed(sc['grid'], sc['w_density'], sc['w_rgb'], bits, 2, 'cuda:0')
 tb.nerf.rendering_min_transmittance = 1e-7
 tb.fov = 40.0
 tb.set_ngp_camera_matrix(syn.nerf_look_at((0.4, -1.3, 0.8)))
-for (w, h, spp) in [(640,480,1),(1008,756,1),(1008,756,8),(1920,1080,8)]:
+for (w, h, spp) in [(1008,756,1),(1008,756,8),(1008,756,8),(1920,1080,8)]:
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
