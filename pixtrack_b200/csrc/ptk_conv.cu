@@ -73,6 +73,19 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// One lane of a CONVERGED warp (always the same one).  The MMA / TMA issue loops run warp-uniformly and
+// predicate only the issuing instruction with this: descriptors then live in uniform registers, whereas
+// an `if (lane == 0)` region makes the compiler wrap every UTCHMMA in an R2UR + elect waterfall loop
+// (measured: ~100 cycles of issue per MMA, which bounds every layer with N <= 128).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -174,15 +187,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      for (int ks = 0; ks < num_steps; ++ks) {
-        const int stage = ks % STAGES;
-        const uint32_t phase = (uint32_t)(ks / STAGES) & 1u;
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-        const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + kABytes);
+    // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues ----------------
+    for (int ks = 0; ks < num_steps; ++ks) {
+      const int stage = ks % STAGES;
+      const uint32_t phase = (uint32_t)(ks / STAGES) & 1u;
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+      const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + kABytes);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kKChunk / 16; ++k) {
           // +32 B per K=16 step inside the 128 B swizzle row = +2 in the (addr >> 4) field
@@ -190,8 +203,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         }
         tc_commit(&empty_bar[stage]);   // stage is free once these MMAs have read it
       }
-      tc_commit(tmem_full_bar);         // accumulator complete
+      __syncwarp();
     }
+    if (elect_one()) tc_commit(tmem_full_bar);   // accumulator complete
+    __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> registers -> bias/ReLU -> fp16 -> global ----------------
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
@@ -223,6 +238,237 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) dst[j] = pk[j];
       }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// conv_halo_kernel: persistent 3x3 convolution with ONE halo load per 64-channel chunk.
+//
+// The tap-shifted operand of conv_tc_kernel re-fetches every input pixel nine times from L2
+// (L2 -> SMEM bandwidth, not the tensor pipe, bounds it: 85 flop per staged byte at best).  Here a
+// CTA owns a 16 x 16 pixel output tile and stages the (16+2) x (16+2) halo of a 64-channel chunk
+// once: TMA box {64 ch, 24 px, 18 px} -> 432 rows of 128 B, 128B-swizzled.  With a 24-pixel row
+// pitch (3 x 1024 B) every 8-pixel run of a halo row is one swizzle atom row group, so the operand
+// of tap (dy, dx) for the 8-wide half tile `sx` is the SAME buffer seen through a descriptor whose
+// start address is shifted by ((1+dy)*24 + 8*sx + 1+dx) rows and whose 8-row groups are 24 rows
+// (3072 B) apart.  The tensor core applies the 128B swizzle to the absolute shared-memory address
+// bits (measured: the descriptor's base-offset field must stay 0 for a start that is not
+// 1024-B aligned), so the shifted view reads exactly what TMA wrote.  Two M=128 MMAs (the two half tiles) share each weight tile, the weights of a
+// layer with <= 72 KB of them stay resident in shared memory, accumulators are double-buffered in
+// TMEM so the epilogue of one tile overlaps the MMAs of the next, and CTAs are persistent.
+// Staged bytes per flop drop 2.5-5x against conv_tc_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHaloW = 24, kHaloH = 18;
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;      // 55296
+constexpr int kBBudget = 73728;                        // weight slots: 72 KB
+constexpr int kHaloThreads = 192;
+
+struct HaloParams {
+  int H, W, Cout;
+  int chunks0, chunks1;
+  int relu;
+  int tiles_w, tiles_hw, total_tiles;
+  int resident;          // all taps x chunks weight tiles fit the slots and Cout == N: load them once
+  int rows_per_op;       // halo rows per TMA operation (the halo is fetched as 18 / rows_per_op boxes in flight)
+  const float* bias;
+  __half* out;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int N>
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                                    const __grid_constant__ CUtensorMap tmA1,
+                                                                    const __grid_constant__ CUtensorMap tmW,
+                                                                    const HaloParams P) {
+  constexpr int kBBytes = N * 128;
+  constexpr int kSlots = kBBudget / kBBytes;
+  constexpr uint32_t kTmemCols = 4 * N < 32 ? 32 : 4 * N;      // 2 buffers x 2 half tiles
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                              // 2 halo stages
+  uint8_t* sB = smem + 2 * kHaloBytes;             // kSlots weight tiles
+  uint64_t* fullA = (uint64_t*)(sB + kSlots * kBBytes);
+  uint64_t* emptyA = fullA + 2;
+  uint64_t* fullB = emptyA + 2;
+  uint64_t* emptyB = fullB + kSlots;
+  uint64_t* tmem_full = emptyB + kSlots;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = P.chunks0 + P.chunks1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    if (P.chunks1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&emptyA[s], 1);
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&fullB[s], 1);
+      mbar_init(&emptyB[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      uint32_t a_it = 0, b_it = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
+        const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
+        const int h0 = th * 16, w0 = tw * 16, n0 = nb * N;
+        for (int c = 0; c < chunks; ++c) {
+          const int sa = a_it & 1;
+          mbar_wait(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&fullA[sa], kHaloBytes);
+          for (int r = 0; r < kHaloH; r += P.rows_per_op) {
+            uint8_t* dst = sA + sa * kHaloBytes + r * (kHaloW * 128);
+            if (c < P.chunks0) tma_load_3d(dst, &tmA0, &fullA[sa], c * kKChunk, w0 - 1, h0 - 1 + r);
+            else tma_load_3d(dst, &tmA1, &fullA[sa], (c - P.chunks0) * kKChunk, w0 - 1, h0 - 1 + r);
+          }
+          ++a_it;
+          if (!P.resident || first) {
+            for (int tap = 0; tap < 9; ++tap) {
+              int sb;
+              if (P.resident) {
+                sb = c * 9 + tap;
+              } else {
+                sb = b_it % kSlots;
+                mbar_wait(&emptyB[sb], ((b_it / kSlots) & 1u) ^ 1u);
+              }
+              mbar_expect_tx(&fullB[sb], kBBytes);
+              tma_load_3d(sB + sb * kBBytes, &tmW, &fullB[sb], c * kKChunk, n0, tap);
+              ++b_it;
+            }
+          }
+        }
+        first = false;
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues ----------------
+    uint32_t a_it = 0, b_it = 0, t_it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++t_it) {
+      const uint32_t buf = t_it & 1u;
+      mbar_wait(&tmem_empty[buf], ((t_it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int c = 0; c < chunks; ++c) {
+        const int sa = a_it & 1;
+        mbar_wait(&fullA[sa], (a_it >> 1) & 1u);
+        ++a_it;
+        const uint32_t abase = smem_u32(sA + sa * kHaloBytes);
+        // descriptor of tap (0,0) of half tile 0; the other taps / half tile are constant offsets of it
+        const uint64_t adesc0 = (uint64_t)((abase & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) |
+                                ((uint64_t)((kHaloW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          int sb;
+          if (P.resident) {
+            sb = c * 9 + tap;
+            if (t_it == 0) mbar_wait(&fullB[sb], 0);
+          } else {
+            sb = b_it % kSlots;
+            mbar_wait(&fullB[sb], (b_it / kSlots) & 1u);
+            ++b_it;
+          }
+          tc_fence_after();
+          const uint64_t bdesc = make_sw128_desc(smem_u32(sB + sb * kBBytes));
+          if (elect_one()) {
+#pragma unroll
+            for (int sx = 0; sx < 2; ++sx) {
+              // start row of this tap's view: ((1+dy)*24 + 8*sx + 1+dx), 128 B per row, >> 4 in the descriptor
+              const int row0 = (tap / 3) * kHaloW + 8 * sx + (tap % 3);
+              const uint64_t adesc = adesc0 + (uint64_t)(row0 * 8);
+              const uint32_t d = tmem_base + (buf * 2u + (uint32_t)sx) * (uint32_t)N;
+#pragma unroll
+              for (int k = 0; k < kKChunk / 16; ++k)
+                tc_mma_f16(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (c | tap | k) != 0 ? 1u : 0u);
+            }
+            if (!P.resident) tc_commit(&emptyB[sb]);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) tc_commit(&emptyA[sa]);
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(&tmem_full[buf]);
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue: 4 warps, TMEM lane quadrant q = rows 32q .. 32q+31 of both half tiles ----------------
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int y = m >> 3, xx = m & 7;
+    uint32_t t_it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++t_it) {
+      const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
+      const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
+      const int h = th * 16 + y, n0 = nb * N;
+      const uint32_t buf = t_it & 1u;
+      mbar_wait(&tmem_full[buf], (t_it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sx = 0; sx < 2; ++sx) {
+        const int w = tw * 16 + 8 * sx + xx;
+        const bool inside = (h < P.H) && (w < P.W);
+        __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
+#pragma unroll 1
+        for (int c = 0; c < N; c += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2u + (uint32_t)sx) * (uint32_t)N + (uint32_t)c, v);
+          if (inside) {
+            uint4 pk[4];
+            uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = __uint_as_float(v[2 * j]) + __ldg(P.bias + n0 + c + 2 * j);
+              float b = __uint_as_float(v[2 * j + 1]) + __ldg(P.bias + n0 + c + 2 * j + 1);
+              if (P.relu) {
+                a = fmaxf(a, 0.f);
+                b = fmaxf(b, 0.f);
+              }
+              const __half2 hv = __floats2half2_rn(a, b);
+              pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(orow + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = pk[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
   }
 
@@ -291,6 +537,23 @@ int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   return PTK_OK;
 }
 
+
+template <int N>
+int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int grid,
+                cudaStream_t stream) {
+  constexpr int kSlots = kBBudget / (N * 128);
+  constexpr int smem = 2 * kHaloBytes + kSlots * N * 128 + (4 + 2 * kSlots + 4) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  conv_halo_kernel<N><<<grid, kHaloThreads, smem, stream>>>(a0, a1, w, P);
+  PTK_CUDA_CHECK(cudaGetLastError());
+  return PTK_OK;
+}
+
+// fp16 tensor map with an explicit box (the halo kernel's A operand)
 }  // namespace
 
 // Picks the N tile so that small maps still fill the machine (>= ~1 CTA per SM when possible).
@@ -321,6 +584,50 @@ extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, cons
   } else {
     a1 = a0;
   }
+  cudaStream_t s = (cudaStream_t)stream;
+  // ---- halo kernel (3x3 only): one halo load per chunk, persistent CTAs ----
+  {
+    static int mode = -1, rows_per_op = 3;   // PTK_CONV_HALO: 0 = never, 1 = when it fills the machine (default), 2 = whenever legal
+    if (mode < 0) {
+      const char* e = getenv("PTK_CONV_HALO");
+      mode = e ? atoi(e) : 1;
+      const char* r = getenv("PTK_CONV_HALO_ROWS");
+      if (r && (atoi(r) == 1 || atoi(r) == 2 || atoi(r) == 3 || atoi(r) == 6 || atoi(r) == 9 || atoi(r) == 18)) rows_per_op = atoi(r);
+    }
+    const int tiles_w16 = (W + 15) / 16, tiles_h16 = (H + 15) / 16;
+    const int n_halo = Cout >= 128 ? 128 : Cout;
+    const int total = tiles_w16 * tiles_h16 * (Cout / n_halo);
+    const bool legal = taps == 9 && (Cout == 32 || Cout == 64 || Cout % 128 == 0);
+    // the 16x16 tiles are coarse: use them only when their last wave is reasonably full, otherwise the
+    // finer-grained kernel fills the machine better
+    const int waves = (total + ctx->num_sms - 1) / ctx->num_sms;
+    const bool wanted = mode == 2 || (mode == 1 && total * 10 >= waves * ctx->num_sms * 8);
+    if (legal && wanted) {
+      rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kHaloW, rows_per_op);
+      if (rc != PTK_OK) return rc;
+      if (cin1 > 0) {
+        rc = make_map_3d(&a1, in1, cin1, W, H, cin1, (uint64_t)in1_W * cin1, kKChunk, kHaloW, rows_per_op);
+        if (rc != PTK_OK) return rc;
+      } else {
+        a1 = a0;
+      }
+      rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, n_halo, 1);
+      if (rc != PTK_OK) return rc;
+      HaloParams Q;
+      Q.H = H; Q.W = W; Q.Cout = Cout; Q.chunks0 = cin0 / kKChunk; Q.chunks1 = cin1 / kKChunk; Q.relu = relu;
+      Q.tiles_w = tiles_w16; Q.tiles_hw = tiles_w16 * tiles_h16; Q.total_tiles = total;
+      Q.resident = (Cout == n_halo && 9 * (Q.chunks0 + Q.chunks1) <= kBBudget / (n_halo * 128)) ? 1 : 0;
+      Q.rows_per_op = rows_per_op;
+      Q.bias = bias;
+      Q.out = (__half*)out;
+      const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+      switch (n_halo) {
+        case 32: return launch_halo<32>(a0, a1, wm, Q, grid, s);
+        case 64: return launch_halo<64>(a0, a1, wm, Q, grid, s);
+        default: return launch_halo<128>(a0, a1, wm, Q, grid, s);
+      }
+    }
+  }
   ConvParams P;
   P.H = H; P.W = W; P.Cout = Cout; P.cin0 = cin0; P.cin1 = cin1; P.taps = taps; P.relu = relu;
   P.tiles_w = (W + kTileW - 1) / kTileW;
@@ -330,10 +637,11 @@ extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, cons
   const int bn = pick_block_n(Cout, m_tiles, ctx->num_sms);
   rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, bn, 1);
   if (rc != PTK_OK) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
   switch (bn) {
     case 32: return launch_conv<32, 4>(a0, a1, wm, P, s);
-    case 64: return launch_conv<64, 4>(a0, a1, wm, P, s);
+    case 64:   // at most one CTA per SM: nothing else hides the load latency, so run a deeper ring
+      if (m_tiles * (Cout / bn) <= ctx->num_sms) return launch_conv<64, 8>(a0, a1, wm, P, s);
+      return launch_conv<64, 4>(a0, a1, wm, P, s);
     case 128: return launch_conv<128, 3>(a0, a1, wm, P, s);
     default: return launch_conv<256, 3>(a0, a1, wm, P, s);
   }

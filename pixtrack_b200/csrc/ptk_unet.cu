@@ -115,12 +115,12 @@ __global__ void __launch_bounds__(256) conv1_direct_kernel(const float* __restri
 
 // 2x2 / stride 2 max pool (floor mode), NHWC fp16, 8 channels per thread.
 __global__ void maxpool2_kernel(const __half* __restrict__ in, int H, int W, int C, __half* __restrict__ out) {
-  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)Ho * Wo * C8) return;
-  const int c8 = (int)(idx % C8);
-  const long long p = idx / C8;
-  const int x = (int)(p % Wo), y = (int)(p / Wo);
+  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;   // C8 is a power of two (C = 64 .. 512)
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)(Ho * Wo * C8)) return;
+  const int sh = 31 - __clz(C8);
+  const unsigned c8 = idx & (unsigned)(C8 - 1), p = idx >> sh;
+  const int y = (int)(p / (unsigned)Wo), x = (int)(p - (unsigned)y * (unsigned)Wo);
   const uint4* src = reinterpret_cast<const uint4*>(in);
   const size_t base = ((size_t)(2 * y) * W + 2 * x) * C8 + c8;
   uint4 a = src[base], b = src[base + C8], c = src[base + (size_t)W * C8], d = src[base + (size_t)W * C8 + C8];
@@ -135,12 +135,12 @@ __global__ void maxpool2_kernel(const __half* __restrict__ in, int H, int W, int
 
 // x2 bilinear upsample, align_corners=False (nn.Upsample in DecoderBlock, unet.py:19-20), NHWC fp16.
 __global__ void upsample2_kernel(const __half* __restrict__ in, int H, int W, int C, __half* __restrict__ out) {
-  const int Ho = 2 * H, Wo = 2 * W, C8 = C >> 3;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)Ho * Wo * C8) return;
-  const int c8 = (int)(idx % C8);
-  const long long p = idx / C8;
-  const int x = (int)(p % Wo), y = (int)(p / Wo);
+  const int Ho = 2 * H, Wo = 2 * W, C8 = C >> 3;   // C8 is a power of two (C = 64 .. 512)
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)(Ho * Wo * C8)) return;
+  const int sh = 31 - __clz(C8);
+  const unsigned c8 = idx & (unsigned)(C8 - 1), p = idx >> sh;
+  const int y = (int)(p / (unsigned)Wo), x = (int)(p - (unsigned)y * (unsigned)Wo);
   const float sxf = fmaxf(((float)x + 0.5f) * 0.5f - 0.5f, 0.f), syf = fmaxf(((float)y + 0.5f) * 0.5f - 0.5f, 0.f);
   const int x0 = (int)sxf, y0 = (int)syf;
   const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
@@ -167,136 +167,138 @@ __global__ void upsample2_kernel(const __half* __restrict__ in, int H, int W, in
 // ---------------------------------------------------------------------------------------------
 // Heads (unet.py:47-50,177-188): 1x1 adaptation conv C_in -> C_out plus the 1x1 uncertainty conv
 // (-> 1 channel), confidence = sigmoid(-u); optional per-pixel L2 normalisation of the descriptor
-// (base_refiner.py:92-94) fused in.  fp16 activations in, fp32 weights, fp32 out.
+// (base_refiner.py:92-94) fused in.  fp16 activations in, fp32 out.
 // w: [C_out + 1][C_in] fp32 (row C_out = uncertainty), b: [C_out + 1].
-// Register-tiled fp32 GEMM on the CUDA cores (the op is 1 GMAC in total and bound by the 78 MB it
-// writes at level 0): 256 threads = NTM x NTN, a thread owns PT pixels x 9 outputs; K advances in
-// chunks of 32 through shared memory with both operands k-contiguous (one LDS.128 feeds 4 k of one
-// row: 13 loads per 144 FMAs at PT = 4); results are staged in shared memory and leave as fully
-// coalesced rows of the channels-last output.
+//
+// A [pixels x C_in] x [C_in x (C_out+1)] GEMM on the warp-level tensor cores (mma.sync m16n8k16, fp16
+// operands, fp32 accumulate): the op is ~1 GMAC in total and bound by the 78 MB it writes at level 0, far too
+// small / too oddly shaped (33 and 129 output columns, K = 32) for a tcgen05 tile, and the CUDA-core version
+// it replaces was shared-memory-bandwidth bound at 5-10 TFLOP/s.  A warp owns 32 pixels: A fragments come
+// straight from the channels-last activation in global memory, the weights (converted to fp16) sit in shared
+// memory with a conflict-free row stride, each pixel's outputs stay in the accumulator fragments of 4 lanes,
+// so the squared norm is two shuffles, and rows leave as 8-byte stores (32 B contiguous per pixel and n-tile).
 // ---------------------------------------------------------------------------------------------
-constexpr int kHeadKC = 32, kHeadLd = kHeadKC + 4, kHeadOut = 9;
-template <int PT, int NTN>
-struct HeadCfg {
-  static constexpr int NTM = 256 / NTN, TM = NTM * PT, TN = kHeadOut * NTN;
-  static constexpr int kOperandFloats = (TM + TN) * kHeadLd;
-  static constexpr int kStageFloats = TM * (TN + 1);
-  static constexpr int kSmemFloats = kOperandFloats > kStageFloats ? kOperandFloats : kStageFloats;
-};
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
-template <int PT, int NTN>
-__global__ void __launch_bounds__(256) head_kernel(const __half* __restrict__ x, long long npix, int Cin, int Cout,
-                                                   const float* __restrict__ w, const float* __restrict__ b,
-                                                   float* __restrict__ feat, float* __restrict__ conf, int normalize) {
-  using Cfg = HeadCfg<PT, NTN>;
-  constexpr int TM = Cfg::TM, TN = Cfg::TN;
-  __shared__ __align__(16) float smem[Cfg::kSmemFloats];
-  float* As = smem;                     // [TM][kHeadLd]
-  float* Ws = smem + TM * kHeadLd;      // [TN][kHeadLd]
-  const int tn = threadIdx.x % NTN, tm = threadIdx.x / NTN;
-  const long long p0 = (long long)blockIdx.x * TM;
+// NT n-tiles of 8 output columns: NT*8 >= C_out + 1 (5 for 32+1, 17 for 128+1)
+template <int NT>
+__global__ void __launch_bounds__(256) head_mma_kernel(const __half* __restrict__ x, int npix, int Cin, int Cout,
+                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       float* __restrict__ feat, float* __restrict__ conf,
+                                                       int normalize) {
+  extern __shared__ __align__(16) __half sw[];   // [NT*8][Cin + 8]
+  const int ws = Cin + 8;
   const int nout = Cout + 1;
-  float acc[PT][kHeadOut];
-#pragma unroll
-  for (int i = 0; i < PT; ++i)
-#pragma unroll
-    for (int j = 0; j < kHeadOut; ++j) acc[i][j] = 0.f;
-
-  for (int k0 = 0; k0 < Cin; k0 += kHeadKC) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < TM * 4; idx += 256) {        // activations: 8 halfs per thread
-      const int p = idx >> 2, q = idx & 3;
-      float v[8];
-      if (p0 + p < npix) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(x + (p0 + p) * Cin + k0 + q * 8);
-        const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h[e]);
-          v[2 * e] = f.x;
-          v[2 * e + 1] = f.y;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      }
-      float4* dst = reinterpret_cast<float4*>(As + p * kHeadLd + q * 8);
-      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-    }
-    for (int idx = threadIdx.x; idx < TN * 8; idx += 256) {        // weights: one float4 per thread
-      const int n = idx >> 3, q = idx & 7;
-      const float4 v = (n < nout) ? __ldg(reinterpret_cast<const float4*>(w + (size_t)n * Cin + k0 + q * 4))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(Ws + n * kHeadLd + q * 4) = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kHeadKC; k += 4) {
-      float4 a[PT];
-#pragma unroll
-      for (int i = 0; i < PT; ++i) a[i] = *reinterpret_cast<const float4*>(As + (tm * PT + i) * kHeadLd + k);
-#pragma unroll
-      for (int j = 0; j < kHeadOut; ++j) {
-        const float4 wv = *reinterpret_cast<const float4*>(Ws + (tn + NTN * j) * kHeadLd + k);
-#pragma unroll
-        for (int i = 0; i < PT; ++i) {
-          acc[i][j] = fmaf(a[i].x, wv.x, acc[i][j]);
-          acc[i][j] = fmaf(a[i].y, wv.y, acc[i][j]);
-          acc[i][j] = fmaf(a[i].z, wv.z, acc[i][j]);
-          acc[i][j] = fmaf(a[i].w, wv.w, acc[i][j]);
-        }
-      }
-    }
-  }
-  // bias, squared norm of the descriptor part (the NTN threads of a pixel are adjacent lanes)
-  float ss[PT];
-#pragma unroll
-  for (int i = 0; i < PT; ++i) ss[i] = 0.f;
-#pragma unroll
-  for (int j = 0; j < kHeadOut; ++j) {
-    const int n = tn + NTN * j;
-    const float bias = (n < nout) ? __ldg(b + n) : 0.f;
-#pragma unroll
-    for (int i = 0; i < PT; ++i) {
-      acc[i][j] += bias;
-      if (n < Cout) ss[i] = fmaf(acc[i][j], acc[i][j], ss[i]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < PT; ++i) {
-#pragma unroll
-    for (int m = NTN >> 1; m >= 1; m >>= 1) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], m);
-  }
-  __syncthreads();                      // operands dead: reuse the buffer as the output stage
-  float* Os = smem;                     // [TM][Cout + 1 (pad)]
-  const int ldo = Cout + 1;
-#pragma unroll
-  for (int i = 0; i < PT; ++i) {
-    const int pl = tm * PT + i;
-    const float inv = normalize ? 1.f / fmaxf(sqrtf(ss[i]), 1e-12f) : 1.f;
-#pragma unroll
-    for (int j = 0; j < kHeadOut; ++j) {
-      const int n = tn + NTN * j;
-      if (n < Cout) Os[pl * ldo + n] = acc[i][j] * inv;
-      else if (n == Cout && p0 + pl < npix) conf[p0 + pl] = 1.f / (1.f + expf(acc[i][j]));   // sigmoid(-u)
-    }
+  for (int idx = threadIdx.x; idx < NT * 8 * (Cin / 4); idx += 256) {
+    const int n = idx / (Cin / 4), q = idx - n * (Cin / 4);
+    const float4 v = n < nout ? __ldg(reinterpret_cast<const float4*>(w + (size_t)n * Cin + q * 4))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    __half2* d = reinterpret_cast<__half2*>(sw + n * ws + q * 4);
+    d[0] = __floats2half2_rn(v.x, v.y);
+    d[1] = __floats2half2_rn(v.z, v.w);
   }
   __syncthreads();
-  const long long rem = npix - p0;
-  const int rows = rem < TM ? (int)rem : TM;
-  float* dst = feat + p0 * Cout;
-  for (int idx = threadIdx.x; idx < rows * Cout; idx += 256) {
-    const int pl = idx / Cout, c = idx - pl * Cout;
-    dst[idx] = Os[pl * ldo + c];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane >> 2, q2 = (lane & 3) * 2;
+  const int groups = (npix + 31) / 32;
+  for (int grp = blockIdx.x * 8 + warp; grp < groups; grp += gridDim.x * 8) {
+    const int p0 = grp * 32;
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+    const __half* xr[2][2];
+    bool ok[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int p = p0 + mt * 16 + h * 8 + r;
+        ok[mt][h] = p < npix;
+        xr[mt][h] = x + (size_t)(ok[mt][h] ? p : 0) * Cin + q2;
+      }
+    auto load_a = [&](int k, uint32_t (&a)[2][4]) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        a[mt][0] = ok[mt][0] ? __ldg(reinterpret_cast<const unsigned*>(xr[mt][0] + k)) : 0u;
+        a[mt][1] = ok[mt][1] ? __ldg(reinterpret_cast<const unsigned*>(xr[mt][1] + k)) : 0u;
+        a[mt][2] = ok[mt][0] ? __ldg(reinterpret_cast<const unsigned*>(xr[mt][0] + k + 8)) : 0u;
+        a[mt][3] = ok[mt][1] ? __ldg(reinterpret_cast<const unsigned*>(xr[mt][1] + k + 8)) : 0u;
+      }
+    };
+    uint32_t a[2][4], an[2][4];
+    load_a(0, a);
+    for (int k = 0; k < Cin; k += 16) {
+      if (k + 16 < Cin) load_a(k + 16, an);     // next K step's operand is in flight during this step's MMAs
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const __half* wr = sw + (nt * 8 + r) * ws + k + q2;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+        mma16816(acc[0][nt], a[0], b0, b1);
+        mma16816(acc[1][nt], a[1], b0, b1);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[mt][i] = an[mt][i];
+    }
+    // bias, squared norm (a pixel's row lives in the 4 lanes of a quad), scale, store
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int n = nt * 8 + q2;
+        const float b0 = n < nout ? __ldg(b + n) : 0.f, b1 = n + 1 < nout ? __ldg(b + n + 1) : 0.f;
+        acc[mt][nt][0] += b0; acc[mt][nt][1] += b1; acc[mt][nt][2] += b0; acc[mt][nt][3] += b1;
+        if (n < Cout) {        // Cout is a multiple of 8: both columns are descriptor channels
+          ss0 = fmaf(acc[mt][nt][0], acc[mt][nt][0], fmaf(acc[mt][nt][1], acc[mt][nt][1], ss0));
+          ss1 = fmaf(acc[mt][nt][2], acc[mt][nt][2], fmaf(acc[mt][nt][3], acc[mt][nt][3], ss1));
+        }
+      }
+      ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
+      ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
+      const float i0 = normalize ? 1.f / fmaxf(sqrtf(ss0), 1e-12f) : 1.f;
+      const float i1 = normalize ? 1.f / fmaxf(sqrtf(ss1), 1e-12f) : 1.f;
+      const int pa = p0 + mt * 16 + r, pb = pa + 8;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int n = nt * 8 + q2;
+        if (n < Cout) {
+          if (pa < npix) *reinterpret_cast<float2*>(feat + (size_t)pa * Cout + n) = make_float2(acc[mt][nt][0] * i0, acc[mt][nt][1] * i0);
+          if (pb < npix) *reinterpret_cast<float2*>(feat + (size_t)pb * Cout + n) = make_float2(acc[mt][nt][2] * i1, acc[mt][nt][3] * i1);
+        } else if (n == Cout) {   // uncertainty column: confidence = sigmoid(-u)
+          if (pa < npix) conf[pa] = 1.f / (1.f + expf(acc[mt][nt][0]));
+          if (pb < npix) conf[pb] = 1.f / (1.f + expf(acc[mt][nt][2]));
+        }
+      }
+    }
   }
 }
 
-template <int PT, int NTN>
-void launch_head(const __half* x, long long npix, int Cin, int Cout, const float* w, const float* b, float* feat,
-                 float* conf, int normalize, cudaStream_t s) {
-  constexpr int TM = HeadCfg<PT, NTN>::TM;
-  head_kernel<PT, NTN><<<(unsigned)((npix + TM - 1) / TM), 256, 0, s>>>(x, npix, Cin, Cout, w, b, feat, conf, normalize);
+template <int NT>
+int launch_head(const PtkContext* ctx, const __half* x, long long npix, int Cin, int Cout, const float* w, const float* b,
+                float* feat, float* conf, int normalize, cudaStream_t s) {
+  const int smem = NT * 8 * (Cin + 8) * 2;
+  static int configured = 0;
+  if (configured < smem) {
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(head_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const long long groups = (npix + 31) / 32;
+  long long blocks = (groups + 7) / 8;
+  const long long cap = 2LL * ctx->num_sms;
+  if (blocks > cap) blocks = cap;
+  head_mma_kernel<NT><<<(unsigned)blocks, 256, smem, s>>>(x, (int)npix, Cin, Cout, w, b, feat, conf, normalize);
+  return PTK_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,12 +477,12 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
     if (kHeadScale[l] == 4) { src = e->enc[4][3]; cin = 512; h = e->eh[4]; w = e->ew[4]; }
     else { const int di = 3 - kHeadScale[l]; src = e->dec[di]; cin = kDec[di]; h = e->dh[di]; w = e->dw[di]; }
     const long long npix = (long long)h * w;
-    if (kHeadDim[l] + 1 <= HeadCfg<4, 4>::TN)          // 32 (+1) outputs: 256 pixels per block
-      launch_head<4, 4>(src, npix, cin, kHeadDim[l], e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
-    else if (npix >= 64LL * 2 * e->ctx->num_sms)       // 128 (+1) outputs: 64 pixels per block
-      launch_head<4, 16>(src, npix, cin, kHeadDim[l], e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
-    else                                               // small maps: 16 pixels per block to fill the SMs
-      launch_head<1, 16>(src, npix, cin, kHeadDim[l], e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
+    int hrc;
+    if (kHeadDim[l] == 32)
+      hrc = launch_head<5>(e->ctx, src, npix, cin, 32, e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
+    else
+      hrc = launch_head<17>(e->ctx, src, npix, cin, 128, e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
+    if (hrc != PTK_OK) return hrc;
     mark();
   }
   PTK_CUDA_CHECK(cudaGetLastError());
