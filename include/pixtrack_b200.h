@@ -295,6 +295,21 @@ int64_t ptk_nerf_grid_entries(int32_t aabb_scale);
 int ptk_nerf_render(PtkNerf* n, const PtkNerfView* view, float* out_rgba, uint8_t* out_u8, float* out_depth,
                     void* stream);
 
+/* ------------------------------------------------------------------------
+ * Query-frame object mask.
+ *
+ * Replaces PixLocPoseTrackerR9.get_mask and the multiply in refine()
+ *   pixtrack/pose_trackers/pixloc_tracker_r9.py:207-214,224-225:
+ *   mask = dilate_5x5^5(erode_5x5((depth != 0))) with OpenCV's default
+ *   morphology border (outside pixels ignored), query = query * mask.
+ * depth_u8: [H][W][3] uint8, the depth-mode render (ptk_nerf_render out_u8).
+ * image / out_image: [H][W][3], img_dtype 0 = fp32, 1 = uint8 (may alias);
+ *   both NULL to get only the mask.  out_mask: [H][W][3] uint8 0/1 or NULL.
+ * workspace: device scratch of at least 2 * H * W * 3 bytes.
+ * ---------------------------------------------------------------------- */
+int ptk_query_mask(PtkContext* ctx, const uint8_t* depth_u8, int32_t H, int32_t W, const void* image,
+                   int32_t img_dtype, void* out_image, uint8_t* out_mask, uint8_t* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,7 @@ class FrameTracker:
                               [l.to(dev) for l in lams], mask=self.valid, pad=pad, **lm_conf)
         self._use_graph, self._captured = use_graph, False
         self._ref_bufs = {}
+        self._masked = None
 
     def refresh_reference(self, view: int, image: Tensor, camera, T_w2cam, scale_image: int = 1):
         """image: CUDA [H,W,3] uint8/fp32 render of reference view `view`; camera / T_w2cam: its camera at the
@@ -75,9 +76,16 @@ class FrameTracker:
         sample_reference(feats, confs, scales, camera, T_w2cam, self.p3d64, pad=self.pad, normalize=True,
                          out=([f[view] for f in self.F_ref], [w[view] for w in self.W_ref], self.valid[view]))
 
-    def track(self, image: Tensor, T_init: Optional[Tensor] = None):
-        """image: CUDA [H,W,3] uint8/fp32 query frame.  Returns (T [B,12], failed [B]) device tensors;
-        stream-ordered, no synchronisation."""
+    def track(self, image: Tensor, T_init: Optional[Tensor] = None, mask_depth: Optional[Tensor] = None):
+        """image: CUDA [H,W,3] uint8/fp32 query frame.  mask_depth: optional CUDA uint8 [H,W,3] depth-mode NeRF
+        render at the query resolution; the frame is then multiplied by the eroded/dilated object mask first
+        (r9.py:207-214,224-225), on the device.  Returns (T [B,12], failed [B]) device tensors; stream-ordered,
+        no synchronisation."""
+        if mask_depth is not None:
+            from .mask import query_mask
+            if self._masked is None or self._masked.shape != image.shape or self._masked.dtype != image.dtype:
+                self._masked = torch.empty_like(image)
+            image, _ = query_mask(mask_depth, image, out=self._masked)
         if self._use_graph and not self._captured:
             self.plan.capture()
             self._captured = True
