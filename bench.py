@@ -268,7 +268,6 @@ def run_ours(args, rank, world, local_rank):
     ms_total = shard.max_over_ranks(ev0.elapsed_time(ev1), dev)
     _lib.device_status(local_rank)
     clk = clocks.stop() if rank == 0 else None
-    launches_per_step = 2 * 32 + 1 + 3          # 2 extractor plans, 1 sampling launch, 3 LM launches (one graph)
 
     # ---- results of the last ring pass: LM iteration counts, failures, pose error vs ground truth ------
     iters, errs, ok = [], [], True
@@ -371,7 +370,7 @@ def run_ours(args, rank, world, local_rank):
                        'median_pose_error_deg_m_vs_gt': errs},
             'e2e': {'value': args.steps * world / float(e2e_s), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h},
-            'gpu_launches': launches_per_step * args.steps, 'clocks': clk, 'roofline': roofline,
+            'gpu_launches': (2 * len(rows) + 1 + 3) * args.steps,   # per frame: 2 extractor plans, 1 sampler, 3 LM launches (one graph) 'clocks': clk, 'roofline': roofline,
             'roofline_lm': stress, 'extractor_plan': plan_prof, 'nerf_render': nerf, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)

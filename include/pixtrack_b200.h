@@ -218,7 +218,7 @@ typedef struct PtkUnetWeights {
   const void* conv_w[20];   /* [0]: fp32 [64][28] ((ky,kx,c) taps + 1 pad); [1..19]: fp16 [9][C_out][C_in];
                                16 encoder convs then 4 decoder convs (BatchNorm folded in)              */
   const float* conv_b[20];  /* fp32 [C_out]                                                             */
-  const float* head_w[3];   /* fp32 [C_l + 1][C_in]: adaptation rows, last row = uncertainty head       */
+  const void* head_w[3];    /* fp16 [C_l + 1][C_in]: adaptation rows, last row = uncertainty head       */
   const float* head_b[3];   /* fp32 [C_l + 1]                                                           */
 } PtkUnetWeights;
 

@@ -41,6 +41,7 @@ struct ConvParams {
   int tiles_w;
   const float* bias;   // [Cout] fp32
   __half* out;         // [H][W][Cout]
+  __half* pool;        // optional [H/2][W/2][Cout]: 2x2 max pool of `out`, written by the same epilogue
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,6 +120,23 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+
+// 2x2 max pool inside a warp: the four pixels of a pooling window sit in lanes l, l^1 (x neighbour) and l^kYBit
+// (y neighbour).  max commutes with the fp16 rounding, so pooling the packed outputs equals pooling `out`.
+template <int kYBit>
+__device__ __forceinline__ void pool_quad(uint32_t (&pw)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    __half2 v = *reinterpret_cast<__half2*>(&pw[j]);
+    uint32_t o = __shfl_xor_sync(0xffffffffu, pw[j], 1);
+    v = __hmax2(v, *reinterpret_cast<__half2*>(&o));
+    uint32_t cur = *reinterpret_cast<uint32_t*>(&v);
+    o = __shfl_xor_sync(0xffffffffu, cur, kYBit);
+    v = __hmax2(v, *reinterpret_cast<__half2*>(&o));
+    pw[j] = *reinterpret_cast<uint32_t*>(&v);
+  }
 }
 
 template <int BLOCK_N, int STAGES>
@@ -216,27 +234,38 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
+    const bool pool_writer = P.pool != nullptr && ((lane & 17) == 0) && (h >> 1) < (P.H >> 1) && (w >> 1) < (P.W >> 1);
+    __half* prow = P.pool != nullptr ? P.pool + ((size_t)(h >> 1) * (P.W >> 1) + (w >> 1)) * P.Cout + n0 : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N; c += 32) {
       uint32_t v[32];
       tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (inside) {
-        uint4 pk[4];
-        uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+      uint32_t pw[16];
+      const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);   // 32 consecutive biases, 16-byte loads
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a = __uint_as_float(v[2 * j]) + __ldg(P.bias + n0 + c + 2 * j);
-          float b = __uint_as_float(v[2 * j + 1]) + __ldg(P.bias + n0 + c + 2 * j + 1);
-          if (P.relu) {
-            a = fmaxf(a, 0.f);
-            b = fmaxf(b, 0.f);
-          }
-          const __half2 hv = __floats2half2_rn(a, b);
-          pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+      for (int j = 0; j < 16; ++j) {
+        const float4 bq = __ldg(b4 + (j >> 1));
+        float a = __uint_as_float(v[2 * j]) + ((j & 1) ? bq.z : bq.x);
+        float b = __uint_as_float(v[2 * j + 1]) + ((j & 1) ? bq.w : bq.y);
+        if (P.relu) {
+          a = fmaxf(a, 0.f);
+          b = fmaxf(b, 0.f);
         }
+        const __half2 hv = __floats2half2_rn(a, b);
+        pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+      }
+      if (inside) {
         uint4* dst = reinterpret_cast<uint4*>(orow + c);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = pk[j];
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
+      }
+      if (P.pool != nullptr) {   // x neighbour = lane ^ 1, y neighbour = lane ^ 16
+        pool_quad<16>(pw);
+        if (pool_writer) {
+          uint4* dst = reinterpret_cast<uint4*>(prow + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
+        }
       }
     }
   }
@@ -280,6 +309,7 @@ struct HaloParams {
   int rows_per_op;       // halo rows per TMA operation (the halo is fetched as 18 / rows_per_op boxes in flight)
   const float* bias;
   __half* out;
+  __half* pool;          // optional [H/2][W/2][Cout]: 2x2 max pool of `out`, written by the same epilogue
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -442,27 +472,38 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int w = tw * 16 + 8 * sx + xx;
         const bool inside = (h < P.H) && (w < P.W);
         __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
+        const bool pool_writer = P.pool != nullptr && ((lane & 9) == 0) && (h >> 1) < (P.H >> 1) && (w >> 1) < (P.W >> 1);
+        __half* prow = P.pool != nullptr ? P.pool + ((size_t)(h >> 1) * (P.W >> 1) + (w >> 1)) * P.Cout + n0 : nullptr;
 #pragma unroll 1
         for (int c = 0; c < N; c += 32) {
           uint32_t v[32];
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2u + (uint32_t)sx) * (uint32_t)N + (uint32_t)c, v);
-          if (inside) {
-            uint4 pk[4];
-            uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+          uint32_t pw[16];
+          const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);   // 32 consecutive biases, 16-byte loads
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a = __uint_as_float(v[2 * j]) + __ldg(P.bias + n0 + c + 2 * j);
-              float b = __uint_as_float(v[2 * j + 1]) + __ldg(P.bias + n0 + c + 2 * j + 1);
-              if (P.relu) {
-                a = fmaxf(a, 0.f);
-                b = fmaxf(b, 0.f);
-              }
-              const __half2 hv = __floats2half2_rn(a, b);
-              pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+          for (int j = 0; j < 16; ++j) {
+            const float4 bq = __ldg(b4 + (j >> 1));
+            float a = __uint_as_float(v[2 * j]) + ((j & 1) ? bq.z : bq.x);
+            float b = __uint_as_float(v[2 * j + 1]) + ((j & 1) ? bq.w : bq.y);
+            if (P.relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
             }
+            const __half2 hv = __floats2half2_rn(a, b);
+            pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+          }
+          if (inside) {
             uint4* dst = reinterpret_cast<uint4*>(orow + c);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = pk[j];
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
+          }
+          if (P.pool != nullptr) {   // x neighbour = lane ^ 1, y neighbour = lane ^ 8
+            pool_quad<8>(pw);
+            if (pool_writer) {
+              uint4* dst = reinterpret_cast<uint4*>(prow + c);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
+            }
           }
         }
       }
@@ -563,9 +604,10 @@ static int pick_block_n(int Cout, int m_tiles, int num_sms) {
   return bn;
 }
 
-extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H,
-                            int32_t W, int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights,
-                            const float* bias, int32_t Cout, int32_t taps, int32_t relu, void* out, void* stream) {
+// ptk_conv_f16 plus an optional fused 2x2 max pool of the result (the extractor plan's encoder blocks)
+int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
+                      int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
+                      int32_t Cout, int32_t taps, int32_t relu, void* out, void* pool_out, void* stream) {
   PTK_REQUIRE(ctx && in0 && weights && bias && out, "null argument");
   PTK_REQUIRE(taps == 9 || taps == 1, "taps must be 9 (3x3, pad 1) or 1 (1x1)");
   PTK_REQUIRE(cin0 > 0 && cin0 % kKChunk == 0 && cin1 >= 0 && cin1 % kKChunk == 0, "C_in must be a multiple of 64");
@@ -620,6 +662,7 @@ extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, cons
       Q.rows_per_op = rows_per_op;
       Q.bias = bias;
       Q.out = (__half*)out;
+      Q.pool = (__half*)pool_out;
       const int grid = total < ctx->num_sms ? total : ctx->num_sms;
       switch (n_halo) {
         case 32: return launch_halo<32>(a0, a1, wm, Q, grid, s);
@@ -633,6 +676,7 @@ extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, cons
   P.tiles_w = (W + kTileW - 1) / kTileW;
   P.bias = bias;
   P.out = (__half*)out;
+  P.pool = (__half*)pool_out;
   const int m_tiles = P.tiles_w * ((H + kTileH - 1) / kTileH);
   const int bn = pick_block_n(Cout, m_tiles, ctx->num_sms);
   rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, bn, 1);
@@ -645,4 +689,11 @@ extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, cons
     case 128: return launch_conv<128, 3>(a0, a1, wm, P, s);
     default: return launch_conv<256, 3>(a0, a1, wm, P, s);
   }
+}
+
+extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H,
+                            int32_t W, int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights,
+                            const float* bias, int32_t Cout, int32_t taps, int32_t relu, void* out, void* stream) {
+  return ptk_conv_f16_pool(ctx, in0, cin0, in1, cin1, H, W, in0_H, in0_W, in1_H, in1_W, weights, bias, Cout, taps, relu, out,
+                           nullptr, stream);
 }

@@ -14,6 +14,9 @@
 extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H,
                             int32_t W, int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights,
                             const float* bias, int32_t Cout, int32_t taps, int32_t relu, void* out, void* stream);
+int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
+                      int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
+                      int32_t Cout, int32_t taps, int32_t relu, void* out, void* pool_out, void* stream);
 
 namespace {
 
@@ -55,61 +58,109 @@ __global__ void prep_image_kernel(const TIn* __restrict__ in, int Hi, int Wi, fl
 }
 
 // ---------------------------------------------------------------------------------------------
-// First VGG layer: 3 -> 64 channels, 3x3, pad 1, bias, ReLU.  K = 27 is too thin for the tensor
-// cores; fp32 CUDA-core direct convolution, one pixel x 64 channels per thread.
+// First VGG layer: 3 -> 64 channels, 3x3, pad 1, bias, ReLU.  K = 27 (padded to 32) is too thin for a
+// tcgen05 tile; it runs on the warp-level tensor cores (mma.sync m16n8k16, fp16 operands, fp32 accumulate).
+// A block owns a 16 x 16 pixel tile: the fp32 image tile + halo goes to shared memory as fp16, a warp takes two
+// rows of 16 pixels (two m16 tiles) and builds its im2col A fragments by gathering 16-bit values from the tile
+// (column j = ky*9 + kx*3 + c of pixel x is tile[y + ky][3*x + j - 9*ky]); the 64 x 32 weight matrix lives in
+// registers as B fragments for the whole kernel (persistent blocks).  The CUDA-core version this replaces was
+// shared-memory-bandwidth bound at 21 TFLOP/s (95 us at 1024 x 576).
 // w: [64][28] fp32 (27 taps ordered (ky, kx, c) + 1 pad), out: fp16 [H][W][64]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv1_direct_kernel(const float* __restrict__ img, int H, int W,
-                                                           const float* __restrict__ w, const float* __restrict__ bias,
-                                                           __half* __restrict__ out) {
-  __shared__ __align__(16) float sw[64 * 28];
-  __shared__ float sb[64];
-  __shared__ float tile[18][18 * 3];
-  for (int i = threadIdx.x; i < 64 * 28; i += 256) sw[i] = w[i];
-  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
-  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
-  for (int i = threadIdx.x; i < 18 * 18 * 3; i += 256) {
-    const int ty = i / 54, r = i - ty * 54;
-    const int tx = r / 3, c = r - tx * 3;
-    const int gy = y0 + ty - 1, gx = x0 + tx - 1;
-    tile[ty][r] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[((size_t)gy * W + gx) * 3 + c] : 0.f;
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kC1Stride = 18 * 3 + 2;   // halfs per tile row (56: keeps rows 4-byte aligned)
+
+__global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict__ img, int H, int W,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        __half* __restrict__ out, int tiles_x, int tiles) {
+  __shared__ __half tile[18 * kC1Stride];
+  __shared__ __half sw[64 * 40];           // [n][k] fp16, k padded 27 -> 32 (+8 to spread the banks)
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+    const int n = i >> 5, k = i & 31;
+    sw[n * 40 + k] = __float2half_rn(k < 27 ? w[n * 28 + k] : 0.f);
   }
   __syncthreads();
-  const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
-  const int x = x0 + lx, y = y0 + ly;
-  if (x >= W || y >= H) return;
-  float in[28];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane >> 2, q2 = (lane & 3) * 2;
+  // B fragments of the whole weight matrix: 8 n-tiles x 2 k-steps
+  uint32_t bf[8][2][2];
+  float bia[8][2];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+  for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-    for (int j = 0; j < 9; ++j) in[ky * 9 + j] = tile[ly + ky][lx * 3 + j];
-  in[27] = 0.f;
-  __half* o = out + ((size_t)y * W + x) * 64;
-#pragma unroll 1
-  for (int c8 = 0; c8 < 64; c8 += 8) {
-    uint4 pk;
-    uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-      float acc[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float4* wr = reinterpret_cast<const float4*>(sw + (c8 + j + e) * 28);
-        float a = sb[c8 + j + e];
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-          const float4 wv = wr[q];
-          a = fmaf(in[4 * q], wv.x, a);
-          a = fmaf(in[4 * q + 1], wv.y, a);
-          a = fmaf(in[4 * q + 2], wv.z, a);
-          a = fmaf(in[4 * q + 3], wv.w, a);
-        }
-        acc[e] = fmaxf(a, 0.f);
-      }
-      const __half2 hv = __floats2half2_rn(acc[0], acc[1]);
-      pw[j >> 1] = *reinterpret_cast<const uint32_t*>(&hv);
+    for (int kk = 0; kk < 2; ++kk) {
+      const __half* wr = sw + (nt * 8 + r) * 40 + kk * 16 + q2;
+      bf[nt][kk][0] = *reinterpret_cast<const uint32_t*>(wr);
+      bf[nt][kk][1] = *reinterpret_cast<const uint32_t*>(wr + 8);
     }
-    *reinterpret_cast<uint4*>(o + c8) = pk;
+    bia[nt][0] = bias[nt * 8 + q2];
+    bia[nt][1] = bias[nt * 8 + q2 + 1];
+  }
+  // im2col offsets of this lane's 8 A columns: j = kk*16 + q2 + {0, 1, 8, 9}
+  int off[2][4];
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = kk * 16 + q2 + (e & 1) + (e >> 1) * 8;
+      off[kk][e] = j < 27 ? (j / 9) * kC1Stride + (j % 9) : -1;
+    }
+  const __half hz = __float2half_rn(0.f);
+
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int x0 = tx * 16, y0 = ty * 16;
+    __syncthreads();   // previous tile fully consumed
+    for (int i = threadIdx.x; i < 18 * 54; i += 256) {
+      const int yy = i / 54, rr = i - yy * 54;
+      const int xx = rr / 3, c = rr - xx * 3;
+      const int gy = y0 + yy - 1, gx = x0 + xx - 1;
+      const float v = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[((size_t)gy * W + gx) * 3 + c] : 0.f;
+      tile[yy * kC1Stride + rr] = __float2half_rn(v);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int ly = warp * 2 + mt;                 // tile row of this m16 tile
+      const __half* base0 = tile + ly * kC1Stride + r * 3;          // pixel r
+      const __half* base1 = base0 + 8 * 3;                          // pixel r + 8
+      uint32_t a[2][4];
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        __half v[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[e] = off[kk][e] >= 0 ? base0[off[kk][e]] : hz;       // row r:     cols (q2, q2+1, q2+8, q2+9)
+          v[4 + e] = off[kk][e] >= 0 ? base1[off[kk][e]] : hz;   // row r + 8
+        }
+        const __half2 p0 = __halves2half2(v[0], v[1]), p1 = __halves2half2(v[4], v[5]);
+        const __half2 p2 = __halves2half2(v[2], v[3]), p3 = __halves2half2(v[6], v[7]);
+        a[kk][0] = *reinterpret_cast<const uint32_t*>(&p0);
+        a[kk][1] = *reinterpret_cast<const uint32_t*>(&p1);
+        a[kk][2] = *reinterpret_cast<const uint32_t*>(&p2);
+        a[kk][3] = *reinterpret_cast<const uint32_t*>(&p3);
+      }
+      const int y = y0 + ly;
+      const int xa = x0 + r, xb = xa + 8;
+      __half* oa = out + ((size_t)y * W + xa) * 64 + q2;
+      __half* ob = out + ((size_t)y * W + xb) * 64 + q2;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float c[4] = {bia[nt][0], bia[nt][1], bia[nt][0], bia[nt][1]};
+        mma16816(c, a[0], bf[nt][0][0], bf[nt][0][1]);
+        mma16816(c, a[1], bf[nt][1][0], bf[nt][1][1]);
+        if (y < H) {
+          if (xa < W) *reinterpret_cast<__half2*>(oa + nt * 8) = __floats2half2_rn(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
+          if (xb < W) *reinterpret_cast<__half2*>(ob + nt * 8) = __floats2half2_rn(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
+        }
+      }
+    }
   }
 }
 
@@ -168,46 +219,53 @@ __global__ void upsample2_kernel(const __half* __restrict__ in, int H, int W, in
 // Heads (unet.py:47-50,177-188): 1x1 adaptation conv C_in -> C_out plus the 1x1 uncertainty conv
 // (-> 1 channel), confidence = sigmoid(-u); optional per-pixel L2 normalisation of the descriptor
 // (base_refiner.py:92-94) fused in.  fp16 activations in, fp32 out.
-// w: [C_out + 1][C_in] fp32 (row C_out = uncertainty), b: [C_out + 1].
+// w: [C_out + 1][C_in] fp16 (row C_out = uncertainty), b: [C_out + 1] fp32.
 //
 // A [pixels x C_in] x [C_in x (C_out+1)] GEMM on the warp-level tensor cores (mma.sync m16n8k16, fp16
 // operands, fp32 accumulate): the op is ~1 GMAC in total and bound by the 78 MB it writes at level 0, far too
 // small / too oddly shaped (33 and 129 output columns, K = 32) for a tcgen05 tile, and the CUDA-core version
 // it replaces was shared-memory-bandwidth bound at 5-10 TFLOP/s.  A warp owns 32 pixels: A fragments come
-// straight from the channels-last activation in global memory, the weights (converted to fp16) sit in shared
+// straight from the channels-last activation in global memory, the fp16 weights sit in shared
 // memory with a conflict-free row stride, each pixel's outputs stay in the accumulator fragments of 4 lanes,
 // so the squared norm is two shuffles, and rows leave as 8-byte stores (32 B contiguous per pixel and n-tile).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 // NT n-tiles of 8 output columns: NT*8 >= C_out + 1 (5 for 32+1, 17 for 128+1)
 template <int NT>
 __global__ void __launch_bounds__(256) head_mma_kernel(const __half* __restrict__ x, int npix, int Cin, int Cout,
-                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       const __half* __restrict__ w, const float* __restrict__ b,
                                                        float* __restrict__ feat, float* __restrict__ conf,
-                                                       int normalize) {
+                                                       int normalize, int wpb) {
   extern __shared__ __align__(16) __half sw[];   // [NT*8][Cin + 8]
   const int ws = Cin + 8;
   const int nout = Cout + 1;
-  for (int idx = threadIdx.x; idx < NT * 8 * (Cin / 4); idx += 256) {
-    const int n = idx / (Cin / 4), q = idx - n * (Cin / 4);
-    const float4 v = n < nout ? __ldg(reinterpret_cast<const float4*>(w + (size_t)n * Cin + q * 4))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-    __half2* d = reinterpret_cast<__half2*>(sw + n * ws + q * 4);
-    d[0] = __floats2half2_rn(v.x, v.y);
-    d[1] = __floats2half2_rn(v.z, v.w);
+  const int c8 = Cin >> 3;                        // 16-byte pieces per weight row
+  for (int idx = threadIdx.x; idx < NT * 8 * c8; idx += 256) {
+    const int n = idx / c8, q = idx - n * c8;
+    const uint4 v = n < nout ? __ldg(reinterpret_cast<const uint4*>(w + (size_t)n * Cin) + q) : make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sw + n * ws + q * 8) = v;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, q2 = (lane & 3) * 2;
   const int groups = (npix + 31) / 32;
-  for (int grp = blockIdx.x * 8 + warp; grp < groups; grp += gridDim.x * 8) {
+  __half* sa = sw + NT * 8 * ws;                  // [wpb * 32 pixels][Cin + 8] activations of this round
+  // wpb warps of the block take a group of 32 pixels each per round; all 8 warps stage the round's activations
+  // (coalesced 16-byte loads, one round trip) -- per-lane fragment loads from global memory left the single
+  // compute warp of a small map waiting on L2 once per K step
+  for (int base = blockIdx.x * wpb; base < groups; base += gridDim.x * wpb) {
+    __syncthreads();
+    const int pbase = base * 32;
+    for (int idx = threadIdx.x; idx < wpb * 32 * c8; idx += 256) {
+      const int pl = idx / c8, q = idx - pl * c8;
+      const int p = pbase + pl;
+      const uint4 v = p < npix ? __ldg(reinterpret_cast<const uint4*>(x + (size_t)p * Cin) + q) : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sa + pl * ws + q * 8) = v;
+    }
+    __syncthreads();
+    const int grp = base + warp;
+    if (warp >= wpb || grp >= groups) continue;
     const int p0 = grp * 32;
+    const __half* ta = sa + warp * 32 * ws;
     float acc[2][NT][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -215,29 +273,16 @@ __global__ void __launch_bounds__(256) head_mma_kernel(const __half* __restrict_
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-    const __half* xr[2][2];
-    bool ok[2][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int p = p0 + mt * 16 + h * 8 + r;
-        ok[mt][h] = p < npix;
-        xr[mt][h] = x + (size_t)(ok[mt][h] ? p : 0) * Cin + q2;
-      }
-    auto load_a = [&](int k, uint32_t (&a)[2][4]) {
+    for (int k = 0; k < Cin; k += 16) {
+      uint32_t a[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        a[mt][0] = ok[mt][0] ? __ldg(reinterpret_cast<const unsigned*>(xr[mt][0] + k)) : 0u;
-        a[mt][1] = ok[mt][1] ? __ldg(reinterpret_cast<const unsigned*>(xr[mt][1] + k)) : 0u;
-        a[mt][2] = ok[mt][0] ? __ldg(reinterpret_cast<const unsigned*>(xr[mt][0] + k + 8)) : 0u;
-        a[mt][3] = ok[mt][1] ? __ldg(reinterpret_cast<const unsigned*>(xr[mt][1] + k + 8)) : 0u;
+        const __half* ar = ta + (mt * 16 + r) * ws + k + q2;
+        a[mt][0] = *reinterpret_cast<const uint32_t*>(ar);
+        a[mt][1] = *reinterpret_cast<const uint32_t*>(ar + 8 * ws);
+        a[mt][2] = *reinterpret_cast<const uint32_t*>(ar + 8);
+        a[mt][3] = *reinterpret_cast<const uint32_t*>(ar + 8 * ws + 8);
       }
-    };
-    uint32_t a[2][4], an[2][4];
-    load_a(0, a);
-    for (int k = 0; k < Cin; k += 16) {
-      if (k + 16 < Cin) load_a(k + 16, an);     // next K step's operand is in flight during this step's MMAs
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const __half* wr = sw + (nt * 8 + r) * ws + k + q2;
@@ -245,10 +290,6 @@ __global__ void __launch_bounds__(256) head_mma_kernel(const __half* __restrict_
         mma16816(acc[0][nt], a[0], b0, b1);
         mma16816(acc[1][nt], a[1], b0, b1);
       }
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[mt][i] = an[mt][i];
     }
     // bias, squared norm (a pixel's row lives in the 4 lanes of a quad), scale, store
 #pragma unroll
@@ -285,19 +326,21 @@ __global__ void __launch_bounds__(256) head_mma_kernel(const __half* __restrict_
 }
 
 template <int NT>
-int launch_head(const PtkContext* ctx, const __half* x, long long npix, int Cin, int Cout, const float* w, const float* b,
+int launch_head(const PtkContext* ctx, const __half* x, long long npix, int Cin, int Cout, const __half* w, const float* b,
                 float* feat, float* conf, int normalize, cudaStream_t s) {
-  const int smem = NT * 8 * (Cin + 8) * 2;
+  const long long groups = (npix + 31) / 32;
+  long long wpb = (groups + ctx->num_sms - 1) / ctx->num_sms;
+  wpb = wpb < 1 ? 1 : (wpb > 8 ? 8 : wpb);
+  const int smem = (NT * 8 + (int)wpb * 32) * (Cin + 8) * 2;
   static int configured = 0;
   if (configured < smem) {
     PTK_CUDA_CHECK(cudaFuncSetAttribute(head_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  const long long groups = (npix + 31) / 32;
-  long long blocks = (groups + 7) / 8;
+  long long blocks = (groups + wpb - 1) / wpb;
   const long long cap = 2LL * ctx->num_sms;
   if (blocks > cap) blocks = cap;
-  head_mma_kernel<NT><<<(unsigned)blocks, 256, smem, s>>>(x, (int)npix, Cin, Cout, w, b, feat, conf, normalize);
+  head_mma_kernel<NT><<<(unsigned)blocks, 256, smem, s>>>(x, (int)npix, Cin, Cout, w, b, feat, conf, normalize, (int)wpb);
   return PTK_OK;
 }
 
@@ -419,8 +462,12 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
   mark();
   // ---- encoder (unet.py:163-167) ----
   int li = 0;
-  conv1_direct_kernel<<<dim3((W + 15) / 16, (H + 15) / 16), 256, 0, s>>>(e->img, H, W, (const float*)e->wts.conv_w[0],
-                                                                       e->wts.conv_b[0], e->enc[0][0]);
+  {
+    const int tiles_x = (W + 15) / 16, tiles = tiles_x * ((H + 15) / 16);
+    const int grid = tiles < 4 * e->ctx->num_sms ? tiles : 4 * e->ctx->num_sms;
+    conv1_mma_kernel<<<grid, 256, 0, s>>>(e->img, H, W, (const float*)e->wts.conv_w[0], e->wts.conv_b[0], e->enc[0][0],
+                                          tiles_x, tiles);
+  }
   PTK_CUDA_CHECK(cudaGetLastError());
   mark();
   li = 1;
@@ -431,18 +478,14 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
     if (b == 0) {
       cur = e->enc[0][0];
       ccur = 64;
-    } else {
-      const int cprev = kEncBlocks[b - 1][kEncCount[b - 1] - 1];
-      const long long n = (long long)h * w * (cprev / 8);
-      maxpool2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(e->enc[b - 1][kEncCount[b - 1] - 1], e->eh[b - 1],
-                                                                  e->ew[b - 1], cprev, e->pool[b - 1]);
+    } else {   // the 2x2 max pool of the previous block was written by that block's last convolution
       cur = e->pool[b - 1];
-      ccur = cprev;
-      mark();
+      ccur = kEncBlocks[b - 1][kEncCount[b - 1] - 1];
     }
     for (int i = (b == 0 ? 1 : 0); i < kEncCount[b]; ++i) {
-      const int rc = ptk_conv_f16(e->ctx, cur, ccur, nullptr, 0, h, w, h, w, 0, 0, e->wts.conv_w[li], e->wts.conv_b[li],
-                                  kEncBlocks[b][i], 9, 1, e->enc[b][i], stream);
+      void* pool_out = (i == kEncCount[b] - 1 && b < 4) ? (void*)e->pool[b] : nullptr;
+      const int rc = ptk_conv_f16_pool(e->ctx, cur, ccur, nullptr, 0, h, w, h, w, 0, 0, e->wts.conv_w[li], e->wts.conv_b[li],
+                                       kEncBlocks[b][i], 9, 1, e->enc[b][i], pool_out, stream);
       if (rc != PTK_OK) return rc;
       mark();
       cur = e->enc[b][i];
@@ -479,9 +522,9 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
     const long long npix = (long long)h * w;
     int hrc;
     if (kHeadDim[l] == 32)
-      hrc = launch_head<5>(e->ctx, src, npix, cin, 32, e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
+      hrc = launch_head<5>(e->ctx, src, npix, cin, 32, (const __half*)e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
     else
-      hrc = launch_head<17>(e->ctx, src, npix, cin, 128, e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
+      hrc = launch_head<17>(e->ctx, src, npix, cin, 128, (const __half*)e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
     if (hrc != PTK_OK) return hrc;
     mark();
   }
@@ -512,7 +555,6 @@ extern "C" int ptk_extractor_profile(PtkExtractor* e, const void* image, int32_t
   put(1, 2.0 * e->H * e->W * 27.0 * 64.0);
   for (int b = 0; b < 5; ++b) {
     int ccur = (b == 0) ? 64 : kEncBlocks[b - 1][kEncCount[b - 1] - 1];
-    if (b > 0) put(2, 0.0);
     for (int i = (b == 0 ? 1 : 0); i < kEncCount[b]; ++i) {
       put(3, 2.0 * e->eh[b] * e->ew[b] * 9.0 * ccur * kEncBlocks[b][i]);
       ccur = kEncBlocks[b][i];

@@ -59,7 +59,7 @@ def pack_weights(sd: Dict[str, Tensor], device) -> Dict[str, List[Tensor]]:
     head_w, head_b = [], []
     for l in range(3):
         wa, wu = sd[f'adaptation.{l}.0.weight'], sd[f'uncertainty.{l}.0.weight']
-        head_w.append(torch.cat([wa.reshape(wa.shape[0], -1), wu.reshape(1, -1)], 0).contiguous())
+        head_w.append(torch.cat([wa.reshape(wa.shape[0], -1), wu.reshape(1, -1)], 0).to(torch.float16).contiguous())
         head_b.append(torch.cat([sd[f'adaptation.{l}.0.bias'], sd[f'uncertainty.{l}.0.bias']]).contiguous())
     return dict(conv_w=conv_w, conv_b=conv_b, head_w=head_w, head_b=head_b)
 
