@@ -252,37 +252,59 @@ __device__ __forceinline__ void load_a(const __half* __restrict__ tile, int lane
   a[3] = *reinterpret_cast<const uint32_t*>(tile + (r + 8) * STRIDE + c + 8);
 }
 
-// hash-grid features of one sample -> 32 halfs in the warp's feature tile row (kernel_grid)
+// hash-grid features of one sample -> 32 halfs in the warp's feature tile row (kernel_grid).
+// Per level: the 8 corner indices (dense levels: x + y*res + z*res^2, wrapped once past the end like the
+// reference's `% size`; hashed levels: x ^ y*2654435761 ^ z*805459861 masked to 2^19), 8 independent 4-byte
+// gathers, then the trilinear blend accumulated in fp16 exactly like kernel_grid (weight * value rounded to
+// fp16, added in fp16, corner order x fastest).
+__device__ __forceinline__ void hash_level(const __half2* __restrict__ g, const uint32_t (&ix)[2], const uint32_t (&iy)[2],
+                                           const uint32_t (&iz)[2], bool hashed, uint32_t size, float wx, float wy,
+                                           float wz, __half* __restrict__ dst) {
+  __half2 v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t idx;
+    if (hashed) {
+      idx = (ix[c & 1] ^ iy[(c >> 1) & 1] ^ iz[c >> 2]) & (size - 1u);   // hashed levels hold 2^19 entries
+    } else {
+      idx = ix[c & 1] + iy[(c >> 1) & 1] + iz[c >> 2];
+      idx -= idx >= size ? size : 0u;                                    // == idx % size: idx < 2 * size here
+    }
+    v[c] = __ldg(g + idx);
+  }
+  const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
+  __half2 acc = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float w = 1.f;
+    w *= (c & 1) ? wx : ux;
+    w *= (c & 2) ? wy : uy;
+    w *= (c & 4) ? wz : uz;
+    const float2 f = __half22float2(v[c]);
+    acc = __hadd2(acc, __floats2half2_rn(w * f.x, w * f.y));
+  }
+  *reinterpret_cast<__half2*>(dst) = acc;
+}
+
 __device__ __forceinline__ void hash_encode(const NerfParams& P, float x, float y, float z, __half* __restrict__ row) {
-#pragma unroll 4
+#pragma unroll 2
   for (int l = 0; l < 16; ++l) {
     const NerfLevel lv = P.lv[l];
     const float fx = x * lv.scale + 0.5f, fy = y * lv.scale + 0.5f, fz = z * lv.scale + 0.5f;
     const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     const uint32_t gx = (uint32_t)(int)flx, gy = (uint32_t)(int)fly, gz = (uint32_t)(int)flz;
-    const float wx = fx - flx, wy = fy - fly, wz = fz - flz;
-    const __half2* g = P.grid + lv.offset;
-    __half2 v[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint32_t cx = gx + (c & 1), cy = gy + ((c >> 1) & 1), cz = gz + (c >> 2);
-      uint32_t idx;
-      if (lv.hashed) idx = (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (lv.size - 1u);   // hashed levels hold 2^19
-      else idx = (cx + cy * lv.res + cz * lv.res * lv.res) % lv.size;
-      v[c] = __ldg(g + idx);
+    uint32_t ix[2], iy[2], iz[2];
+    if (lv.hashed) {   // uniform per level
+      ix[0] = gx; ix[1] = gx + 1u;
+      iy[0] = gy * 2654435761u; iy[1] = (gy + 1u) * 2654435761u;
+      iz[0] = gz * 805459861u; iz[1] = (gz + 1u) * 805459861u;
+    } else {
+      const uint32_t r2 = lv.res * lv.res;
+      ix[0] = gx; ix[1] = gx + 1u;
+      iy[0] = gy * lv.res; iy[1] = iy[0] + lv.res;
+      iz[0] = gz * r2; iz[1] = iz[0] + r2;
     }
-    __half ax = __float2half(0.f), ay = __float2half(0.f);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float w = 1.f;
-      w *= (c & 1) ? wx : 1.f - wx;
-      w *= (c & 2) ? wy : 1.f - wy;
-      w *= (c & 4) ? wz : 1.f - wz;
-      const float2 f = __half22float2(v[c]);
-      ax = __hadd(ax, __float2half_rn(w * f.x));
-      ay = __hadd(ay, __float2half_rn(w * f.y));
-    }
-    *reinterpret_cast<__half2*>(row + 2 * l) = __halves2half2(ax, ay);
+    hash_level(P.grid + lv.offset, ix, iy, iz, lv.hashed != 0, lv.size, fx - flx, fy - fly, fz - flz, row + 2 * l);
   }
 }
 

@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0, '.')
+import sys; sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np, torch
 from pixtrack_b200 import synthetic as syn
 from pixtrack_b200.nerf import NerfTestbed, occupancy_bitfield
