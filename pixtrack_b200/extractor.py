@@ -138,16 +138,18 @@ class B200FeatureExtractor(torch.nn.Module):
                 return int(round(h * s)), int(round(w * s)), (s, s)
         return h, w, (1.0, 1.0)
 
-    def plan(self, H: int, W: int) -> _Plan:
-        if (H, W) not in self._plans:
-            self._plans[(H, W)] = _Plan(self._lib, self._ctx, self._wts, H, W)
-        return self._plans[(H, W)]
+    def plan(self, H: int, W: int, slot: int = 0) -> _Plan:
+        """Plans own their activation arena: use a different `slot` for extractions that may run concurrently on
+        different streams (e.g. the reference view next to the query frame)."""
+        if (H, W, slot) not in self._plans:
+            self._plans[(H, W, slot)] = _Plan(self._lib, self._ctx, self._wts, H, W)
+        return self._plans[(H, W, slot)]
 
     def level_shapes(self, ih: int, iw: int, scale_image: int = 1):
         H, W, _ = self.network_size(ih, iw, scale_image)
         return self.plan(H, W).shapes
 
-    def extract_device(self, image: Tensor, scale_image: int = 1, normalize: bool = False, out=None):
+    def extract_device(self, image: Tensor, scale_image: int = 1, normalize: bool = False, out=None, slot: int = 0):
         """image: CUDA [H,W,3] RGB, fp32 in 0..255 or uint8.  Returns (feats_hwc list [H_l,W_l,C_l], confs list
         [H_l,W_l], scales); nothing is synchronised.  `out=(feats, confs)` writes into caller-owned buffers
         (static addresses for prepared LM launches / CUDA graphs)."""
@@ -155,7 +157,7 @@ class B200FeatureExtractor(torch.nn.Module):
         assert image.shape[2] == 3
         ih, iw = image.shape[:2]
         H, W, sr = self.network_size(ih, iw, scale_image)
-        plan = self.plan(H, W)
+        plan = self.plan(H, W, slot)
         if out is None:
             feats = [torch.empty((h, w, c), dtype=torch.float32, device=self.device) for c, h, w in plan.shapes]
             confs = [torch.empty((h, w), dtype=torch.float32, device=self.device) for c, h, w in plan.shapes]

@@ -33,7 +33,8 @@ Tensor = torch.Tensor
 
 class FrameTracker:
     def __init__(self, extractor: B200FeatureExtractor, image_hw, camera: Tensor, p3d: Tensor, lams: Sequence[Tensor],
-                 n_views: int, scale_image: int = 1, use_graph: bool = True, pad: int = 1, **lm_conf):
+                 n_views: int, scale_image: int = 1, use_graph: bool = True, pad: int = 1,
+                 overlap_reference: bool = True, **lm_conf):
         """camera: [n_cam] query camera at the IMAGE resolution; p3d [N,3] model points (float64 kept for
         the reference-side projection, float32 copy for the LM); lams[l] [6] damping per level;
         lm_conf -> LmLaunch (num_iters, stop criteria)."""
@@ -60,6 +61,10 @@ class FrameTracker:
         self._use_graph, self._captured = use_graph, False
         self._ref_bufs = {}
         self._masked = None
+        # the reference-view refresh runs on a side stream next to the query extraction (its low-occupancy layers
+        # overlap the other plan's); the LM launches wait for it through an event
+        self._side = torch.cuda.Stream(dev) if overlap_reference else None
+        self._ref_done = None
 
     def refresh_reference(self, view: int, image: Tensor, camera, T_w2cam, scale_image: int = 1):
         """image: CUDA [H,W,3] uint8/fp32 render of reference view `view`; camera / T_w2cam: its camera at the
@@ -72,9 +77,21 @@ class FrameTracker:
             self._ref_bufs[key] = ([torch.empty((h, w, c), dtype=torch.float32, device=dev) for c, h, w in shapes],
                                    [torch.empty((h, w), dtype=torch.float32, device=dev) for c, h, w in shapes])
         bufs = self._ref_bufs[key]
-        feats, confs, scales = self.extractor.extract_device(image, scale_image, normalize=False, out=bufs)
-        sample_reference(feats, confs, scales, camera, T_w2cam, self.p3d64, pad=self.pad, normalize=True,
-                         out=([f[view] for f in self.F_ref], [w[view] for w in self.W_ref], self.valid[view]))
+        dev = self.extractor.device
+        if self._side is None:
+            feats, confs, scales = self.extractor.extract_device(image, scale_image, normalize=False, out=bufs)
+            sample_reference(feats, confs, scales, camera, T_w2cam, self.p3d64, pad=self.pad, normalize=True,
+                             out=([f[view] for f in self.F_ref], [w[view] for w in self.W_ref], self.valid[view]))
+            return
+        cur = torch.cuda.current_stream(dev)
+        self._side.wait_stream(cur)          # the previous frame's LM has finished reading the observation cache
+        with torch.cuda.stream(self._side):
+            feats, confs, scales = self.extractor.extract_device(image, scale_image, normalize=False, out=bufs, slot=1)
+            sample_reference(feats, confs, scales, camera, T_w2cam, self.p3d64, pad=self.pad, normalize=True,
+                             out=([f[view] for f in self.F_ref], [w[view] for w in self.W_ref], self.valid[view]))
+            self._ref_done = torch.cuda.Event()
+            self._ref_done.record(self._side)
+        image.record_stream(self._side)
 
     def track(self, image: Tensor, T_init: Optional[Tensor] = None, mask_depth: Optional[Tensor] = None):
         """image: CUDA [H,W,3] uint8/fp32 query frame.  mask_depth: optional CUDA uint8 [H,W,3] depth-mode NeRF
@@ -92,5 +109,8 @@ class FrameTracker:
         if T_init is not None:
             self.T_init.copy_(T_init, non_blocking=True)
         self.extractor.extract_device(image, self.scale_image, normalize=True, out=(self.feats, self.confs))
+        if self._ref_done is not None:       # observations refreshed on the side stream must be complete
+            torch.cuda.current_stream(self.extractor.device).wait_event(self._ref_done)
+            self._ref_done = None
         self.plan.run()
         return self.plan.T, self.plan.failed
