@@ -371,6 +371,10 @@ struct PtkExtractor {
   // optional per-launch timing (ptk_extractor_profile): events recorded after every launch
   cudaEvent_t* prof_ev;
   int prof_n;
+  // the coarse heads run next to the decoder on a side stream (forked / joined with events, so the
+  // plan is still one stream-ordered unit for the caller and can be captured in a CUDA graph)
+  cudaStream_t side;
+  cudaEvent_t ev_fork[2], ev_join;
 };
 #define PTK_MAX_LAUNCHES 48
 
@@ -412,12 +416,18 @@ extern "C" int ptk_extractor_create(PtkContext* ctx, const PtkUnetWeights* w, in
     e->up[i] = (__half*)take((size_t)e->dh[i] * e->dw[i] * cprev * 2);
     e->dec[i] = (__half*)take((size_t)e->dh[i] * e->dw[i] * kDec[i] * 2);
   }
+  PTK_CUDA_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) PTK_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming));
+  PTK_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   *out = e;
   return PTK_OK;
 }
 
 extern "C" void ptk_extractor_destroy(PtkExtractor* e) {
   if (e == nullptr) return;
+  if (e->side) cudaStreamDestroy(e->side);
+  for (int i = 0; i < 2; ++i) if (e->ev_fork[i]) cudaEventDestroy(e->ev_fork[i]);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->arena) cudaFree(e->arena);
   free(e);
 }
@@ -493,6 +503,27 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
       ++li;
     }
   }
+  // ---- heads (unet.py:175-188): pre_features fine -> coarse = dec[3], dec[2], dec[1], dec[0], enc[4] ----
+  auto run_head = [&](int l, cudaStream_t hs) -> int {
+    const __half* src;
+    int cin, h, w;
+    if (kHeadScale[l] == 4) { src = e->enc[4][3]; cin = 512; h = e->eh[4]; w = e->ew[4]; }
+    else { const int di = 3 - kHeadScale[l]; src = e->dec[di]; cin = kDec[di]; h = e->dh[di]; w = e->dw[di]; }
+    const long long npix = (long long)h * w;
+    if (kHeadDim[l] == 32)
+      return launch_head<5>(e->ctx, src, npix, cin, 32, (const __half*)e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, hs);
+    return launch_head<17>(e->ctx, src, npix, cin, 128, (const __half*)e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, hs);
+  };
+  // The two coarse heads only need the encoder output / the second decoder block: they run on the plan's side
+  // stream next to the remaining decoder convolutions (which leave SMs idle at these map sizes).  With per-launch
+  // profiling on, everything stays on the caller's stream.
+  const bool fork = e->prof_ev == nullptr;
+  if (fork) {
+    PTK_CUDA_CHECK(cudaEventRecord(e->ev_fork[0], s));
+    PTK_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->ev_fork[0], 0));
+    const int hrc = run_head(2, e->side);
+    if (hrc != PTK_OK) return hrc;
+  }
   // ---- decoder (unet.py:169-173; DecoderBlock.forward :33-44) ----
   const __half* prev = e->enc[4][3];
   int cprev = 512, ph = e->eh[4], pw = e->ew[4];
@@ -507,26 +538,32 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
                                 1, e->dec[i], stream);
     if (rc != PTK_OK) return rc;
     mark();
+    if (fork && i == 1) {   // dec[1] feeds the level-1 head
+      PTK_CUDA_CHECK(cudaEventRecord(e->ev_fork[1], s));
+      PTK_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->ev_fork[1], 0));
+      const int hrc = run_head(1, e->side);
+      if (hrc != PTK_OK) return hrc;
+    }
     prev = e->dec[i];
     cprev = kDec[i];
     ph = e->dh[i];
     pw = e->dw[i];
     ++li;
   }
-  // ---- heads (unet.py:175-188): pre_features fine -> coarse = dec[3], dec[2], dec[1], dec[0], enc[4] ----
-  for (int l = 0; l < 3; ++l) {
-    const __half* src;
-    int cin, h, w;
-    if (kHeadScale[l] == 4) { src = e->enc[4][3]; cin = 512; h = e->eh[4]; w = e->ew[4]; }
-    else { const int di = 3 - kHeadScale[l]; src = e->dec[di]; cin = kDec[di]; h = e->dh[di]; w = e->dw[di]; }
-    const long long npix = (long long)h * w;
-    int hrc;
-    if (kHeadDim[l] == 32)
-      hrc = launch_head<5>(e->ctx, src, npix, cin, 32, (const __half*)e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
-    else
-      hrc = launch_head<17>(e->ctx, src, npix, cin, 128, (const __half*)e->wts.head_w[l], e->wts.head_b[l], feat[l], conf[l], normalize, s);
+  {
+    const int hrc = run_head(0, s);
     if (hrc != PTK_OK) return hrc;
     mark();
+  }
+  if (fork) {
+    PTK_CUDA_CHECK(cudaEventRecord(e->ev_join, e->side));
+    PTK_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
+  } else {
+    for (int l = 1; l < 3; ++l) {
+      const int hrc = run_head(l, s);
+      if (hrc != PTK_OK) return hrc;
+      mark();
+    }
   }
   PTK_CUDA_CHECK(cudaGetLastError());
   return PTK_OK;

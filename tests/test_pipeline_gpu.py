@@ -1,0 +1,104 @@
+"""GPU: the whole per-frame hot path (FrameTracker: two extractions, reference sampling, 3-level LM chain, optional
+device-side mask) against the CPU oracle pipeline on the same frame.
+
+The LM alone is held to 1e-4 rad / 1e-3 on identical feature maps (tests/test_lm_parity_gpu.py).  End to end the
+extractor runs on fp16 tensor-core operands while the oracle UNet is fp32, which perturbs the features by ~1e-2
+relative and moves the optimum slightly: the poses of the two pipelines are required to agree within 2e-3 rad and
+2e-3 translation units (about 10x below the distance of either to the ground truth on this noisy scene), the
+iteration counts within +-1, and nothing may fail.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lm, unet
+from pixtrack_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+STOP = dict(num_iters=150, grad_stop=1e-4, dt_stop=5e-3, dR_stop=5e-2)
+N_VIEWS, N = 3, 800
+
+
+def _rot_angle(Ra, Rb):
+    c = ((Ra @ Rb.transpose(-1, -2)).diagonal(dim1=-2, dim2=-1).sum(-1) - 1) / 2
+    return torch.acos(c.clamp(-1, 1))
+
+
+def _setup(overlap=True):
+    from pixtrack_b200.extractor import B200FeatureExtractor
+    from pixtrack_b200.pipeline import FrameTracker
+    dev = torch.device('cuda:0')
+    seq = syn.tracked_sequence(7, n_frames=1, N=N, n_views=N_VIEWS, query_wh=(640, 360), ref_wh=(448, 336))
+    sd = syn.unet_weights(0)
+    ext = B200FeatureExtractor(sd, dev)
+    lam = lm.damping_lambda(torch.zeros(6))
+    fr = seq['frames'][0]
+    trk = FrameTracker(ext, fr['img_q'].shape[:2], seq['cam_q'], seq['p3d'], [lam.to(dev)] * 3, N_VIEWS,
+                       overlap_reference=overlap, **STOP)
+    return dev, seq, sd, lam, fr, trk
+
+
+def _run(trk, dev, seq, fr, mask_depth=None):
+    T_ref = torch.cat([fr['R_r'].reshape(-1), fr['t_r']])
+    for v in range(N_VIEWS):
+        trk.refresh_reference(v, fr['img_r'].to(dev), seq['cam_r'], T_ref)
+    T, failed = trk.track(fr['img_q'].to(dev), fr['T_init'].to(dev), mask_depth=mask_depth)
+    torch.cuda.synchronize()
+    return T.clone(), failed.clone(), [n.clone() for n in trk.plan.n_iters]
+
+
+def test_frame_tracker_matches_the_oracle_pipeline():
+    dev, seq, sd, lam, fr, trk = _setup()
+    T, failed, n_it = _run(trk, dev, seq, fr)
+    assert not bool(failed.any())
+    # oracle: the reference's per-frame path restated on the CPU (bench.py's CpuFrame does the same)
+    fr_f, sc_r, cf_r = unet.extract(sd, fr['img_r'].numpy().astype(np.float32))
+    maps_r = [torch.cat([f, c], 0) for f, c in zip(fr_f, cf_r)]
+    obs, keep = lm.sample_reference(maps_r, sc_r, seq['cam_r'], fr['R_r'], fr['t_r'], seq['p3d'])
+    fq, sc_q, cf_q = unet.extract(sd, fr['img_q'].numpy().astype(np.float32))
+    maps_q = [torch.cat([f, c], 0) for f, c in zip(fq, cf_q)]
+    assert int(trk.valid[0].sum()) == int(keep.sum())              # same points kept by the reference sampler
+    for v in range(N_VIEWS):
+        T0 = fr['T_init'][v]
+        out = lm.refine_levels(maps_q, sc_q, seq['cam_q'].float(), T0[:9].reshape(3, 3), T0[9:], [o[keep] for o in obs],
+                               seq['p3d'][keep].float(), [lam] * 3, **STOP)
+        assert out['success']
+        Tg = T[v].cpu()
+        dR = float(_rot_angle(Tg[:9].reshape(3, 3).double(), out['R'].double()))
+        dt = float((Tg[9:].double() - out['t'].double()).norm())
+        assert dR < 2e-3 and dt < 2e-3, (v, dR, dt)
+        gt_R = float(_rot_angle(out['R'].double(), fr['R_q']))
+        assert dR < 0.5 * max(gt_R, 1e-3) or dR < 5e-4            # far inside the distance to the ground truth
+        its = [int(n[v]) for n in n_it]
+        ref_its = [r['n_iters'] for r in out['runs']]
+        assert all(abs(a - b) <= 1 for a, b in zip(its, ref_its)), (its, ref_its)
+    from pixtrack_b200 import _lib
+    _lib.device_status(0)
+
+
+def test_side_stream_overlap_does_not_change_results():
+    dev, seq, _, _, fr, trk = _setup(overlap=True)
+    a = _run(trk, dev, seq, fr)
+    b = _run(trk, dev, seq, fr)                                     # re-run on the captured graph
+    dev, seq, _, _, fr, trk2 = _setup(overlap=False)
+    c = _run(trk2, dev, seq, fr)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    assert all(torch.equal(x, y) for x, y in zip(a[2], c[2]))
+
+
+def test_mask_hook_equals_masking_the_frame_first():
+    from pixtrack_b200.mask import query_mask
+    dev, seq, _, _, fr, trk = _setup()
+    H, W = fr['img_q'].shape[:2]
+    depth = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+    depth[40:320, 100:560] = 77                                     # the object's depth render (non-zero = object)
+    T1, f1, _ = _run(trk, dev, seq, fr, mask_depth=depth)
+    masked, m = query_mask(depth, fr['img_q'].to(dev), want_mask=True)
+    assert 0 < int(m.sum()) < m.numel()
+    _, _, _, _, _, trk2 = _setup()
+    T_ref = torch.cat([fr['R_r'].reshape(-1), fr['t_r']])
+    for v in range(N_VIEWS):
+        trk2.refresh_reference(v, fr['img_r'].to(dev), seq['cam_r'], T_ref)
+    T2, f2 = trk2.track(masked, fr['T_init'].to(dev))
+    torch.cuda.synchronize()
+    assert torch.equal(T1, T2) and torch.equal(f1, f2)
