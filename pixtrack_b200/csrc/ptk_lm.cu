@@ -725,8 +725,11 @@ extern "C" int ptk_lm_run(PtkContext* ctx, const PtkLmProblem* prob, const PtkLm
   PTK_REQUIRE(p.H >= 2 && p.W >= 2, "map must be at least 2x2");
   PTK_REQUIRE(p.n_cam == 6 || p.n_cam == 8 || p.n_cam == 10, "n_cam must be 6, 8 or 10");
   PTK_REQUIRE(p.num_iters >= 0 && p.pad >= 0, "num_iters and pad must be >= 0");
-  PTK_REQUIRE(p.p3d && p.f_ref && p.fq && p.cam && p.T_init && p.lambda, "null input pointer");
-  PTK_REQUIRE((p.w_ref == nullptr) == (p.wq == nullptr), "w_ref and wq must be given together");
+  // N == 0 (every point dropped upstream) is legal: the per-point arrays may then be null; the launch fails the
+  // problems at the first iteration like learned_optimizer.py:65 does with an empty p3D
+  PTK_REQUIRE(p.fq && p.cam && p.T_init && p.lambda, "null input pointer");
+  PTK_REQUIRE(p.N == 0 || (p.p3d && p.f_ref), "null point / descriptor pointer");
+  PTK_REQUIRE(p.N == 0 || (p.w_ref == nullptr) == (p.wq == nullptr), "w_ref and wq must be given together");
   PTK_REQUIRE(res->T && res->failed && res->n_iters, "null output pointer");
   PTK_REQUIRE(((uintptr_t)p.fq % 16 == 0) && ((uintptr_t)p.f_ref % 16 == 0), "fq and f_ref must be 16-byte aligned");
   PTK_REQUIRE((p.fq_bstride % 4 == 0) && (p.f_ref_bstride % 4 == 0), "batch strides of fq/f_ref must be multiples of 4");

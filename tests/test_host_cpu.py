@@ -84,3 +84,43 @@ def test_geometry_wrappers():
     np.testing.assert_allclose(I.numpy(), np.r_[np.eye(3).ravel(), 0, 0, 0], atol=1e-6)
     dr, dt = T.magnitude()
     np.testing.assert_allclose(float(dr), np.degrees(np.linalg.norm([0.1, -0.2, 0.3])), rtol=1e-5)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_install_and_adapters_fail_loudly_without_cuda():
+    """install() on a reference-shaped localizer must raise instead of leaving the PyTorch path in place."""
+    from types import SimpleNamespace
+    from pixtrack_b200 import _lib, synthetic as syn
+    from pixtrack_b200.install import install
+    from pixtrack_b200.nerf import NerfTestbed
+    from pixtrack_b200.mask import query_mask
+
+    class RefOpt(torch.nn.Module):                       # what BaseOptimizer exposes (base_optimizer.py:23-60)
+        def __init__(self):
+            super().__init__()
+            self.conf = dict(num_iters=150, loss_fn='scaled_barron(0, 0.1)', jacobi_scaling=False, normalize_features=False,
+                             grad_stop_criteria=1e-4, dt_stop_criteria=5e-3, dR_stop_criteria=5e-2,
+                             interpolation=dict(mode='linear', pad=1), damping=dict(type='constant', log_range=[-6, 5]))
+            self.dampingnet = SimpleNamespace(const=torch.nn.Parameter(torch.zeros(6)))
+            self.logging_fn = None
+    unet = torch.nn.Module()
+    unet.state_dict = lambda: syn.unet_weights(0)
+    ref_ext = SimpleNamespace(conf=SimpleNamespace(resize=1024, resize_by='max'), model=unet, device=torch.device('cpu'))
+    loc = SimpleNamespace(optimizer=[RefOpt(), RefOpt(), RefOpt()], extractor=ref_ext,
+                          refiner=SimpleNamespace(optimizer=None, feature_extractor=None, tracker=None))
+    with pytest.raises(_lib.PtkError):
+        install(loc)
+    assert isinstance(loc.optimizer[0], RefOpt)          # nothing was half-swapped
+    with pytest.raises(_lib.PtkError):
+        NerfTestbed(np.zeros((8, 2), np.float16), [np.zeros((64, 32)), np.zeros((16, 64))],
+                    [np.zeros((64, 32)), np.zeros((64, 64)), np.zeros((16, 64))], np.zeros(8 * 128 ** 3 // 8, np.uint8), 1, 'cpu')
+    with pytest.raises(_lib.PtkError):
+        query_mask(torch.zeros(4, 4, 3, dtype=torch.uint8))
+
+
+def test_shared_structs_match_the_header_layout():
+    from pixtrack_b200 import _lib
+    assert ctypes.sizeof(_lib.NerfModelStruct) == 8 + 8 + 5 * 8 + 8 + 4 + 4
+    assert ctypes.sizeof(_lib.NerfView) == (12 + 3 + 3 + 3 + 4 + 4) * 4
+    assert ctypes.sizeof(_lib.RefLevel) == 4 * 8 + 2 * 8 + 4 * 4
+    assert ctypes.sizeof(_lib.UnetWeights) == (20 + 20 + 3 + 3) * 8
