@@ -67,6 +67,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (!done && ++spins > (1u << 22)) __trap();   // never hang the GPU on a protocol bug
   }
 }
+// mbar_wait that adds the cycles spent waiting to `acc` (stall attribution, PTK_CONV_DBG)
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc, bool timed) {
+  if (!timed) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
                                             int c2) {
   asm volatile(
@@ -291,14 +301,16 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 // (3072 B) apart.  The tensor core applies the 128B swizzle to the absolute shared-memory address
 // bits (measured: the descriptor's base-offset field must stay 0 for a start that is not
 // 1024-B aligned), so the shifted view reads exactly what TMA wrote.  Two M=128 MMAs (the two half tiles) share each weight tile, the weights of a
-// layer with <= 72 KB of them stay resident in shared memory, accumulators are double-buffered in
+// layer with <= 112 KB of them stay resident in shared memory, accumulators are double-buffered in
 // TMEM so the epilogue of one tile overlaps the MMAs of the next, and CTAs are persistent.
 // Staged bytes per flop drop 2.5-5x against conv_tc_kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int kHaloW = 24, kHaloH = 18;
 constexpr int kHaloBytes = kHaloW * kHaloH * 128;      // 55296
-constexpr int kBBudget = 73728;                        // weight slots: 72 KB
-constexpr int kHaloThreads = 192;
+constexpr int kBBudget = 114688;                       // weight slots: 112 KB (7 x 16 KB at N = 128: the ring has to
+                                                       // cover ~2 us of commit -> refill -> TMA round trip)
+constexpr int kHaloThreads = 192;      // CTA-pair kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kHalo1Threads = 320;     // single-CTA kernel: TMA warp, MMA warp, 8 epilogue warps (4 per half tile)
 
 struct HaloParams {
   int H, W, Cout;
@@ -307,6 +319,7 @@ struct HaloParams {
   int tiles_w, tiles_hw, total_tiles;
   int resident;          // all taps x chunks weight tiles fit the slots and Cout == N: load them once
   int rows_per_op;       // halo rows per TMA operation (the halo is fetched as 18 / rows_per_op boxes in flight)
+  long long* dbg;        // optional (PTK_CONV_DBG=1): cycles CTA 0 spent waiting on each barrier kind
   const float* bias;
   __half* out;
   __half* pool;          // optional [H/2][W/2][Cout]: 2x2 max pool of `out`, written by the same epilogue
@@ -317,7 +330,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <int N>
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                     const __grid_constant__ CUtensorMap tmA1,
                                                                     const __grid_constant__ CUtensorMap tmW,
                                                                     const HaloParams P) {
@@ -349,7 +362,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       mbar_init(&fullA[s], 1);
       mbar_init(&emptyA[s], 1);
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 8);
     }
     for (int s = 0; s < kSlots; ++s) {
       mbar_init(&fullB[s], 1);
@@ -373,13 +386,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       // ---------------- TMA producer ----------------
       uint32_t a_it = 0, b_it = 0;
       bool first = true;
+      const bool timed = P.dbg != nullptr && blockIdx.x == 0;
+      long long wA = 0, wB = 0;
+      const long long tstart = clock64();
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
         const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
         const int h0 = th * 16, w0 = tw * 16, n0 = nb * N;
         for (int c = 0; c < chunks; ++c) {
           const int sa = a_it & 1;
-          mbar_wait(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u);
+          mbar_wait_t(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u, wA, timed);
           mbar_expect_tx(&fullA[sa], kHaloBytes);
           for (int r = 0; r < kHaloH; r += P.rows_per_op) {
             uint8_t* dst = sA + sa * kHaloBytes + r * (kHaloW * 128);
@@ -394,7 +410,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 sb = c * 9 + tap;
               } else {
                 sb = b_it % kSlots;
-                mbar_wait(&emptyB[sb], ((b_it / kSlots) & 1u) ^ 1u);
+                mbar_wait_t(&emptyB[sb], ((b_it / kSlots) & 1u) ^ 1u, wB, timed);
               }
               mbar_expect_tx(&fullB[sb], kBBytes);
               tma_load_3d(sB + sb * kBBytes, &tmW, &fullB[sb], c * kKChunk, n0, tap);
@@ -404,47 +420,66 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
         first = false;
       }
+      if (timed) {
+        P.dbg[0] = clock64() - tstart;
+        P.dbg[1] = wA;
+        P.dbg[2] = wB;
+      }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues ----------------
     uint32_t a_it = 0, b_it = 0, t_it = 0;
+    const bool timed = P.dbg != nullptr && blockIdx.x == 0;
+    long long wT = 0, wA = 0, wB = 0;
+    const long long tstart = clock64();
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++t_it) {
       const uint32_t buf = t_it & 1u;
-      mbar_wait(&tmem_empty[buf], ((t_it >> 1) & 1u) ^ 1u);
+      mbar_wait_t(&tmem_empty[buf], ((t_it >> 1) & 1u) ^ 1u, wT, timed);
       tc_fence_after();
       for (int c = 0; c < chunks; ++c) {
         const int sa = a_it & 1;
-        mbar_wait(&fullA[sa], (a_it >> 1) & 1u);
+        mbar_wait_t(&fullA[sa], (a_it >> 1) & 1u, wA, timed);
         ++a_it;
         const uint32_t abase = smem_u32(sA + sa * kHaloBytes);
         // descriptor of tap (0,0) of half tile 0; the other taps / half tile are constant offsets of it
         const uint64_t adesc0 = (uint64_t)((abase & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) |
                                 ((uint64_t)((kHaloW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        // Taps are issued in groups of three: one elected region per group keeps the tensor pipe's queue fed
+        // across tap boundaries (every elect / fence / barrier poll between MMAs is a bubble when the MMAs
+        // are short: 41 cycles at N = 32).
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          int sb;
-          if (P.resident) {
-            sb = c * 9 + tap;
-            if (t_it == 0) mbar_wait(&fullB[sb], 0);
-          } else {
-            sb = b_it % kSlots;
-            mbar_wait(&fullB[sb], (b_it / kSlots) & 1u);
-            ++b_it;
+        for (int tg = 0; tg < 3; ++tg) {
+          int sb[3];
+#pragma unroll
+          for (int t3 = 0; t3 < 3; ++t3) {
+            const int tap = tg * 3 + t3;
+            if (P.resident) {
+              sb[t3] = c * 9 + tap;
+              if (t_it == 0) mbar_wait_t(&fullB[sb[t3]], 0, wB, timed);
+            } else {
+              sb[t3] = b_it % kSlots;
+              mbar_wait_t(&fullB[sb[t3]], (b_it / kSlots) & 1u, wB, timed);
+              ++b_it;
+            }
           }
           tc_fence_after();
-          const uint64_t bdesc = make_sw128_desc(smem_u32(sB + sb * kBBytes));
           if (elect_one()) {
 #pragma unroll
-            for (int sx = 0; sx < 2; ++sx) {
-              // start row of this tap's view: ((1+dy)*24 + 8*sx + 1+dx), 128 B per row, >> 4 in the descriptor
-              const int row0 = (tap / 3) * kHaloW + 8 * sx + (tap % 3);
-              const uint64_t adesc = adesc0 + (uint64_t)(row0 * 8);
-              const uint32_t d = tmem_base + (buf * 2u + (uint32_t)sx) * (uint32_t)N;
+            for (int t3 = 0; t3 < 3; ++t3) {
+              const int tap = tg * 3 + t3;
+              const uint64_t bdesc = make_sw128_desc(smem_u32(sB + sb[t3] * kBBytes));
 #pragma unroll
-              for (int k = 0; k < kKChunk / 16; ++k)
-                tc_mma_f16(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (c | tap | k) != 0 ? 1u : 0u);
+              for (int sx = 0; sx < 2; ++sx) {
+                // start row of this tap's view: ((1+dy)*24 + 8*sx + 1+dx), 128 B per row, >> 4 in the descriptor
+                const int row0 = (tap / 3) * kHaloW + 8 * sx + (tap % 3);
+                const uint64_t adesc = adesc0 + (uint64_t)(row0 * 8);
+                const uint32_t d = tmem_base + (buf * 2u + (uint32_t)sx) * (uint32_t)N;
+#pragma unroll
+                for (int k = 0; k < kKChunk / 16; ++k)
+                  tc_mma_f16(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (c | tap | k) != 0 ? 1u : 0u);
+              }
+              if (!P.resident) tc_commit(&emptyB[sb[t3]]);
             }
-            if (!P.resident) tc_commit(&emptyB[sb]);
           }
           __syncwarp();
         }
@@ -454,21 +489,32 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       if (elect_one()) tc_commit(&tmem_full[buf]);
       __syncwarp();
     }
+    if (timed && lane == 0) {
+      P.dbg[3] = clock64() - tstart;
+      P.dbg[4] = wT;
+      P.dbg[5] = wA;
+      P.dbg[6] = wB;
+      P.dbg[7] = t_it;
+    }
   } else {
-    // ---------------- epilogue: 4 warps, TMEM lane quadrant q = rows 32q .. 32q+31 of both half tiles ----------------
+    // ---------------- epilogue: 8 warps; warp w reads TMEM lane quadrant q = w % 4 (rows 32q .. 32q+31) of half
+    //                  tile sx = (w - 2) / 4, so the two half tiles drain in parallel ----------------
     const int q = warp & 3;
+    const int sx = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int y = m >> 3, xx = m & 7;
     uint32_t t_it = 0;
+    const bool timed = P.dbg != nullptr && blockIdx.x == 0 && warp == 2;   // warp 2: quadrant 2 of half tile 0
+    long long wF = 0;
+    const long long tstart = clock64();
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++t_it) {
       const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
       const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
       const int h = th * 16 + y, n0 = nb * N;
       const uint32_t buf = t_it & 1u;
-      mbar_wait(&tmem_full[buf], (t_it >> 1) & 1u);
+      mbar_wait_t(&tmem_full[buf], (t_it >> 1) & 1u, wF, timed);
       tc_fence_after();
-#pragma unroll 1
-      for (int sx = 0; sx < 2; ++sx) {
+      {
         const int w = tw * 16 + 8 * sx + xx;
         const bool inside = (h < P.H) && (w < P.W);
         __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
@@ -511,12 +557,259 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
+    if (timed && lane == 0) {
+      P.dbg[8] = clock64() - tstart;
+      P.dbg[9] = wF;
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_halo2_kernel: the halo kernel on CTA pairs (tcgen05 cta_group::2) for C_out = k * 256.
+//
+// A single-CTA MMA in SS mode is bounded by its operand fetch from shared memory (measured: cycles per
+// M=128 MMA ~ (A bytes + B bytes) / 64, 147 cycles at N=128 against a floor of 64).  A CTA pair issues
+// M=256 x N=256 MMAs: each SM still supplies its own 128 A rows but only HALF of the B rows, so the
+// operand bytes per SM and per flop halve and the MMA runs at its floor (128 cycles per K=16 step).
+// The pair owns two horizontally adjacent 16x16 tiles (CTA r: tile 2*pair + r): every CTA stages the halo
+// of its own tile and rows [128 r, 128 r + 128) of each 256-row weight tile; TMA completions of both
+// CTAs land on the leader's (rank 0) mbarriers, the leader's MMA warp issues for the pair and releases
+// stages / publishes accumulators with multicast commits, and both CTAs run the epilogue on their own
+// TMEM lanes (2 half tiles x 256 columns = all 512 columns, so the epilogue is not overlapped).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPairN = 256;
+constexpr int kPairBBytes = (kPairN / 2) * 128;      // this CTA's half of a weight tile: 16 KB
+constexpr int kPairSlots = 7;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the mbarrier at the same offset in the pair's leader CTA
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                                 int c2) {
+  const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;   // clear the peer bit: rank 0's copy of the barrier
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on rank 0's copy of `bar`
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(bar)));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+    conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                      const __grid_constant__ CUtensorMap tmW, const HaloParams P) {
+  constexpr int N = kPairN;
+  constexpr uint32_t kTmemCols = 512;
+  // D=F32, A=B=F16 K-major, N >> 3 at bit 17, M (= 256 for the pair) >> 4 at bit 24
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2 * kHaloBytes;
+  uint64_t* fullA = (uint64_t*)(sB + kPairSlots * kPairBBytes);
+  uint64_t* emptyA = fullA + 2;
+  uint64_t* fullB = emptyA + 2;
+  uint64_t* emptyB = fullB + kPairSlots;
+  uint64_t* tmem_full = emptyB + kPairSlots;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int chunks = P.chunks0 + P.chunks1;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    if (P.chunks1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&emptyA[s], 1);
+    }
+    for (int s = 0; s < kPairSlots; ++s) {
+      mbar_init(&fullB[s], 1);
+      mbar_init(&emptyB[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 8);        // 4 epilogue warps of each CTA arrive on the leader's copy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                // barriers of both CTAs initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs: own halo, own half of the weight rows) ----------------
+      uint32_t a_it = 0, b_it = 0;
+      for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs) {
+        const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
+        const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;     // tiles_w counts PAIRS of 16-pixel columns
+        const int h0 = th * 16, w0 = (tw * 2 + (int)rank) * 16, n0 = nb * N + (int)rank * (N / 2);
+        for (int c = 0; c < chunks; ++c) {
+          const int sa = a_it & 1;
+          mbar_wait(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u);
+          if (leader) mbar_expect_tx(&fullA[sa], 2 * kHaloBytes);    // both CTAs' halos are credited here
+          for (int r = 0; r < kHaloH; r += P.rows_per_op) {
+            uint8_t* dst = sA + sa * kHaloBytes + r * (kHaloW * 128);
+            if (c < P.chunks0) tma_load_3d_pair(dst, &tmA0, &fullA[sa], c * kKChunk, w0 - 1, h0 - 1 + r);
+            else tma_load_3d_pair(dst, &tmA1, &fullA[sa], (c - P.chunks0) * kKChunk, w0 - 1, h0 - 1 + r);
+          }
+          ++a_it;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int sb = b_it % kPairSlots;
+            mbar_wait(&emptyB[sb], ((b_it / kPairSlots) & 1u) ^ 1u);
+            if (leader) mbar_expect_tx(&fullB[sb], 2 * kPairBBytes);
+            tma_load_3d_pair(sB + sb * kPairBBytes, &tmW, &fullB[sb], c * kKChunk, n0, tap);
+            ++b_it;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---------------- MMA issuer of the pair (warp-uniform loop, one elected lane issues) ----------------
+      uint32_t a_it = 0, b_it = 0, t_it = 0;
+      for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs, ++t_it) {
+        mbar_wait(tmem_empty, (t_it & 1u) ^ 1u);
+        tc_fence_after();
+        for (int c = 0; c < chunks; ++c) {
+          const int sa = a_it & 1;
+          mbar_wait(&fullA[sa], (a_it >> 1) & 1u);
+          ++a_it;
+          const uint32_t abase = smem_u32(sA + sa * kHaloBytes);
+          const uint64_t adesc0 = (uint64_t)((abase & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) |
+                                  ((uint64_t)((kHaloW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int sb = b_it % kPairSlots;
+            mbar_wait(&fullB[sb], (b_it / kPairSlots) & 1u);
+            ++b_it;
+            tc_fence_after();
+            const uint64_t bdesc = make_sw128_desc(smem_u32(sB + sb * kPairBBytes));
+            if (elect_one()) {
+#pragma unroll
+              for (int sx = 0; sx < 2; ++sx) {
+                const int row0 = (tap / 3) * kHaloW + 8 * sx + (tap % 3);
+                const uint64_t adesc = adesc0 + (uint64_t)(row0 * 8);
+                const uint32_t d = tmem_base + (uint32_t)sx * (uint32_t)N;
+#pragma unroll
+                for (int k = 0; k < kKChunk / 16; ++k)
+                  tc_mma_f16_pair(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (c | tap | k) != 0 ? 1u : 0u);
+              }
+              tc_commit_pair(&emptyB[sb]);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) tc_commit_pair(&emptyA[sa]);
+          __syncwarp();
+        }
+        if (elect_one()) tc_commit_pair(tmem_full);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs, own TMEM lanes) ----------------
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int y = m >> 3, xx = m & 7;
+    uint32_t t_it = 0;
+    for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs, ++t_it) {
+      const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
+      const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
+      const int h = th * 16 + y, n0 = nb * N;
+      mbar_wait(tmem_full, t_it & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sx = 0; sx < 2; ++sx) {
+        const int w = (tw * 2 + (int)rank) * 16 + 8 * sx + xx;
+        const bool inside = (h < P.H) && (w < P.W);
+        __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
+        const bool pool_writer = P.pool != nullptr && ((lane & 9) == 0) && (h >> 1) < (P.H >> 1) && (w >> 1) < (P.W >> 1);
+        __half* prow = P.pool != nullptr ? P.pool + ((size_t)(h >> 1) * (P.W >> 1) + (w >> 1)) * P.Cout + n0 : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < N; c += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sx * (uint32_t)N + (uint32_t)c, v);
+          uint32_t pw[16];
+          const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 bq = __ldg(b4 + (j >> 1));
+            float a = __uint_as_float(v[2 * j]) + ((j & 1) ? bq.z : bq.x);
+            float b = __uint_as_float(v[2 * j + 1]) + ((j & 1) ? bq.w : bq.y);
+            if (P.relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            const __half2 hv = __floats2half2_rn(a, b);
+            pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+          }
+          if (inside) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
+          }
+          if (P.pool != nullptr) {
+            pool_quad<8>(pw);
+            if (pool_writer) {
+              uint4* dst = reinterpret_cast<uint4*>(prow + c);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tmem_empty);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                // the peer may still read this CTA's shared memory / TMEM until here
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -589,12 +882,24 @@ int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  conv_halo_kernel<N><<<grid, kHaloThreads, smem, stream>>>(a0, a1, w, P);
+  conv_halo_kernel<N><<<grid, kHalo1Threads, smem, stream>>>(a0, a1, w, P);
   PTK_CUDA_CHECK(cudaGetLastError());
   return PTK_OK;
 }
 
-// fp16 tensor map with an explicit box (the halo kernel's A operand)
+int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int n_pairs,
+                 cudaStream_t stream) {
+  constexpr int smem = 2 * kHaloBytes + kPairSlots * kPairBBytes + (4 + 2 * kPairSlots + 2) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  conv_halo2_kernel<<<2 * n_pairs, kHaloThreads, smem, stream>>>(a0, a1, w, P);   // __cluster_dims__(2, 1, 1)
+  PTK_CUDA_CHECK(cudaGetLastError());
+  return PTK_OK;
+}
+
 }  // namespace
 
 // Picks the N tile so that small maps still fill the machine (>= ~1 CTA per SM when possible).
@@ -639,6 +944,46 @@ int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void
     const int tiles_w16 = (W + 15) / 16, tiles_h16 = (H + 15) / 16;
     const int n_halo = Cout >= 128 ? 128 : Cout;
     const int total = tiles_w16 * tiles_h16 * (Cout / n_halo);
+    // CTA pairs (cta_group::2): C_out = k * 256 and enough pairs of 16x16 tiles for most of a wave of SM pairs
+    {
+      // PTK_CONV_PAIR: 0 = never (default), 1 = when the pairs fill a wave, 2 = whenever legal.  Measured on the
+      // 256-channel block (144x256, 43.5 GFLOP): 40.9 us as pairs vs 40.8 us single-CTA -- the layer is bound by MMA
+      // execution + issue, not by the operand bytes a pair saves, and the pair's epilogue is not overlapped -- so the
+      // single-CTA kernel stays the default; the pair kernel is kept (and tested) for the shapes where B traffic binds.
+      static int pair_mode = -1;
+      if (pair_mode < 0) {
+        const char* e = getenv("PTK_CONV_PAIR");
+        pair_mode = e ? atoi(e) : 0;
+      }
+      const int pairs_w = (tiles_w16 + 1) / 2;
+      const int total_pairs = pairs_w * tiles_h16 * (Cout / kPairN);
+      const int pair_slots = ctx->num_sms / 2;
+      const int pwaves = (total_pairs + pair_slots - 1) / pair_slots;
+      const bool pair_legal = taps == 9 && Cout % kPairN == 0 && mode != 0;
+      const bool pair_wanted = pair_mode == 2 || (pair_mode == 1 && total_pairs * 10 >= pwaves * pair_slots * 8);
+      if (pair_legal && pair_wanted) {
+        rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kHaloW, rows_per_op);
+        if (rc != PTK_OK) return rc;
+        if (cin1 > 0) {
+          rc = make_map_3d(&a1, in1, cin1, W, H, cin1, (uint64_t)in1_W * cin1, kKChunk, kHaloW, rows_per_op);
+          if (rc != PTK_OK) return rc;
+        } else {
+          a1 = a0;
+        }
+        rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, kPairN / 2, 1);
+        if (rc != PTK_OK) return rc;
+        HaloParams Q;
+        Q.H = H; Q.W = W; Q.Cout = Cout; Q.chunks0 = cin0 / kKChunk; Q.chunks1 = cin1 / kKChunk; Q.relu = relu;
+        Q.tiles_w = pairs_w; Q.tiles_hw = pairs_w * tiles_h16; Q.total_tiles = total_pairs;
+        Q.resident = 0;
+        Q.dbg = nullptr;
+        Q.rows_per_op = rows_per_op;
+        Q.bias = bias;
+        Q.out = (__half*)out;
+        Q.pool = (__half*)pool_out;
+        return launch_halo2(a0, a1, wm, Q, total_pairs < pair_slots ? total_pairs : pair_slots, s);
+      }
+    }
     const bool legal = taps == 9 && (Cout == 32 || Cout == 64 || Cout % 128 == 0);
     // the 16x16 tiles are coarse: use them only when their last wave is reasonably full, otherwise the
     // finer-grained kernel fills the machine better
@@ -663,7 +1008,28 @@ int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void
       Q.bias = bias;
       Q.out = (__half*)out;
       Q.pool = (__half*)pool_out;
+      Q.dbg = nullptr;
       const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+      static int dbg_mode = -1;
+      if (dbg_mode < 0) dbg_mode = getenv("PTK_CONV_DBG") ? atoi(getenv("PTK_CONV_DBG")) : 0;
+      if (dbg_mode) {   // stall attribution (debug only: synchronises and prints)
+        static long long* dbuf = nullptr;
+        if (!dbuf) cudaMalloc(&dbuf, 16 * sizeof(long long));
+        cudaMemsetAsync(dbuf, 0, 16 * sizeof(long long), s);
+        Q.dbg = dbuf;
+        int lrc;
+        switch (n_halo) {
+          case 32: lrc = launch_halo<32>(a0, a1, wm, Q, grid, s); break;
+          case 64: lrc = launch_halo<64>(a0, a1, wm, Q, grid, s); break;
+          default: lrc = launch_halo<128>(a0, a1, wm, Q, grid, s); break;
+        }
+        long long h[16];
+        cudaMemcpy(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[halo N=%d %dx%d cin=%d cout=%d res=%d tiles/cta=%lld] producer: total %lld waitEmptyA %lld waitEmptyB %lld | "
+                "mma: total %lld waitTmemEmpty %lld waitFullA %lld waitFullB %lld | epilogue: total %lld waitTmemFull %lld\n",
+                n_halo, H, W, cin0 + cin1, Cout, Q.resident, h[7], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[8], h[9]);
+        return lrc;
+      }
       switch (n_halo) {
         case 32: return launch_halo<32>(a0, a1, wm, Q, grid, s);
         case 64: return launch_halo<64>(a0, a1, wm, Q, grid, s);

@@ -141,3 +141,29 @@ def test_full_size_plan_runs_and_is_deterministic():
     for x, y in zip(a + ca, b + cb):
         assert torch.equal(x, y) and bool(torch.isfinite(x).all())
     assert abs(float(a[1].pow(2).sum(-1).mean()) - 1.0) < 1e-4
+
+
+def test_cta_pair_kernel_matches_fp32_conv_in_a_subprocess():
+    """conv_halo2_kernel (tcgen05 cta_group::2, off by default) is selected with PTK_CONV_PAIR=2; the switch is read
+    once per process, so the check runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = '''
+import sys, torch, torch.nn.functional as tF
+sys.path.insert(0, %r)
+from pixtrack_b200.extractor import conv_f16, pack_conv3x3
+g = torch.Generator().manual_seed(5)
+for cin, cout, H, W in [(128, 256, 40, 70), (64, 512, 33, 17)]:
+    x = torch.randn(H, W, cin, generator=g).half().cuda()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).half().cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    y = conv_f16(x, pack_conv3x3(w), b, relu=True)
+    ref = tF.relu(tF.conv2d(x.float().permute(2, 0, 1)[None], w.float(), b, padding=1))[0].permute(1, 2, 0)
+    err = (y.float() - ref).abs().max().item()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item()), err
+print("pair ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PTK_CONV_PAIR='2')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'pair ok' in r.stdout, r.stdout + r.stderr
