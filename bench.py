@@ -180,6 +180,23 @@ def lm_stress(dev, lam, peak):
                     'this is L2-served traffic measured against the HBM copy peak'}
 
 
+def conv_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the plan's tensor-core conv launches, summed, from the committed
+    `ncu --set full` capture of profiles/extractor_profile.py (cold caches, so an upper bound; None when absent)."""
+    path = os.path.join(ROOT, 'profiles', 'r1_conv_final_ncu.json')
+    try:
+        rows = json.load(open(path))['launches']
+    except (OSError, KeyError, ValueError):
+        return None
+    mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tot = 0.0
+    for r in rows:
+        for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            v, u = r[k].split()
+            tot += float(v) * mult[u]
+    return {'bytes': tot, 'launches': len(rows), 'source': 'profiles/r1_conv_final_ncu.json'}
+
+
 def nerf_leg(dev, frame_step, steps):
     """Reference-view re-render (1008x756, spp 8: r9.py:81,150 + run_vis_on_poses.py:29) of a random-weight
     instant-ngp model with a ball-shaped occupancy, alone and in front of the tracked frame."""
@@ -306,9 +323,9 @@ def run_ours(args, rank, world, local_rank):
             d[1] += f
             d[2] += 1
         plan_prof = {k: {'launches': v[2], 'ms': v[0], 'gflop': v[1] / 1e9} for k, v in by_kind.items()}
-        roofline = {'bound': 'tensor', 'kernel': f'conv_tc_kernel (tcgen05 implicit-GEMM conv; {n_tc} launches of the '
-                    '1024x576 plan, 549 of its 561 GFLOP)', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                    'frac': ach / peak_tf, 'traffic': None,
+        roofline = {'bound': 'tensor', 'kernel': f'conv_halo_kernel / conv_tc_kernel (tcgen05 implicit-GEMM convs; the {n_tc} '
+                    'launches of the 1024x576 plan = 557 of its 561 GFLOP)', 'achieved': ach, 'peak': peak_tf,
+                    'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': conv_dram_traffic(),
                     'peak_source': ('MEASURED_PEAKS.json bf16_tflops (burst; kernels timed one by one with CUDA events)'
                                     if peaks else 'fallback 1590 TFLOP/s'),
                     'avg_launch_us': 1e3 * tc_ms / n_tc, 'share_of_plan_time': tc_ms / sum(r[1] for r in rows)}
@@ -380,16 +397,18 @@ def run_ours(args, rank, world, local_rank):
         line = {
             'metric': 'tracked frames/sec (LM-to-convergence)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16 tensor-core convs (f32 '
-            'accumulate) + f32 LM', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16+f32',
+            'data': 'synthetic',
             'config': {'workload': WORKLOAD,
+                       'arithmetic': 'extractor: fp16 tensor-core operands, fp32 accumulation; sampler projection f64; LM f32',
                        'l2': f'inputs larger than L2: ring of {RING} distinct frames; one frame streams >600 MB of '
                              'activations and maps through the 126 MB L2',
                        'cuda_graph': trk.plan.graph is not None, 'lm_iters_coarse_to_fine': iters, 'no_failures': ok,
                        'median_pose_error_deg_m_vs_gt': errs},
             'e2e': {'value': args.steps * world / float(e2e_s), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h},
-            'gpu_launches': (2 * len(rows) + 1 + 3) * args.steps,   # per frame: 2 extractor plans, 1 sampler, 3 LM launches (one graph) 'clocks': clk, 'roofline': roofline,
+            # launches per frame: 2 extractor plans, 1 sampler, 3 LM launches (one graph)
+            'gpu_launches': (2 * len(rows) + 1 + 3) * args.steps, 'clocks': clk, 'roofline': roofline,
             'roofline_lm': stress, 'extractor_plan': plan_prof, 'nerf_render': nerf, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
