@@ -422,7 +422,17 @@ def main():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c4'],
+                    help='c2 (default, the configuration the metric is quoted on) or c4: BASELINE.json configs[3] '
+                         '(16 views, 20000 points, 30 fixed LM iterations per level, frames sharded over the GPUs)')
     args = ap.parse_args()
+    if args.workload == 'c4':
+        global N_POINTS, N_VIEWS, STOP, WORKLOAD
+        N_POINTS, N_VIEWS = 20000, 16
+        STOP = dict(num_iters=30, grad_stop=0.0, dt_stop=0.0, dR_stop=0.0)
+        WORKLOAD = ('C4 frame: synthetic 1920x1080 query + 1008x756 reference view; per frame 2 UNet(VGG19) extractions, '
+                    'reference sparse sampling at N=20000 points into 1 of B=16 view slots, 3-level LM with 30 fixed '
+                    'iterations per level against the 16 views; independent frames sharded over the GPUs')
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

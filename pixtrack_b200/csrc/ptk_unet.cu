@@ -185,34 +185,58 @@ __global__ void maxpool2_kernel(const __half* __restrict__ in, int H, int W, int
 }
 
 // x2 bilinear upsample, align_corners=False (nn.Upsample in DecoderBlock, unet.py:19-20), NHWC fp16.
+// For scale 2 the source position of output 2i is i - 0.25 and of 2i+1 is i + 0.25 (clamped at the borders), so
+// every output is a 0.75 / 0.25 blend of input i with its left/upper or right/lower neighbour.  A thread produces the
+// 2x2 output block of input pixel (y, x) for 8 channels from the 3x3 input neighbourhood (9 loads for 4 outputs,
+// separable blend) instead of 4 loads and a general bilinear evaluation per output.
 __global__ void upsample2_kernel(const __half* __restrict__ in, int H, int W, int C, __half* __restrict__ out) {
-  const int Ho = 2 * H, Wo = 2 * W, C8 = C >> 3;   // C8 is a power of two (C = 64 .. 512)
+  const int C8 = C >> 3;                           // power of two (C = 64 .. 512)
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (unsigned)(Ho * Wo * C8)) return;
+  if (idx >= (unsigned)(H * W * C8)) return;
   const int sh = 31 - __clz(C8);
   const unsigned c8 = idx & (unsigned)(C8 - 1), p = idx >> sh;
-  const int y = (int)(p / (unsigned)Wo), x = (int)(p - (unsigned)y * (unsigned)Wo);
-  const float sxf = fmaxf(((float)x + 0.5f) * 0.5f - 0.5f, 0.f), syf = fmaxf(((float)y + 0.5f) * 0.5f - 0.5f, 0.f);
-  const int x0 = (int)sxf, y0 = (int)syf;
-  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-  const float lx = sxf - (float)x0, ly = syf - (float)y0;
+  const int y = (int)(p / (unsigned)W), x = (int)(p - (unsigned)y * (unsigned)W);
+  const int xm = max(x - 1, 0), xp = min(x + 1, W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
   const uint4* src = reinterpret_cast<const uint4*>(in);
-  const uint4 v00 = src[((size_t)y0 * W + x0) * C8 + c8], v01 = src[((size_t)y0 * W + x1) * C8 + c8];
-  const uint4 v10 = src[((size_t)y1 * W + x0) * C8 + c8], v11 = src[((size_t)y1 * W + x1) * C8 + c8];
-  const __half2* a = reinterpret_cast<const __half2*>(&v00);
-  const __half2* b = reinterpret_cast<const __half2*>(&v01);
-  const __half2* c = reinterpret_cast<const __half2*>(&v10);
-  const __half2* d = reinterpret_cast<const __half2*>(&v11);
-  uint4 o;
-  __half2* ho = reinterpret_cast<__half2*>(&o);
-  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const int rows[3] = {ym, y, yp}, cols[3] = {xm, x, xp};
+  float2 v[3][3][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 fa = __half22float2(a[i]), fb = __half22float2(b[i]), fc = __half22float2(c[i]), fd = __half22float2(d[i]);
-    ho[i] = __floats2half2_rn(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
-                              w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint4 raw = __ldg(src + ((size_t)rows[r] * W + cols[c]) * C8 + c8);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[r][c][e] = __half22float2(h[e]);
+    }
+  // horizontal blend: left output = 0.25 * west + 0.75 * centre, right output = 0.75 * centre + 0.25 * east
+  float2 hl[3][4], hr[3][4];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hl[r][e] = make_float2(0.25f * v[r][0][e].x + 0.75f * v[r][1][e].x, 0.25f * v[r][0][e].y + 0.75f * v[r][1][e].y);
+      hr[r][e] = make_float2(0.75f * v[r][1][e].x + 0.25f * v[r][2][e].x, 0.75f * v[r][1][e].y + 0.25f * v[r][2][e].y);
+    }
+  uint4 o[2][2];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __half2* o00 = reinterpret_cast<__half2*>(&o[0][0]);
+    __half2* o01 = reinterpret_cast<__half2*>(&o[0][1]);
+    __half2* o10 = reinterpret_cast<__half2*>(&o[1][0]);
+    __half2* o11 = reinterpret_cast<__half2*>(&o[1][1]);
+    o00[e] = __floats2half2_rn(0.25f * hl[0][e].x + 0.75f * hl[1][e].x, 0.25f * hl[0][e].y + 0.75f * hl[1][e].y);
+    o01[e] = __floats2half2_rn(0.25f * hr[0][e].x + 0.75f * hr[1][e].x, 0.25f * hr[0][e].y + 0.75f * hr[1][e].y);
+    o10[e] = __floats2half2_rn(0.75f * hl[1][e].x + 0.25f * hl[2][e].x, 0.75f * hl[1][e].y + 0.25f * hl[2][e].y);
+    o11[e] = __floats2half2_rn(0.75f * hr[1][e].x + 0.25f * hr[2][e].x, 0.75f * hr[1][e].y + 0.25f * hr[2][e].y);
   }
-  reinterpret_cast<uint4*>(out)[idx] = o;
+  uint4* dst = reinterpret_cast<uint4*>(out);
+  const int Wo = 2 * W;
+  const size_t base = ((size_t)(2 * y) * Wo + 2 * x) * C8 + c8;
+  dst[base] = o[0][0];
+  dst[base + C8] = o[0][1];
+  dst[base + (size_t)Wo * C8] = o[1][0];
+  dst[base + (size_t)Wo * C8 + C8] = o[1][1];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -530,7 +554,7 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
   for (int i = 0; i < 4; ++i) {
     const int sb = 3 - i;   // skip feature comes from encoder block 3, 2, 1, 0
     const int cskip = kEncBlocks[sb][kEncCount[sb] - 1];
-    const long long n = (long long)e->dh[i] * e->dw[i] * (cprev / 8);
+    const long long n = (long long)ph * pw * (cprev / 8);      // one thread per input pixel and 8 channels
     upsample2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(prev, ph, pw, cprev, e->up[i]);
     mark();
     const int rc = ptk_conv_f16(e->ctx, e->up[i], cprev, e->enc[sb][kEncCount[sb] - 1], cskip, e->dh[i], e->dw[i],
