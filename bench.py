@@ -142,7 +142,7 @@ def run_reference(args, rank, world):
         'config': {'workload': WORKLOAD},
         'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                          'sample': f'{done} full frames (of {args.steps} requested; 240 s budget) through oracle/: 2 UNet '
-                                   'extractions + reference sampling + 8 view refinements each'},
+                                   f'extractions + reference sampling + {N_VIEWS} view refinements each'},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -392,7 +392,7 @@ def run_ours(args, rank, world, local_rank):
             dt = time.perf_counter() - t0
             cpu = {'value': n_f / dt, 'unit': 'frames/s', 'cores': th, 'kind': 'port',
                    'sample': f'{n_f} full frame(s) of the same sequence through oracle/ (2 UNet extractions + reference '
-                             f'sampling + 8 view refinements each) in {dt:.1f} s'}
+                             f'sampling + {N_VIEWS} view refinements each) in {dt:.1f} s'}
         fps = args.steps * world / (ms_total * 1e-3)
         line = {
             'metric': 'tracked frames/sec (LM-to-convergence)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
