@@ -102,3 +102,37 @@ def test_mask_hook_equals_masking_the_frame_first():
     T2, f2 = trk2.track(masked, fr['T_init'].to(dev))
     torch.cuda.synchronize()
     assert torch.equal(T1, T2) and torch.equal(f1, f2)
+
+
+def test_whole_r9_frame_stays_on_the_device():
+    """One tracked frame the way pixloc_tracker_r9.py:216-266 runs it, composed from the adapters without leaving the
+    device: NeRF reference render -> reference features -> depth render -> mask -> query extraction -> LM.  The
+    random-weight NeRF does not depict the plane scene, so this checks composition (shapes, dtypes, stream order,
+    determinism, no failure flags from the device), not pose accuracy."""
+    from types import SimpleNamespace
+    from pixtrack_b200.nerf import NerfTestbed, get_nerf_image, occupancy_bitfield
+    dev, seq, _, _, fr, trk = _setup()
+    sc = syn.nerf_scene(3, 1)
+    tb = NerfTestbed(sc['grid'], sc['w_density'], sc['w_rgb'], occupancy_bitfield(sc['density_grid'], sc['max_cascade']), 1, dev)
+    tb.nerf.rendering_min_transmittance = 1e-7
+    pose = np.eye(4)
+    pose[:3, 3] = [0.0, 0.0, 3.2]
+    cam_r = SimpleNamespace(size=np.array([448, 336], np.float32), f=np.array([500.0, 500.0], np.float32))
+    cam_q = SimpleNamespace(size=np.array([640, 360], np.float32), f=np.array([700.0, 700.0], np.float32))
+    T_ref = torch.cat([fr['R_r'].reshape(-1), fr['t_r']])
+
+    def frame():
+        ref_img = get_nerf_image(tb, pose, cam_r, device_output=True)                    # r9.py:145-152
+        assert ref_img.is_cuda and ref_img.dtype == torch.uint8 and tuple(ref_img.shape) == (336, 448, 3)
+        for v in range(N_VIEWS):
+            trk.refresh_reference(v, ref_img, seq['cam_r'], T_ref)                       # r9.py:154-160
+        depth = get_nerf_image(tb, pose, cam_q, depth=True, device_output=True)          # r9.py:207-214
+        T, failed = trk.track(fr['img_q'].to(dev), fr['T_init'].to(dev), mask_depth=depth)
+        torch.cuda.synchronize()
+        return ref_img.clone(), depth.clone(), T.clone(), failed.clone()
+    a, b = frame(), frame()
+    assert bool((a[0] != 0).any()) and bool((a[1] != 0).any()) and bool((a[1] == 0).any())
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert torch.isfinite(a[2]).all()
+    from pixtrack_b200 import _lib
+    _lib.device_status(0)
