@@ -91,6 +91,8 @@ struct NerfParams {
   float* out_depth;              // [H][W] or null
   unsigned* counter;             // pixel queue
   float* starts;                 // [spp][H*W] first sample position of every ray, < 0: the ray is dead (nerf_start_kernel)
+  float4* frames;                // [spp][H*W] shaded result of every live ray (nerf_render_kernel -> nerf_resolve_kernel)
+  float* frame_depth;            // [H*W] depth of the last sample-per-pixel ray
 };
 
 struct V3 {
@@ -399,15 +401,14 @@ __device__ __forceinline__ void run_network(const __half* __restrict__ wts, cons
 
 // ---- the render kernel ---------------------------------------------------------------------------
 struct Ray {
-  int pix;          // -1: no pixel
-  int s;            // current sample-per-pixel index
+  int pix;          // -1: no ray
+  int s;            // sample-per-pixel index of this ray
   int steps;
   bool alive;
   V3 d, id;
-  float t, tentry, tu0, tu1;
-  float r, g, b, a; // this sample's compositing state
+  float t, tu0, tu1;
+  float r, g, b, a; // compositing state
   float maxw, dep;
-  float ar, ag, ab, aa, adep;   // running mean over spp
 };
 
 // Ray of a pixel (pixel_to_ray with snap_to_pixel_centers: offset 0.5, screen centre 0.5, no parallax), its entry
@@ -481,59 +482,20 @@ __device__ __forceinline__ float first_sample(const NerfParams& P, const V3& o, 
   return skip_empty(P, o, d, id, tu0, tu1, t, p, dt) ? t : -1.f;
 }
 
-__device__ __forceinline__ void start_spp(const NerfParams& P, const V3& o, Ray& ry) {
-  ry.r = ry.g = ry.b = ry.a = 0.f;
-  ry.maxw = 0.f;
-  ry.dep = 0.f;
-  ry.steps = 1;
-  const float t = __ldg(P.starts + (size_t)ry.s * (size_t)(P.W * P.H) + ry.pix);
-  ry.alive = t >= 0.f;
-  ry.t = t;
-}
-
-__device__ __forceinline__ void finish_spp(const NerfParams& P, Ray& ry) {
+// A ray is finished: compact_kernel_nerf keeps it only above alpha 0.001, shade_kernel_nerf converts the colour to
+// linear; the result goes to the per-ray frame buffer that nerf_resolve_kernel averages in sample order.
+__device__ __forceinline__ void finish_ray(const NerfParams& P, const Ray& ry) {
   float fr = 0.f, fg = 0.f, fb = 0.f, fa = 0.f, fd = 0.f;
-  if (ry.a > 0.001f) {   // compact_kernel_nerf keeps a finished ray only above this alpha
+  if (ry.a > 0.001f) {
     fr = ry.r; fg = ry.g; fb = ry.b; fa = ry.a;
-    if (!P.depth_mode) {   // shade_kernel_nerf: accumulate in linear colours
+    if (!P.depth_mode) {
       fr = srgb_to_linear(fr); fg = srgb_to_linear(fg); fb = srgb_to_linear(fb);
     }
     if (ry.a > 0.2f) fd = ry.dep;
   }
-  const float n = (float)ry.s;
-  ry.ar = (ry.ar * n + fr) / (n + 1.f);   // accumulate_kernel
-  ry.ag = (ry.ag * n + fg) / (n + 1.f);
-  ry.ab = (ry.ab * n + fb) / (n + 1.f);
-  ry.aa = (ry.aa * n + fa) / (n + 1.f);
-  ry.adep = fd;
-}
-
-__device__ __forceinline__ void write_pixel(const NerfParams& P, const Ray& ry) {
-  const float w = (1.f - ry.aa) * P.bg[3];   // tonemap_kernel, linear in / linear out, identity curve
-  const float r = ry.ar + P.bg[0] * w, g = ry.ag + P.bg[1] * w, b = ry.ab + P.bg[2] * w, a = ry.aa + w;
-  if (P.out_rgba) P.out_rgba[ry.pix] = make_float4(r, g, b, a);
-  if (P.out_u8) {   // run_vis_on_poses.py:52-54: (rgb * 255).astype(uint8)
-    uint8_t* o = P.out_u8 + (size_t)ry.pix * 3;
-    o[0] = (uint8_t)((int)(r * 255.f) & 0xFF);
-    o[1] = (uint8_t)((int)(g * 255.f) & 0xFF);
-    o[2] = (uint8_t)((int)(b * 255.f) & 0xFF);
-  }
-  if (P.out_depth) P.out_depth[ry.pix] = ry.adep;
-}
-
-// Runs dead samples to completion: finish the sample, start the next one, until a live ray or the
-// end of the pixel (which is then written and released).
-__device__ __forceinline__ void drain(const NerfParams& P, const V3& o, Ray& ry) {
-  while (ry.pix >= 0 && !ry.alive) {
-    finish_spp(P, ry);
-    ++ry.s;
-    if (ry.s < P.spp) {
-      start_spp(P, o, ry);
-    } else {
-      write_pixel(P, ry);
-      ry.pix = -1;
-    }
-  }
+  const size_t npix = (size_t)P.W * P.H;
+  P.frames[(size_t)ry.s * npix + ry.pix] = make_float4(fr, fg, fb, fa);
+  if (ry.s == P.spp - 1) P.frame_depth[ry.pix] = fd;
 }
 
 // Phase 1: the first sample position of every (pixel, sample) ray.  One thread per pixel, so the warps walk
@@ -551,6 +513,36 @@ __global__ void __launch_bounds__(256) nerf_start_kernel(const __grid_constant__
   const bool any = tu0 <= tu1;
   for (int s = 0; s < P.spp; ++s)
     P.starts[(size_t)s * npix + pix] = any ? first_sample(P, o, d, id, tentry, tu0, tu1, pix, s) : -1.f;
+}
+
+// Phase 3: accumulate_kernel (running mean over the samples, in sample order) + tonemap_kernel (background weighted
+// by 1 - alpha, linear in / linear out, identity curve) + the uint8 conversion of get_nerf_image, one thread per pixel.
+__global__ void __launch_bounds__(256) nerf_resolve_kernel(const __grid_constant__ NerfParams P) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npix = P.W * P.H;
+  if (pix >= npix) return;
+  float ar = 0.f, ag = 0.f, ab = 0.f, aa = 0.f;
+  bool last_alive = false;
+  for (int s = 0; s < P.spp; ++s) {
+    const bool live = P.starts[(size_t)s * npix + pix] >= 0.f;
+    const float4 f = live ? P.frames[(size_t)s * npix + pix] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float n = (float)s;
+    ar = (ar * n + f.x) / (n + 1.f);
+    ag = (ag * n + f.y) / (n + 1.f);
+    ab = (ab * n + f.z) / (n + 1.f);
+    aa = (aa * n + f.w) / (n + 1.f);
+    last_alive = live;
+  }
+  const float w = (1.f - aa) * P.bg[3];
+  const float r = ar + P.bg[0] * w, g = ag + P.bg[1] * w, b = ab + P.bg[2] * w, a = aa + w;
+  if (P.out_rgba) P.out_rgba[pix] = make_float4(r, g, b, a);
+  if (P.out_u8) {   // run_vis_on_poses.py:52-54: (rgb * 255).astype(uint8)
+    uint8_t* o = P.out_u8 + (size_t)pix * 3;
+    o[0] = (uint8_t)((int)(r * 255.f) & 0xFF);
+    o[1] = (uint8_t)((int)(g * 255.f) & 0xFF);
+    o[2] = (uint8_t)((int)(b * 255.f) & 0xFF);
+  }
+  if (P.out_depth) P.out_depth[pix] = last_alive ? P.frame_depth[pix] : 0.f;
 }
 
 __global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_constant__ NerfParams P) {
@@ -574,6 +566,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_c
 
   const unsigned full = 0xffffffffu;
   const int npix = P.W * P.H;
+  const unsigned nrays = (unsigned)npix * (unsigned)P.spp;
   const V3 o = {P.cam[3], P.cam[7], P.cam[11]};
   const V3 fwd = {P.cam[2], P.cam[6], P.cam[10]};
   Ray ry;
@@ -582,8 +575,10 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_c
   bool exhausted = false;
 
   while (true) {
-    // ---- take new pixels until every lane has a live ray or the queue is empty (pixels whose rays
-    //      all miss are finished right here) -------------------------------------------------------
+    // ---- take new rays until every lane has a live one or the queue is empty.  The work unit is a (pixel, sample)
+    //      ray, pixel-major (the spp rays of a pixel follow the same path and run side by side in a warp); rays
+    //      that nerf_start_kernel found dead cost one load here.  Ray-sized units balance the lanes much better
+    //      than whole pixels (an object covers ~1e5 pixels, the grid has ~7.5e4 lanes). -----------------------
 #pragma unroll 1
     while (true) {
       const bool need = ry.pix < 0 && !exhausted;
@@ -594,20 +589,20 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_c
       base = __shfl_sync(full, base, __ffs(m) - 1);
       if (need) {
         const unsigned mine = base + __popc(m & ((1u << lane) - 1u));
-        if (mine < (unsigned)npix) {
-          ry.pix = (int)mine;
-          ry.s = 0;
-          ry.ar = ry.ag = ry.ab = ry.aa = ry.adep = 0.f;
-          setup_ray(P, o, ry.pix, ry.d, ry.id, ry.tentry, ry.tu0, ry.tu1);
-          if (!(ry.tu0 <= ry.tu1)) {   // nothing occupied along this ray: every sample-per-pixel is empty
-            ry.s = P.spp - 1;
-            ry.alive = false;
+        if (mine < nrays) {
+          const int pix = (int)(mine / (unsigned)P.spp), sidx = (int)(mine - (unsigned)pix * (unsigned)P.spp);
+          const float t = __ldg(P.starts + (size_t)sidx * (size_t)npix + pix);
+          if (t >= 0.f) {
+            float tentry;
+            setup_ray(P, o, pix, ry.d, ry.id, tentry, ry.tu0, ry.tu1);
+            ry.pix = pix;
+            ry.s = sidx;
+            ry.t = t;
+            ry.alive = true;
+            ry.steps = 1;
             ry.r = ry.g = ry.b = ry.a = 0.f;
             ry.maxw = ry.dep = 0.f;
-          } else {
-            start_spp(P, o, ry);
           }
-          drain(P, o, ry);
         } else {
           exhausted = true;
         }
@@ -675,7 +670,10 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_c
       }
       __syncwarp();
     }
-    drain(P, o, ry);
+    if (ry.pix >= 0 && !ry.alive) {
+      finish_ray(P, ry);
+      ry.pix = -1;
+    }
   }
 }
 
@@ -685,7 +683,7 @@ struct PtkNerf {
   PtkContext* ctx;
   NerfParams base;
   unsigned* counter;
-  float* starts;        // [spp][pixels] workspace of the last render size
+  float* starts;        // workspace of the largest render so far: per-ray frames, first-sample positions, depth
   size_t starts_cap;    // floats
   int aabb_scale;
 };
@@ -840,15 +838,19 @@ extern "C" int ptk_nerf_render(PtkNerf* n, const PtkNerfView* v, float* out_rgba
   P.out_depth = out_depth;
   P.counter = n->counter;
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t need = (size_t)v->width * v->height * v->spp;
-  if (need > n->starts_cap) {   // grows only when a larger view is rendered (synchronising free)
+  const size_t npix = (size_t)v->width * v->height;
+  const size_t need = npix * v->spp;
+  const size_t floats = 4 * need + need + npix + 16;       // frames (float4), starts, last-sample depth
+  if (floats > n->starts_cap) {   // grows only when a larger view is rendered (synchronising free)
     if (n->starts) PTK_CUDA_CHECK(cudaFree(n->starts));
     n->starts = nullptr;
     n->starts_cap = 0;
-    PTK_CUDA_CHECK(cudaMalloc(&n->starts, need * sizeof(float)));
-    n->starts_cap = need;
+    PTK_CUDA_CHECK(cudaMalloc(&n->starts, floats * sizeof(float)));
+    n->starts_cap = floats;
   }
-  P.starts = n->starts;
+  P.frames = reinterpret_cast<float4*>(n->starts);           // 16-byte aligned start of the workspace
+  P.starts = n->starts + 4 * need;
+  P.frame_depth = P.starts + need;
   PTK_CUDA_CHECK(cudaMemsetAsync(n->counter, 0, sizeof(unsigned), s));
   nerf_start_kernel<<<(unsigned)(((size_t)v->width * v->height + 255) / 256), 256, 0, s>>>(P);
   int per_sm = 1;
@@ -859,6 +861,7 @@ extern "C" int ptk_nerf_render(PtkNerf* n, const PtkNerfView* v, float* out_rgba
   const long long cap = (long long)n->ctx->num_sms * per_sm;
   if (ctas > cap) ctas = cap;
   nerf_render_kernel<<<(unsigned)ctas, kThreads, kSmemBytes, s>>>(P);
+  nerf_resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(P);
   PTK_CUDA_CHECK(cudaGetLastError());
   return PTK_OK;
 }
