@@ -231,7 +231,7 @@ int ptk_extractor_level_shape(const PtkExtractor* e, int32_t level, int32_t* C, 
 int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
                       float* const* feat, float* const* conf, int32_t normalize, void* stream);
 /* Benchmark helper (SYNCHRONISES): runs the plan once with a CUDA event after every launch.  ms[i] = device
- * time of launch i; kinds[i]: 0 prep, 1 first conv (direct), 2 max-pool, 3 tensor-core conv, 4 upsample,
+ * time of launch i; kinds[i]: 0 prep, 1 first conv (mma.sync), 3 tensor-core conv (2x2 max pools fused), 4 upsample,
  * 5 head; flops[i] = 2 x multiply-adds of launch i. */
 int ptk_extractor_profile(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
                           float* const* feat, float* const* conf, int32_t normalize, void* stream, int32_t max_n,

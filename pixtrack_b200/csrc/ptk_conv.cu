@@ -4,7 +4,15 @@
 // Replaces the cuDNN convolutions under UNet._forward (reference
 // pixloc/pixloc/pixlib/models/unet.py:68-99 encoder blocks, :15-44 decoder blocks).
 //
-// GEMM view:  D[128 pixels, BLOCK_N channels] += A[128, 64] * B[BLOCK_N, 64]^T over
+// Three kernels, chosen per layer by ptk_conv_f16_pool (bottom of the file):
+//   conv_halo_kernel   persistent, one halo load per 64-channel chunk, taps = shifted descriptors (default for the
+//                      large maps; see its header comment)
+//   conv_halo2_kernel  the same on CTA pairs (tcgen05 cta_group::2); off by default (PTK_CONV_PAIR)
+//   conv_tc_kernel     one tap-shifted TMA box per k-step; small maps and 1x1 (described next)
+// All epilogues add the bias (conv bias or folded BatchNorm), apply ReLU, write fp16 and can also write the
+// 2x2 max pool of the result.
+//
+// conv_tc_kernel, GEMM view:  D[128 pixels, BLOCK_N channels] += A[128, 64] * B[BLOCK_N, 64]^T over
 //             K = taps x (C_in / 64) steps.
 //  * A: one TMA 3-D box {64 ch, 16 px wide, 8 px high} of the NHWC input at the tap-shifted
 //    position lands in shared memory as 128 rows x 128 B, 128B-swizzled -- exactly the K-major
@@ -15,8 +23,8 @@
 //    (unet.py:44) is never materialised.
 //  * B: weights pre-packed as [tap][C_out][C_in] fp16, box {64, BLOCK_N, 1}.
 //  * Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer
-//    (one lane), warps 2-5 = epilogue: tcgen05.ld 32 lanes x 32 columns, + bias (conv bias or
-//    folded BatchNorm), ReLU, fp16, 64 B per pixel per store.
+//    (warp-uniform loop, one elected lane issues), warps 2-5 = epilogue: tcgen05.ld 32 lanes x 32
+//    columns, + bias, ReLU, fp16, 64 B per pixel per store.
 //  * STAGES-deep mbarrier ring between TMA and MMA; tcgen05.commit releases a stage when the
 //    MMAs that read it retire.  Several CTAs are resident per SM (smem permitting) so one CTA's
 //    epilogue overlaps another's main loop.

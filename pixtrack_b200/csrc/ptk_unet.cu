@@ -1,5 +1,5 @@
-// The PixLoc UNet feature extractor as a native plan: small CUDA-core kernels around the
-// tcgen05 convolution (ptk_conv.cu), and the layer schedule.
+// The PixLoc UNet feature extractor as a native plan: the small kernels around the tcgen05
+// convolutions of ptk_conv.cu (image prep, first layer and heads on mma.sync, upsample) and the layer schedule.
 //
 // Replaces UNet._forward (reference pixloc/pixloc/pixlib/models/unet.py:158-190) with the PixLoc
 // configuration (pixlib/configs/train_pixloc_megadepth.yaml:22-31: vgg19 encoder, decoder
@@ -164,25 +164,7 @@ __global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict_
   }
 }
 
-// 2x2 / stride 2 max pool (floor mode), NHWC fp16, 8 channels per thread.
-__global__ void maxpool2_kernel(const __half* __restrict__ in, int H, int W, int C, __half* __restrict__ out) {
-  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;   // C8 is a power of two (C = 64 .. 512)
-  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (unsigned)(Ho * Wo * C8)) return;
-  const int sh = 31 - __clz(C8);
-  const unsigned c8 = idx & (unsigned)(C8 - 1), p = idx >> sh;
-  const int y = (int)(p / (unsigned)Wo), x = (int)(p - (unsigned)y * (unsigned)Wo);
-  const uint4* src = reinterpret_cast<const uint4*>(in);
-  const size_t base = ((size_t)(2 * y) * W + 2 * x) * C8 + c8;
-  uint4 a = src[base], b = src[base + C8], c = src[base + (size_t)W * C8], d = src[base + (size_t)W * C8 + C8];
-  __half2* ha = reinterpret_cast<__half2*>(&a);
-  const __half2* hb = reinterpret_cast<const __half2*>(&b);
-  const __half2* hc = reinterpret_cast<const __half2*>(&c);
-  const __half2* hd = reinterpret_cast<const __half2*>(&d);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) ha[i] = __hmax2(__hmax2(ha[i], hb[i]), __hmax2(hc[i], hd[i]));
-  reinterpret_cast<uint4*>(out)[idx] = a;
-}
+// (the 2x2 max pools of the encoder are written by the epilogue of the convolution in front of them, ptk_conv.cu)
 
 // x2 bilinear upsample, align_corners=False (nn.Upsample in DecoderBlock, unet.py:19-20), NHWC fp16.
 // For scale 2 the source position of output 2i is i - 0.25 and of 2i+1 is i + 0.25 (clamped at the borders), so
@@ -594,9 +576,9 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
 }
 
 // Runs the plan once with a CUDA event after every launch and returns the per-launch durations
-// (SYNCHRONISES; for benchmarks).  Launch order: prep, conv1, then per encoder block
-// [pool] conv..., per decoder block upsample conv, 3 heads.  kinds[i]: 0 prep, 1 conv1 (direct),
-// 2 pool, 3 tensor-core conv, 4 upsample, 5 head.  flops[i]: multiply-add count x 2 of launch i.
+// (SYNCHRONISES; for benchmarks; everything on the caller's stream).  Launch order: prep, conv1, the encoder
+// convolutions (pools fused), per decoder block upsample + conv, 3 heads.  kinds[i]: 0 prep, 1 conv1 (mma.sync),
+// 3 tensor-core conv, 4 upsample, 5 head.  flops[i]: multiply-add count x 2 of launch i.
 extern "C" int ptk_extractor_profile(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
                                      float* const* feat, float* const* conf, int32_t normalize, void* stream,
                                      int32_t max_n, float* ms, int32_t* kinds, double* flops, int32_t* n_out) {

@@ -185,7 +185,7 @@ class B200FeatureExtractor(torch.nn.Module):
                                                    ih, iw, fp, cp, 1 if normalize else 0,
                                                    _lib.current_stream_ptr(self.device), 48, ms, kinds, flops,
                                                    C.byref(n)))
-        names = {0: 'prep', 1: 'conv1_direct', 2: 'maxpool', 3: 'conv_tc', 4: 'upsample', 5: 'head'}
+        names = {0: 'prep', 1: 'conv1_mma', 2: 'maxpool', 3: 'conv_tc', 4: 'upsample', 5: 'head'}
         return [(names[kinds[i]], ms[i], flops[i]) for i in range(n.value)]
 
     def activation(self, H: int, W: int, kind: int, index: int) -> Tensor:
