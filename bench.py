@@ -175,9 +175,24 @@ def lm_stress(dev, lam, peak):
     return {'kernel': 'lm_kernel', 'bound': 'hbm',
             'workload': 'C4 level 1: C=128 144x256, N=20000, B=16, 30 fixed iterations', 'ms_per_launch': ms,
             'us_per_iteration': 1e3 * ms / 30, 'achieved': byts / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-            'frac': byts / (ms * 1e-3) / 1e9 / peak, 'ctas_per_problem': g, 'problems_in_flight': ng,
+            'frac': byts / (ms * 1e-3) / 1e9 / peak, 'traffic': lm_dram_traffic(), 'algorithmic_bytes': byts,
+            'ctas_per_problem': g, 'problems_in_flight': ng,
             'note': 'algorithmic bytes (52C+32 per valid point per iteration); the 19 MB map stays L2-resident, so '
                     'this is L2-served traffic measured against the HBM copy peak'}
+
+
+def lm_dram_traffic():
+    """DRAM bytes of one lm_kernel launch of the C4 stress problem from the committed `ncu --set full` capture."""
+    try:
+        r = json.load(open(os.path.join(ROOT, 'profiles', 'r1_lm_v3_ncu.json')))['launches'][0]
+    except (OSError, KeyError, ValueError, IndexError):
+        return None
+    mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tot = 0.0
+    for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+        v, u = r[k].split()
+        tot += float(v) * mult[u]
+    return tot
 
 
 def conv_dram_traffic():
