@@ -257,7 +257,19 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        # keep stdout to the one JSON line: NCCL prints its version banner with printf while the communicator is
+        # created, so file descriptor 1 points at stderr during the (eager) initialisation and a first collective
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lam = lam0().to(dev)
     seq = syn.tracked_sequence(100 + rank, n_frames=RING, N=N_POINTS, n_views=N_VIEWS)
     frames = seq['frames']
