@@ -47,9 +47,10 @@ struct ConvParams {
   int taps;            // 9 (3x3, pad 1) or 1 (1x1)
   int relu;
   int tiles_w;
+  int tw_log2;         // the CTA's 128 output pixels form a (1 << tw_log2) wide, (128 >> tw_log2) high tile
   const float* bias;   // [Cout] fp32
   __half* out;         // [H][W][Cout]
-  __half* pool;        // optional [H/2][W/2][Cout]: 2x2 max pool of `out`, written by the same epilogue
+  __half* pool;        // optional [H/2][W/2][Cout]: 2x2 max pool of `out` (16 x 8 tiles only)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -157,7 +158,43 @@ __device__ __forceinline__ void pool_quad(uint32_t (&pw)[16]) {
   }
 }
 
-template <int BLOCK_N, int STAGES>
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank0(uint32_t smem_addr) {   // the same offset in cluster rank 0's shared memory
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_addr));
+  return remote;
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on rank 0's copy of `bar`
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_rank0(smem_u32(bar))) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquires remote (DSMEM) writes
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  unsigned spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 22)) __trap();
+  }
+}
+
+// SPLIT = 2: the K loop of one output tile is shared by a cluster of two CTAs (blockIdx.z = cluster rank).  Rank 1
+// ships its fp32 partial accumulators into rank 0's shared memory (DSMEM stores, column-major so a warp writes 128
+// contiguous bytes) and arrives on rank 0's `peer_bar`; rank 0 adds them in its epilogue.  Used for layers whose
+// tiles would otherwise occupy at most half of the SMs (long K, few pixels, few output channels).
+template <int BLOCK_N, int STAGES, int SPLIT>
 __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                const __grid_constant__ CUtensorMap tmA1,
                                                                const __grid_constant__ CUtensorMap tmW,
@@ -173,16 +210,20 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+  uint64_t* peer_bar = tmem_full_bar + 1;                       // SPLIT: rank 1's partial sums have landed
+  uint32_t* tmem_slot = (uint32_t*)(peer_bar + 1);
+  float* xbuf = (float*)(smem + STAGES * kStageBytes + 256);    // SPLIT: [BLOCK_N][128] fp32 partial sums of rank 1
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
   const int th = tile / P.tiles_w, tw = tile - th * P.tiles_w;
-  const int h0 = th * kTileH, w0 = tw * kTileW;
+  const int h0 = th * (128 >> P.tw_log2), w0 = tw << P.tw_log2;
   const int n0 = blockIdx.y * BLOCK_N;
   const int chunks0 = P.cin0 / kKChunk, chunks1 = P.cin1 / kKChunk;
   const int steps_per_tap = chunks0 + chunks1;
-  const int num_steps = P.taps * steps_per_tap;
+  const int krank = SPLIT > 1 ? (int)cluster_ctarank() : 0;
+  const int ks_begin = P.taps * steps_per_tap * krank / SPLIT;
+  const int num_steps = P.taps * steps_per_tap * (krank + 1) / SPLIT - ks_begin;   // this CTA's share of the K loop
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
@@ -193,6 +234,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(peer_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation is a warp-wide instruction; this warp also frees it
@@ -202,7 +244,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (SPLIT > 1) cluster_sync_all();   // rank 0's peer_bar must exist before rank 1 can arrive on it
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -213,7 +256,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         const int stage = ks % STAGES;
         const uint32_t phase = (uint32_t)(ks / STAGES) & 1u;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        const int tap = ks / steps_per_tap, cc = ks - tap * steps_per_tap;
+        const int kg = ks_begin + ks;
+        const int tap = kg / steps_per_tap, cc = kg - tap * steps_per_tap;
         const int dy = (P.taps == 9) ? tap / 3 - 1 : 0, dx = (P.taps == 9) ? tap % 3 - 1 : 0;
         uint8_t* sa = smem + stage * kStageBytes;
         mbar_expect_tx(&full_bar[stage], kStageBytes);
@@ -247,10 +291,23 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     // ---------------- epilogue: TMEM -> registers -> bias/ReLU -> fp16 -> global ----------------
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;                  // row of the tile = pixel
-    const int h = h0 + m / kTileW, w = w0 + m % kTileW;
+    const int h = h0 + (m >> P.tw_log2), w = w0 + (m & ((1 << P.tw_log2) - 1));
     const bool inside = (h < P.H) && (w < P.W);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (SPLIT > 1 && krank != 0) {   // hand the partial sums to rank 0 and leave
+      const uint32_t remote = map_to_rank0(smem_u32(xbuf)) + (uint32_t)m * 4u;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(remote + (uint32_t)(c + j) * 512u), "r"(v[j]) : "memory");
+      }
+      mbar_arrive_leader(peer_bar);
+    } else {
+    if (SPLIT > 1) mbar_wait_cluster(peer_bar, 0);
     __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
     const bool pool_writer = P.pool != nullptr && ((lane & 17) == 0) && (h >> 1) < (P.H >> 1) && (w >> 1) < (P.W >> 1);
     __half* prow = P.pool != nullptr ? P.pool + ((size_t)(h >> 1) * (P.W >> 1) + (w >> 1)) * P.Cout + n0 : nullptr;
@@ -258,6 +315,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     for (int c = 0; c < BLOCK_N; c += 32) {
       uint32_t v[32];
       tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (SPLIT > 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + xbuf[(c + j) * 128 + m]);
+      }
       uint32_t pw[16];
       const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);   // 32 consecutive biases, 16-byte loads
 #pragma unroll
@@ -285,6 +346,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
           for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
         }
       }
+    }
     }
   }
 
@@ -595,14 +657,6 @@ constexpr int kPairN = 256;
 constexpr int kPairBBytes = (kPairN / 2) * 128;      // this CTA's half of a weight tile: 16 KB
 constexpr int kPairSlots = 7;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // TMA load whose completion bytes are credited to the mbarrier at the same offset in the pair's leader CTA
 __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
                                                  int c2) {
@@ -626,11 +680,6 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc,
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on rank 0's copy of `bar`
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(bar)));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
@@ -863,19 +912,39 @@ int make_map_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uin
   return PTK_OK;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int SPLIT = 1>
 int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& P,
                 cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + 1024 + 256;
+  // stage ring | barriers + TMEM slot (256 B) | SPLIT: fp32 exchange buffer | alignment slack
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + 256 + (SPLIT > 1 ? BLOCK_N * 128 * 4 : 0) + 1024;
+  static_assert(smem <= 232448, "shared memory budget");
+  static_assert(2 * STAGES + 2 <= 31, "barriers + TMEM slot must fit the 256-byte block");
   static bool configured = false;
   if (!configured) {
-    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int tiles_h = (P.H + kTileH - 1) / kTileH;
-  dim3 grid(P.tiles_w * tiles_h, P.Cout / BLOCK_N);
-  conv_tc_kernel<BLOCK_N, STAGES><<<grid, kConvThreads, smem, stream>>>(a0, a1, w, P);
-  PTK_CUDA_CHECK(cudaGetLastError());
+  const int tile_h = 128 >> P.tw_log2;
+  const int tiles_h = (P.H + tile_h - 1) / tile_h;
+  dim3 grid(P.tiles_w * tiles_h, P.Cout / BLOCK_N, SPLIT);
+  if (SPLIT == 1) {
+    conv_tc_kernel<BLOCK_N, STAGES, SPLIT><<<grid, kConvThreads, smem, stream>>>(a0, a1, w, P);
+    PTK_CUDA_CHECK(cudaGetLastError());
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = SPLIT;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PTK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, STAGES, SPLIT>, a0, a1, w, P));
+  }
   return PTK_OK;
 }
 
@@ -928,17 +997,9 @@ int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void
   PTK_REQUIRE((cin1 == 0) == (in1 == nullptr), "in1 and cin1 must be given together");
   PTK_REQUIRE(H >= 1 && W >= 1 && in0_H >= H && in0_W >= W, "input 0 smaller than the output");
   const int ctot = cin0 + cin1;
+  PTK_REQUIRE(cin1 == 0 || (in1_H >= H && in1_W >= W), "input 1 smaller than the output");
   CUtensorMap a0, a1, wm;
-  // extents = the OUTPUT size: anything beyond (incl. a larger skip tensor's extra rows/cols) reads as zero
-  int rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kTileW, kTileH);
-  if (rc != PTK_OK) return rc;
-  if (cin1 > 0) {
-    PTK_REQUIRE(in1_H >= H && in1_W >= W, "input 1 smaller than the output");
-    rc = make_map_3d(&a1, in1, cin1, W, H, cin1, (uint64_t)in1_W * cin1, kKChunk, kTileW, kTileH);
-    if (rc != PTK_OK) return rc;
-  } else {
-    a1 = a0;
-  }
+  int rc;
   cudaStream_t s = (cudaStream_t)stream;
   // ---- halo kernel (3x3 only): one halo load per chunk, persistent CTAs ----
   {
@@ -1047,18 +1108,61 @@ int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void
   }
   ConvParams P;
   P.H = H; P.W = W; P.Cout = Cout; P.cin0 = cin0; P.cin1 = cin1; P.taps = taps; P.relu = relu;
-  P.tiles_w = (W + kTileW - 1) / kTileW;
+  // tile shape: the 128 pixels of a CTA as 16x8 (default; the only shape the fused pool handles), or 32x4 / 64x2 /
+  // 8x16 when that covers the map with fewer tiles (e.g. 64x36: 18 tiles of 32x4 instead of 20 of 16x8)
+  P.tw_log2 = 4;
+  {
+    static int shapes = -1;   // PTK_CONV_SHAPES=0 pins 16x8 (A/B measurements)
+    if (shapes < 0) shapes = getenv("PTK_CONV_SHAPES") ? atoi(getenv("PTK_CONV_SHAPES")) : 1;
+    int best = ((W + 15) / 16) * ((H + 7) / 8);
+    if (pool_out == nullptr && shapes) {
+      const int cand[3] = {5, 6, 3};
+      for (int lg : cand) {
+        const int n = ((W + (1 << lg) - 1) >> lg) * ((H + (128 >> lg) - 1) / (128 >> lg));
+        if (n < best) {
+          best = n;
+          P.tw_log2 = lg;
+        }
+      }
+    }
+  }
+  const int tile_w = 1 << P.tw_log2, tile_h = 128 >> P.tw_log2;
+  // extents = the OUTPUT size: anything beyond (incl. a larger skip tensor's extra rows/cols) reads as zero
+  rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, tile_w, tile_h);
+  if (rc != PTK_OK) return rc;
+  if (cin1 > 0) {
+    rc = make_map_3d(&a1, in1, cin1, W, H, cin1, (uint64_t)in1_W * cin1, kKChunk, tile_w, tile_h);
+    if (rc != PTK_OK) return rc;
+  } else {
+    a1 = a0;
+  }
+  P.tiles_w = (W + tile_w - 1) / tile_w;
   P.bias = bias;
   P.out = (__half*)out;
   P.pool = (__half*)pool_out;
-  const int m_tiles = P.tiles_w * ((H + kTileH - 1) / kTileH);
+  const int m_tiles = P.tiles_w * ((H + tile_h - 1) / tile_h);
   const int bn = pick_block_n(Cout, m_tiles, ctx->num_sms);
   rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, bn, 1);
   if (rc != PTK_OK) return rc;
+  static int split_mode = -1;   // PTK_CONV_SPLIT=0 disables the two-CTA K split
+  if (split_mode < 0) split_mode = getenv("PTK_CONV_SPLIT") ? atoi(getenv("PTK_CONV_SPLIT")) : 1;
+  const int ctas = m_tiles * (Cout / bn);
+  const int k_steps = taps * (ctot / kKChunk);
   switch (bn) {
     case 32: return launch_conv<32, 4>(a0, a1, wm, P, s);
-    case 64:   // at most one CTA per SM: nothing else hides the load latency, so run a deeper ring
-      if (m_tiles * (Cout / bn) <= ctx->num_sms) return launch_conv<64, 8>(a0, a1, wm, P, s);
+    case 64:
+      // many output channels on a small map: the layer is bound by L2 -> shared-memory bytes, and a 128-channel
+      // tile shared by two CTAs (half of K each) stages 1/3 fewer bytes than two 64-channel tiles
+      if (split_mode && Cout % 128 == 0 && 2 * m_tiles * (Cout / 128) <= ctx->num_sms && k_steps >= 16 && pool_out == nullptr) {
+        rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, 128, 1);
+        if (rc != PTK_OK) return rc;
+        return launch_conv<128, 5, 2>(a0, a1, wm, P, s);
+      }
+      // tiles for at most half of the SMs and a long K loop: two CTAs per tile, each runs half of K
+      if (split_mode && 2 * ctas <= ctx->num_sms && k_steps >= 16 && pool_out == nullptr)
+        return launch_conv<64, 8, 2>(a0, a1, wm, P, s);
+      // at most one CTA per SM: nothing else hides the load latency, so run a deeper ring
+      if (ctas <= ctx->num_sms) return launch_conv<64, 8>(a0, a1, wm, P, s);
       return launch_conv<64, 4>(a0, a1, wm, P, s);
     case 128: return launch_conv<128, 3>(a0, a1, wm, P, s);
     default: return launch_conv<256, 3>(a0, a1, wm, P, s);

@@ -26,7 +26,10 @@ def _conv_ref(x_hwc, w, b, relu, x1=None, hw=None):
 
 
 @pytest.mark.parametrize('cin,cout,H,W', [(64, 64, 24, 40), (128, 256, 17, 33), (64, 32, 8, 16), (256, 512, 9, 20),
-                                          (512, 128, 40, 70), (64, 64, 130, 250)])
+                                          (512, 128, 40, 70), (64, 64, 130, 250),
+                                          # tile shapes 32x4 / 8x16 / 64x2 and the two-CTA K split (ptk_conv.cu dispatch)
+                                          (512, 512, 36, 64), (128, 64, 40, 8), (64, 64, 2, 128), (1024, 64, 36, 64),
+                                          (192, 64, 19, 37)])
 def test_conv3x3_against_fp32_conv_of_same_operands(cin, cout, H, W):
     from pixtrack_b200.extractor import conv_f16, pack_conv3x3
     g = torch.Generator().manual_seed(cin * 7 + cout)
