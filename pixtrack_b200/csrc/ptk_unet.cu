@@ -381,6 +381,17 @@ struct PtkExtractor {
   // plan is still one stream-ordered unit for the caller and can be captured in a CUDA graph)
   cudaStream_t side;
   cudaEvent_t ev_fork[2], ev_join;
+  // CUDA graphs of the whole plan, one per distinct (image, outputs) binding: the second call with a binding
+  // captures the launches on `cap`, later calls replay the graph (one launch instead of ~30 + tensor-map encodes)
+  struct PlanGraph {
+    const void* image;
+    int img_dtype, img_h, img_w, normalize, seen;
+    float* feat[3];
+    float* conf[3];
+    cudaGraphExec_t exec;
+  } graphs[8];
+  int n_graphs;
+  cudaStream_t cap;
 };
 #define PTK_MAX_LAUNCHES 48
 
@@ -432,6 +443,8 @@ extern "C" int ptk_extractor_create(PtkContext* ctx, const PtkUnetWeights* w, in
 extern "C" void ptk_extractor_destroy(PtkExtractor* e) {
   if (e == nullptr) return;
   if (e->side) cudaStreamDestroy(e->side);
+  if (e->cap) cudaStreamDestroy(e->cap);
+  for (int i = 0; i < e->n_graphs; ++i) if (e->graphs[i].exec) cudaGraphExecDestroy(e->graphs[i].exec);
   for (int i = 0; i < 2; ++i) if (e->ev_fork[i]) cudaEventDestroy(e->ev_fork[i]);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->arena) cudaFree(e->arena);
@@ -464,15 +477,13 @@ extern "C" int ptk_extractor_activation(const PtkExtractor* e, int32_t kind, int
   return PTK_ERR_INVALID;
 }
 
-extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
-                                 float* const* feat, float* const* conf, int32_t normalize, void* stream) {
-  PTK_REQUIRE(e && image && feat && conf, "null argument");
+static int run_plan(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
+                    float* const* feat, float* const* conf, int32_t normalize, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int H = e->H, W = e->W;
   e->prof_n = 0;
   auto mark = [&]() { if (e->prof_ev != nullptr && e->prof_n < PTK_MAX_LAUNCHES) cudaEventRecord(e->prof_ev[e->prof_n++], s); };
   mark();
-  PTK_REQUIRE(img_dtype == 0 || img_dtype == 1, "img_dtype must be 0 (fp32) or 1 (uint8)");
   if (img_dtype == 0) prep_image_kernel<float><<<(H * W + 255) / 256, 256, 0, s>>>((const float*)image, img_h, img_w, e->img, H, W);
   else prep_image_kernel<uint8_t><<<(H * W + 255) / 256, 256, 0, s>>>((const uint8_t*)image, img_h, img_w, e->img, H, W);
   mark();
@@ -572,6 +583,65 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
     }
   }
   PTK_CUDA_CHECK(cudaGetLastError());
+  return PTK_OK;
+}
+
+extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
+                                 float* const* feat, float* const* conf, int32_t normalize, void* stream) {
+  PTK_REQUIRE(e && image && feat && conf, "null argument");
+  PTK_REQUIRE(img_dtype == 0 || img_dtype == 1, "img_dtype must be 0 (fp32) or 1 (uint8)");
+  cudaStream_t s = (cudaStream_t)stream;
+  static int graph_mode = -1;   // PTK_PLAN_GRAPH=0: always launch kernel by kernel
+  if (graph_mode < 0) graph_mode = getenv("PTK_PLAN_GRAPH") ? atoi(getenv("PTK_PLAN_GRAPH")) : 1;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (graph_mode == 0 || e->prof_ev != nullptr || cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();   // (a legacy default stream reports an error for the query while another stream captures)
+    return run_plan(e, image, img_dtype, img_h, img_w, feat, conf, normalize, stream);
+  }
+  PtkExtractor::PlanGraph* g = nullptr;
+  for (int i = 0; i < e->n_graphs && g == nullptr; ++i) {
+    PtkExtractor::PlanGraph& c = e->graphs[i];
+    bool same = c.image == image && c.img_dtype == img_dtype && c.img_h == img_h && c.img_w == img_w && c.normalize == normalize;
+    for (int l = 0; l < 3 && same; ++l) same = c.feat[l] == feat[l] && c.conf[l] == conf[l];
+    if (same) g = &c;
+  }
+  if (g != nullptr && g->exec != nullptr) {
+    PTK_CUDA_CHECK(cudaGraphLaunch(g->exec, s));
+    return PTK_OK;
+  }
+  if (g == nullptr) {   // first call with this binding: run directly (also configures every kernel it uses)
+    if (e->n_graphs < 8) {
+      g = &e->graphs[e->n_graphs++];
+      g->image = image; g->img_dtype = img_dtype; g->img_h = img_h; g->img_w = img_w; g->normalize = normalize;
+      for (int l = 0; l < 3; ++l) { g->feat[l] = feat[l]; g->conf[l] = conf[l]; }
+      g->seen = 1;
+      g->exec = nullptr;
+    }
+    return run_plan(e, image, img_dtype, img_h, img_w, feat, conf, normalize, stream);
+  }
+  // second call: capture on the plan's own stream (the caller's may be the legacy default stream), then launch
+  if (e->cap == nullptr) PTK_CUDA_CHECK(cudaStreamCreateWithFlags(&e->cap, cudaStreamNonBlocking));
+  PTK_CUDA_CHECK(cudaStreamBeginCapture(e->cap, cudaStreamCaptureModeThreadLocal));
+  const int rc = run_plan(e, image, img_dtype, img_h, img_w, feat, conf, normalize, (void*)e->cap);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(e->cap, &graph);
+  if (rc != PTK_OK || ce != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc != PTK_OK) return rc;
+    g->seen = 2;   // capture not possible here: keep launching directly
+    g->image = nullptr;
+    return run_plan(e, image, img_dtype, img_h, img_w, feat, conf, normalize, stream);
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    g->exec = nullptr;
+    g->image = nullptr;
+    cudaGetLastError();
+    return run_plan(e, image, img_dtype, img_h, img_w, feat, conf, normalize, stream);
+  }
+  PTK_CUDA_CHECK(cudaGraphLaunch(g->exec, s));
   return PTK_OK;
 }
 

@@ -146,6 +146,49 @@ def test_full_size_plan_runs_and_is_deterministic():
     assert abs(float(a[1].pow(2).sum(-1).mean()) - 1.0) < 1e-4
 
 
+def test_plan_graph_replay_matches_direct_launches():
+    """ptk_extractor_run launches a binding (image + output buffers) directly the first time, captures the plan
+    in a CUDA graph the second time and replays it afterwards: all three must write the same bytes, a changed
+    image must show up through the replay, and a second binding gets its own graph."""
+    from pixtrack_b200.extractor import B200FeatureExtractor
+    ext = B200FeatureExtractor(syn.unet_weights(2), D)
+    img = syn.textured_image(96, 160, seed=1).to(D)
+    shapes = ext.level_shapes(96, 160, 1)
+    out = ([torch.zeros((h, w, c), device=D) for c, h, w in shapes], [torch.zeros((h, w), device=D) for c, h, w in shapes])
+    runs = []
+    for _ in range(4):                       # direct, capture + launch, replay, replay
+        for t in out[0] + out[1]:
+            t.zero_()
+        ext.extract_device(img, normalize=True, out=out)
+        torch.cuda.synchronize()
+        runs.append([t.clone() for t in out[0] + out[1]])
+    for r in runs[1:]:
+        assert all(torch.equal(x, y) for x, y in zip(runs[0], r))
+    assert float(runs[0][0].abs().sum()) > 0
+    img2 = syn.textured_image(96, 160, seed=2).to(D)
+    fresh, fresh_c, _ = ext.extract_device(img2, normalize=True)     # another binding: direct launches
+    img.copy_(img2)                                                  # same binding, new pixels: replayed graph
+    ext.extract_device(img, normalize=True, out=out)
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(fresh + fresh_c, out[0] + out[1]))
+    assert not torch.equal(out[0][0], runs[0][0])
+    # a non-default stream and use inside the caller's own capture both keep working
+    st = torch.cuda.Stream(D)
+    with torch.cuda.stream(st):
+        ext.extract_device(img, normalize=True, out=out)
+    st.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(fresh + fresh_c, out[0] + out[1]))
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ext.extract_device(img, normalize=True, out=out)
+    img.copy_(syn.textured_image(96, 160, seed=1).to(D))
+    g.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(runs[0], out[0] + out[1]))
+    from pixtrack_b200 import _lib
+    _lib.device_status(0)
+
+
 def test_cta_pair_kernel_matches_fp32_conv_in_a_subprocess():
     """conv_halo2_kernel (tcgen05 cta_group::2, off by default) is selected with PTK_CONV_PAIR=2; the switch is read
     once per process, so the check runs in a child process."""
