@@ -65,6 +65,34 @@ class FrameTracker:
         # overlap the other plan's); the LM launches wait for it through an event
         self._side = torch.cuda.Stream(dev) if overlap_reference else None
         self._ref_done = None
+        self.n_active = N
+
+    def set_points(self, xyz):
+        """Replace the model points by `xyz` [n <= N, 3] (host or device): the point set follows the reference image
+        (Model3D.get_p3did_to_dbids, pixloc/pixloc/localization/model3d.py:49-87).  Buffers keep their size and
+        addresses (prepared launches / graphs stay valid); rows n.. are switched off through the validity flags at
+        the next refresh_reference.  Stream-ordered."""
+        n = int(xyz.shape[0])
+        if n > self.p3d64.shape[0]:
+            raise ValueError(f'{n} points exceed the capacity {self.p3d64.shape[0]} this tracker was built for')
+        src = torch.as_tensor(xyz, dtype=torch.float64).to(self.p3d64.device, non_blocking=True)
+        self.p3d64[:n].copy_(src)
+        self.p3d32[:n].copy_(src)
+        self.n_active = n
+
+    def last_costs(self):
+        """Per view, the final mean cost of every level the LM visited, coarse to fine -- what
+        DebugTracker.costs[level][-1] holds in the reference (pixtrack/localization/tracker.py:37-46, read at
+        pixloc_tracker_r9.py:251).  Synchronises (reads the iteration counts and one log record per level)."""
+        out = [[] for _ in range(self.B)]
+        for L in self.plan.launches:
+            n_it = L.n_iters.cpu()
+            for b in range(self.B):
+                n = int(n_it[b])
+                if n > 0 and L.log is not None:
+                    rec = L.log[b, n - 1, :2].cpu()
+                    out[b].append(float(rec[0] / rec[1]))
+        return out
 
     def refresh_reference(self, view: int, image: Tensor, camera, T_w2cam, scale_image: int = 1):
         """image: CUDA [H,W,3] uint8/fp32 render of reference view `view`; camera / T_w2cam: its camera at the
@@ -82,6 +110,8 @@ class FrameTracker:
             feats, confs, scales = self.extractor.extract_device(image, scale_image, normalize=False, out=bufs)
             sample_reference(feats, confs, scales, camera, T_w2cam, self.p3d64, pad=self.pad, normalize=True,
                              out=([f[view] for f in self.F_ref], [w[view] for w in self.W_ref], self.valid[view]))
+            if self.n_active < self.valid.shape[1]:
+                self.valid[view, self.n_active:].zero_()
             return
         cur = torch.cuda.current_stream(dev)
         self._side.wait_stream(cur)          # the previous frame's LM has finished reading the observation cache
@@ -89,6 +119,8 @@ class FrameTracker:
             feats, confs, scales = self.extractor.extract_device(image, scale_image, normalize=False, out=bufs, slot=1)
             sample_reference(feats, confs, scales, camera, T_w2cam, self.p3d64, pad=self.pad, normalize=True,
                              out=([f[view] for f in self.F_ref], [w[view] for w in self.W_ref], self.valid[view]))
+            if self.n_active < self.valid.shape[1]:
+                self.valid[view, self.n_active:].zero_()
             self._ref_done = torch.cuda.Event()
             self._ref_done.record(self._side)
         image.record_stream(self._side)
