@@ -364,12 +364,27 @@ def _morton_cell_centers(level: int):
     return ((xyz + 0.5) / NERF_GRID - 0.5) * (2.0 ** level) + 0.5
 
 
+def nerf_level_offsets(aabb_scale: int):
+    """Entry offset of each of the 16 hash-grid levels (and the total as a 17th element); same layout as
+    nerf_grid_size."""
+    import numpy as np
+    pls = np.float32(math.exp(math.log(2048.0 * aabb_scale / 16) / 15))
+    log2 = np.float32(np.log2(pls))
+    offs = [0]
+    for lv in range(16):
+        scale = np.float32(np.exp2(np.float32(lv) * log2) * np.float32(16) - np.float32(1))
+        res = int(np.ceil(scale)) + 1
+        offs.append(offs[-1] + min((min(res ** 3, 2 ** 31 - 1) + 7) // 8 * 8, 1 << 19))
+    return offs
+
+
 def nerf_scene(seed: int = 0, aabb_scale: int = 1, radius: float = 0.28, density_gain: float = 8.0,
-               zero_network: bool = False) -> Dict[str, object]:
+               zero_network: bool = False, texture_levels: int = 16) -> Dict[str, object]:
     """A random-weight instant-ngp model with a procedurally filled occupancy grid (a ball of
     `radius` around the cube centre, in every cascade).  Returns numpy arrays shaped like an
     unpacked snapshot: grid fp16 [n,2], w_density ([64,32],[16,64]), w_rgb ([64,32],[64,64],[16,64]),
-    density_grid float32 [(max_cascade+1) * 128^3] (Morton order), aabb_scale."""
+    density_grid float32 [(max_cascade+1) * 128^3] (Morton order), aabb_scale.  texture_levels < 16 zeroes
+    the finer hash levels."""
     import numpy as np
     g = _gen(seed)
     n = nerf_grid_size(aabb_scale)
@@ -380,6 +395,8 @@ def nerf_scene(seed: int = 0, aabb_scale: int = 1, radius: float = 0.28, density
         grid = np.zeros((n, 2), np.float16)
     else:
         grid = ((torch.rand(n, 2, generator=g) * 2 - 1) * 0.6).numpy().astype(np.float16)
+        if texture_levels < 16:      # only the coarse (dense) levels carry signal: a smooth, trackable texture
+            grid[nerf_level_offsets(aabb_scale)[texture_levels]:] = 0
     w_density = (rnd(64, 32, scale=math.sqrt(2.0 / 32)), rnd(16, 64, scale=density_gain * math.sqrt(1.0 / 64)))
     w_density[1][0] = np.abs(w_density[1][0])      # density row: positive weights on ReLU outputs -> dense medium
     w_rgb = (rnd(64, 32, scale=math.sqrt(2.0 / 32)), rnd(64, 64, scale=math.sqrt(2.0 / 64)),
@@ -394,6 +411,37 @@ def nerf_scene(seed: int = 0, aabb_scale: int = 1, radius: float = 0.28, density
         dens.append(np.where(inside, 1.0, -1.0).astype(np.float32))
     return dict(aabb_scale=aabb_scale, grid=grid, w_density=w_density, w_rgb=w_rgb,
                 density_grid=np.concatenate(dens), max_cascade=max_cascade)
+
+
+def nerf_textured_scene(seed: int = 0, aabb_scale: int = 1, radius: float = 0.2, texture_levels: int = 5,
+                        contrast: float = 4.0) -> Dict[str, object]:
+    """Like nerf_scene, but with CONSTRUCTED networks so that the ball is opaque and carries a smooth,
+    zero-mean, view-independent, high-contrast colour pattern (a trackable object): the density MLP passes
+    the signed hash features through (relu(x) - relu(-x)) and sums their magnitudes into the density, the
+    colour MLP ignores the view direction and mixes the features of the `texture_levels` coarsest levels
+    with random +-contrast weights in front of the logistic.  Same array layout as nerf_scene."""
+    import numpy as np
+    sc = nerf_scene(seed, aabb_scale, radius=radius, texture_levels=texture_levels)
+    g = _gen(seed + 7919)
+    wd0 = np.zeros((64, 32), np.float16)
+    for i in range(32):
+        wd0[2 * i, i], wd0[2 * i + 1, i] = 1.0, -1.0
+    wd1 = np.zeros((16, 64), np.float16)
+    wd1[0, :] = 2.0                                         # density raw = 2 * sum |feature| (>> 0 inside the ball)
+    for k in range(1, 16):
+        wd1[k, 2 * (k - 1)], wd1[k, 2 * (k - 1) + 1] = 1.0, -1.0
+    wc0 = np.zeros((64, 32), np.float16)
+    for k in range(1, 16):
+        wc0[2 * k, k], wc0[2 * k + 1, k] = 1.0, -1.0
+    wc1 = np.eye(64, dtype=np.float16)
+    wc2 = np.zeros((16, 64), np.float16)
+    n_feat = min(15, 2 * texture_levels)
+    a = (torch.randint(0, 2, (3, n_feat), generator=g).float() * 2 - 1).numpy() * contrast
+    for c in range(3):
+        for k in range(1, n_feat + 1):
+            wc2[c, 2 * k], wc2[c, 2 * k + 1] = a[c, k - 1], -a[c, k - 1]
+    sc['w_density'], sc['w_rgb'] = (wd0, wd1), (wc0, wc1, wc2)
+    return sc
 
 
 def nerf_look_at(eye, target=(0.5, 0.5, 0.5), up=(0.0, 0.0, 1.0)):

@@ -1,0 +1,90 @@
+'''The whole r9 frame loop on one GPU over a synthetic, self-consistent scene: a NeRF ball (smooth random texture)
+is both the object in the camera frames and the model the tracker renders its references from.
+
+    python profiles/tracker_demo.py [n_frames]
+
+Per frame: (depth render -> mask) -> reference render at the current pose -> 2 UNet extractions -> reference
+sampling -> 3-level LM -> policy (cost threshold, reference choice).  Prints success, cost and pose error.'''
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+from pixtrack_b200 import synthetic as syn  # noqa: E402
+from pixtrack_b200.extractor import B200FeatureExtractor  # noqa: E402
+from pixtrack_b200.geometry import Camera  # noqa: E402
+from pixtrack_b200.nerf import NerfTestbed, get_nerf_image, occupancy_bitfield  # noqa: E402
+from pixtrack_b200.tracker import (B200PoseTracker, DeviceEngine, PoseRt, camera_in_world_from_pose,  # noqa: E402
+                                   sfm_to_nerf_pose)
+
+DEV = 'cuda:0'
+N2S = dict(centroid=np.zeros(3), avglen=3.0, R=np.eye(4), totp=np.zeros(3))      # SfM frame == NeRF frame up to axes
+RADIUS = float(os.environ.get('DEMO_RADIUS', 0.2))                               # ball radius in the NGP unit cube
+R_SURF = (RADIUS + 0.87 / 128) / 0.33                                            # ... and in the SfM frame
+RGB_GAIN = float(os.environ.get('DEMO_RGB_GAIN', 4.0))                           # contrast of the random texture
+LEVELS = int(os.environ.get('DEMO_LEVELS', 5))                                   # hash levels that carry texture
+
+
+def orbit_pose(yaw_deg, pitch_deg=12.0, dist=3.0):
+    """World-to-camera pose of a camera on an orbit around the origin, looking at it."""
+    a, b = np.deg2rad(yaw_deg), np.deg2rad(pitch_deg)
+    Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    Rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+    R = Rx @ Ry
+    return PoseRt(R, np.array([0.0, 0.0, dist]))
+
+
+def visible_points(pose: PoseRt, n, seed):
+    g = np.random.default_rng(seed)
+    x = g.normal(size=(4 * n, 3))
+    x = x / np.linalg.norm(x, axis=1, keepdims=True) * R_SURF
+    c = -pose.R.T @ pose.t                                    # camera centre
+    keep = ((c[None] - x) * x).sum(1) > 0.35 * R_SURF * np.linalg.norm(c)      # well inside the visible cap
+    return x[keep][:n]
+
+
+def build(n_points=3000, seed=4):
+    sc = syn.nerf_textured_scene(seed, 1, radius=RADIUS, texture_levels=LEVELS, contrast=RGB_GAIN)
+    tb = NerfTestbed(sc['grid'], sc['w_density'], sc['w_rgb'], occupancy_bitfield(sc['density_grid'], sc['max_cascade']), 1, DEV)
+    tb.nerf.rendering_min_transmittance = 1e-7
+    ext = B200FeatureExtractor(syn.unet_weights(0), DEV)
+    cam_q = Camera(syn.pixtrack_camera(1920, 1080).double())
+    cam_r = Camera(syn.pixtrack_camera(2016, 1512).double())
+    db = {i + 1: orbit_pose(y) for i, y in enumerate((-24.0, -12.0, 0.0, 12.0, 24.0))}
+    pts = {i: visible_points(p, n_points, 100 + i) for i, p in db.items()}
+    covis = {i: {j: 100 for j in db if j != i and abs(j - i) == 1} for i in db}
+    lams = [10.0 ** (-6.0 + torch.sigmoid(torch.zeros(6)) * 11.0)] * 3            # DampingNet at const = 0 (learned_optimizer.py:24-33)
+    eng = DeviceEngine(ext, tb, N2S, lambda rid: (None, pts[rid]), cam_q, cam_r, lams, (1080, 1920), n_points,
+                       num_iters=150, grad_stop=1e-4, dt_stop=5e-3, dR_stop=5e-2)
+    trk = B200PoseTracker(eng, {i: p.R for i, p in db.items()}, {i: p.t for i, p in db.items()}, covis, 3)
+    return tb, cam_q, trk
+
+
+def query_frame(tb, cam_q, pose):
+    nerf_pose = sfm_to_nerf_pose(N2S, camera_in_world_from_pose(pose))
+    return get_nerf_image(tb, nerf_pose, cam_q, device_output=True).clone()
+
+
+def main(n_frames=8):
+    tb, cam_q, trk = build()
+    rows = []
+    for f in range(n_frames):
+        gt = orbit_pose(1.0 + 2.0 * f, 12.0 + 0.3 * f, 3.0 + 0.01 * f)
+        img = query_frame(tb, cam_q, gt)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        trk.run_single_frame((f'frame{f:03d}.png', img))
+        dt = time.perf_counter() - t0
+        dR, dT = (gt.inv() @ trk.pose).magnitude()
+        log = trk.pose_tracker_history[f'frame{f:03d}.png']
+        rows.append((trk.success, dR, dT))
+        print(f'frame {f}: success={trk.success} ref={trk.reference_ids} costs={[round(c[-1], 4) for c in log.costs]} '
+              f'thr={trk.cost_threshold:.4f} err={dR:.3f} deg {dT:.4f}  wall {dt * 1e3:.1f} ms', flush=True)
+    return rows
+
+
+if __name__ == '__main__':
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 8)
