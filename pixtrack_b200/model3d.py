@@ -69,6 +69,11 @@ class PointTables:
         """(point ids [n], xyz float64 [n,3]) of the 3D points seen by `image_id` with a long enough track."""
         return self._points_of_image[int(image_id)]
 
+    @property
+    def max_points(self) -> int:
+        """Largest per-image point set: the capacity a FrameTracker / DeviceEngine needs."""
+        return max((len(v[0]) for v in self._points_of_image.values()), default=0)
+
     def points_of_images(self, image_ids: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
         """Union over several reference images, in the reference's first-seen order."""
         ids = np.concatenate([self._points_of_image[int(i)][0] for i in image_ids]) if len(image_ids) else np.zeros(0, np.int64)

@@ -65,3 +65,18 @@ def test_edge_cases():
     covis = om.extract_covisibility(img_pts, tracks)
     assert tab.covisible(7) == covis[7] and tab.covisible(9) == covis[9]
     assert tab.nearest_reference(np.eye(3), 5) == [5]
+
+
+def test_tracker_built_from_tables_chooses_references_like_the_tables():
+    """B200PoseTracker.from_tables: its dict-based update_reference_ids (the pinned restatement of r9.py:120-143)
+    and PointTables.nearest_reference agree on a synthetic SfM model."""
+    from pixtrack_b200.tracker import B200PoseTracker, PoseRt
+    img_pts, R, xyz, tracks, rng = _model(4)
+    tab = PointTables(img_pts, R, xyz, tracks)
+    assert tab.max_points == max(len(tab.points_of_image(i)[0]) for i in img_pts)
+    trk = B200PoseTracker.from_tables(None, tab, {i: np.zeros(3) for i in img_pts}, int(list(img_pts)[0]), min_covis=3)
+    for _ in range(20):
+        cur = int(rng.choice(list(img_pts)))
+        trk.reference_ids, trk.cache_hit = [cur], False
+        trk.pose = PoseRt(_rot(rng), np.zeros(3))
+        assert trk.update_reference_ids() == tab.nearest_reference(trk.pose.R, cur, min_covis=3)
