@@ -427,7 +427,7 @@ def nerf_textured_scene(seed: int = 0, aabb_scale: int = 1, radius: float = 0.2,
     for i in range(32):
         wd0[2 * i, i], wd0[2 * i + 1, i] = 1.0, -1.0
     wd1 = np.zeros((16, 64), np.float16)
-    wd1[0, :] = 2.0                                         # density raw = 2 * sum |feature| (>> 0 inside the ball)
+    wd1[0, :] = 6.0                                         # density raw = 6 * sum |feature|: opaque within a step or two
     for k in range(1, 16):
         wd1[k, 2 * (k - 1)], wd1[k, 2 * (k - 1) + 1] = 1.0, -1.0
     wc0 = np.zeros((64, 32), np.float16)

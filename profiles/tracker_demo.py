@@ -4,7 +4,8 @@ is both the object in the camera frames and the model the tracker renders its re
     python profiles/tracker_demo.py [n_frames]
 
 Per frame: (depth render -> mask) -> reference render at the current pose -> 2 UNet extractions -> reference
-sampling -> 3-level LM -> policy (cost threshold, reference choice).  Prints success, cost and pose error.'''
+sampling -> 3-level LM -> policy (cost threshold, reference choice).  Prints success, cost, pose error and the
+wall time of the whole frame (measured: 13-14 ms with the 1920x1080 depth render for the mask, 6 ms without).'''
 import os
 import sys
 import time
@@ -72,7 +73,9 @@ def main(n_frames=8):
     tb, cam_q, trk = build()
     rows = []
     for f in range(n_frames):
-        gt = orbit_pose(1.0 + 2.0 * f, 12.0 + 0.3 * f, 3.0 + 0.01 * f)
+        # a static object, then one 15-degree jump, then back.  (The UNet weights are random, so the features are not
+        # smooth and the refinement only holds a pose it is already close to; following motion needs trained weights.)
+        gt = orbit_pose(15.0 if f == n_frames - 2 else 0.0)
         img = query_frame(tb, cam_q, gt)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
