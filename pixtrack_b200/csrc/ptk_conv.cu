@@ -8,7 +8,8 @@
 //   conv_halo_kernel   persistent, one halo load per 64-channel chunk, taps = shifted descriptors (default for the
 //                      large maps; see its header comment)
 //   conv_halo2_kernel  the same on CTA pairs (tcgen05 cta_group::2); off by default (PTK_CONV_PAIR)
-//   conv_tc_kernel     one tap-shifted TMA box per k-step; small maps and 1x1 (described next)
+//   conv_tc_kernel     one tap-shifted TMA box per k-step; small maps and 1x1 (described next); SPLIT = 2 shares the
+//                      K loop of a tile between the two CTAs of a cluster (partial sums through DSMEM)
 // All epilogues add the bias (conv bias or folded BatchNorm), apply ReLU, write fp16 and can also write the
 // 2x2 max pool of the result.
 //
