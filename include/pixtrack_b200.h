@@ -229,8 +229,8 @@ int ptk_extractor_level_shape(const PtkExtractor* e, int32_t level, int32_t* C, 
 /* image: [img_h][img_w][3] RGB, img_dtype 0 = fp32 in 0..255, 1 = uint8 (converted to float before the
  * bilinear resize; the reference's cv2 path for uint8 rounds the resized image back to uint8 first).
  * Stream-ordered.  A binding (image pointer + the six output pointers + sizes) is launched kernel by kernel the
- * first time it is seen, captured into a CUDA graph the second time and replayed afterwards (at most 8 bindings per
- * extractor; PTK_PLAN_GRAPH=0 disables it; inside a caller's own stream capture the kernels are launched directly),
+ * first time it is seen, captured into a CUDA graph the second time and replayed afterwards (8 bindings per extractor, least
+ * recently used replaced; PTK_PLAN_GRAPH=0 disables it; inside a caller's own stream capture the kernels are launched directly),
  * so the buffers of a binding must stay allocated for as long as it is used -- as for any prepared launch. */
 int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
                       float* const* feat, float* const* conf, int32_t normalize, void* stream);

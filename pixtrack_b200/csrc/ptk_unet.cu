@@ -389,8 +389,10 @@ struct PtkExtractor {
     float* feat[3];
     float* conf[3];
     cudaGraphExec_t exec;
+    unsigned long long last_use;
   } graphs[8];
   int n_graphs;
+  unsigned long long use_clock;
   cudaStream_t cap;
 };
 #define PTK_MAX_LAUNCHES 48
@@ -605,6 +607,7 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
     for (int l = 0; l < 3 && same; ++l) same = c.feat[l] == feat[l] && c.conf[l] == conf[l];
     if (same) g = &c;
   }
+  if (g != nullptr) g->last_use = ++e->use_clock;
   if (g != nullptr && g->exec != nullptr) {
     PTK_CUDA_CHECK(cudaGraphLaunch(g->exec, s));
     return PTK_OK;
@@ -612,11 +615,20 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
   if (g == nullptr) {   // first call with this binding: run directly (also configures every kernel it uses)
     if (e->n_graphs < 8) {
       g = &e->graphs[e->n_graphs++];
-      g->image = image; g->img_dtype = img_dtype; g->img_h = img_h; g->img_w = img_w; g->normalize = normalize;
-      for (int l = 0; l < 3; ++l) { g->feat[l] = feat[l]; g->conf[l] = conf[l]; }
-      g->seen = 1;
-      g->exec = nullptr;
+    } else {            // table full: the least recently used binding makes room (callers that allocate fresh outputs
+      g = &e->graphs[0];   // every call only ever occupy key slots; their graphs are never built)
+      for (int i = 1; i < 8; ++i) if (e->graphs[i].last_use < g->last_use) g = &e->graphs[i];
+      if (g->exec != nullptr) {
+        // a replay of this graph may still be in flight on some stream: retire it before destroying it
+        PTK_CUDA_CHECK(cudaDeviceSynchronize());
+        cudaGraphExecDestroy(g->exec);
+      }
     }
+    g->image = image; g->img_dtype = img_dtype; g->img_h = img_h; g->img_w = img_w; g->normalize = normalize;
+    for (int l = 0; l < 3; ++l) { g->feat[l] = feat[l]; g->conf[l] = conf[l]; }
+    g->seen = 1;
+    g->exec = nullptr;
+    g->last_use = ++e->use_clock;
     return run_plan(e, image, img_dtype, img_h, img_w, feat, conf, normalize, stream);
   }
   // second call: capture on the plan's own stream (the caller's may be the legacy default stream), then launch

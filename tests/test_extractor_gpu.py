@@ -185,6 +185,15 @@ def test_plan_graph_replay_matches_direct_launches():
     g.replay()
     torch.cuda.synchronize()
     assert all(torch.equal(x, y) for x, y in zip(runs[0], out[0] + out[1]))
+    # more bindings than the plan keeps (8): the least recently used ones are replaced, results never change
+    outs = [([torch.zeros((h, w, c), device=D) for c, h, w in shapes], [torch.zeros((h, w), device=D) for c, h, w in shapes])
+            for _ in range(10)]
+    for rep in range(3):                     # direct, capture, replay -- while cycling through 10 bindings
+        for o in outs:
+            ext.extract_device(img, normalize=True, out=o)
+    torch.cuda.synchronize()
+    for o in outs:
+        assert all(torch.equal(x, y) for x, y in zip(runs[0], o[0] + o[1]))
     from pixtrack_b200 import _lib
     _lib.device_status(0)
 

@@ -121,7 +121,7 @@ def test_dynamic_reference_store_is_bounded_and_outputs_are_written(tmp_path):
     assert sorted(poses) == [f'f{i:03d}.jpg' for i in range(9)] == sorted(logs)
     ok = poses['f008.jpg']
     assert set(ok) == {'T_init', 'T_refined', 'camera', 'dbids', 'diff_R', 'diff_t', 'query_path', 'reference_ids', 'success'}
-    R, t = ok['T_refined'].numpy()                              # what run_vis_on_poses.py reads
+    R, t = ok['T_refined'].cpu().numpy()                        # how run_vis_on_poses.py / pose_utils.py:16-22 read it
     assert R.shape == (3, 3) and t.shape == (3,)
     assert 'T_refined' not in poses['f005.jpg'] and poses['f005.jpg']['success'] is False
 
