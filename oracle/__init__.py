@@ -17,6 +17,9 @@ the unmodified reference executed in the authoring container:
 `interpolate_tensor`, `Camera.world2image`, `UNet._forward`, ... on seeded
 inputs and stores inputs + outputs in `tests/golden/*.npz`;
 `tests/test_oracle_golden.py` checks every oracle function against them.
-The NeRF render has no runnable reference here (pyngp cannot be built):
-"parity unpinned" for that row.
+The NeRF render has no runnable reference here (pyngp cannot be built or run):
+its host-callable header code is compiled in place (oracle/build_ref.py ->
+oracle/_ref/ngp_host) and pins the jitter, colour transfer, camera conversion,
+ray generation and box test of oracle/nerf.py (tests/golden/nerf_host.json);
+the device-only rest of that row stays "parity unpinned".
 """

@@ -2,12 +2,17 @@
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  numpy float32/float16, vectorised over rays.
 
-PARITY UNPINNED: the reference renderer is the native `pyngp` module (instant-ngp + tiny-cuda-nn,
-CUDA only).  It cannot be built in this container (cmake project with GLFW/GLEW/Vulkan and
-CUDA-11-era sources), no snapshot ships with the reference, and the reference holds no
-test vectors for it.  This file restates the published algorithm from the reference sources; it is
-checked against analytic cases in tests/test_nerf_oracle.py (empty occupancy -> nothing rendered,
-zero network -> closed-form transmittance, hash/index known answers) instead of reference outputs.
+PARITY PARTLY PINNED.  The reference renderer is the native `pyngp` module (instant-ngp + tiny-cuda-nn,
+CUDA only): it cannot be built or run in this container (cmake project with GLFW/GLEW/Vulkan, no GPU),
+no snapshot ships with the reference, and the reference holds no test vectors for it.  What CAN run here
+is the reference's host-callable header code, compiled in place by oracle/build_ref.py
+(oracle/ngp_ref/ngp_host.cu -> oracle/_ref/ngp_host); its outputs are stored in
+tests/golden/nerf_host.json and pin, in tests/test_nerf_oracle.py:
+    ld_random_val (bit-exact), srgb_to_linear / linear_to_srgb, fov_to_focal, nerf_matrix_to_ngp (bit-exact),
+    pixel_rays (= pixel_to_ray + normalisation), ray_box / _contains (= BoundingBox::ray_intersect / contains).
+UNPINNED (device-only code in the reference: hash grid, SH encoding, fused MLPs, occupancy marching,
+compositing): restated from the sources and checked against analytic cases (empty occupancy -> nothing
+rendered, zero network -> closed-form transmittance, hash/index known answers).
 One deliberate numerical difference: tiny-cuda-nn's fully fused MLP accumulates in fp16 inside
 wmma fragments (fully_fused_mlp.cu:67-69); here, and in csrc/ptk_nerf.cu, products of fp16
 operands are accumulated in fp32 and rounded to fp16 once per layer.
@@ -375,6 +380,48 @@ def nerf_matrix_to_ngp(m: NerfModel, mat: np.ndarray) -> np.ndarray:
     return r[[1, 2, 0], :]
 
 
+def pixel_rays(cam: np.ndarray, width: int, height: int, fov_deg: float, fov_axis: int = 0):
+    """Origin and unit direction of the ray through every pixel centre, row-major: pixel_to_ray with
+    snap_to_pixel_centers (the offset is fract(0.5 - v + v) = 0.5), screen centre 0.5, no parallax / aperture /
+    distortion (common_device.cuh:260-307), then the normalisation of init_rays_with_payload_kernel_nerf
+    (testbed_nerf.cu:1842-1849).  focal = calc_focal_length at zoom 1 (testbed.cu:2460-2462)."""
+    cam = np.asarray(cam, f32)
+    res = (width, height)
+    focal = f32(fov_to_focal(1, fov_deg) * f32(res[fov_axis]))
+    ys, xs = np.meshgrid(np.arange(height), np.arange(width), indexing='ij')
+    px, py = xs.ravel().astype(f32), ys.ravel().astype(f32)
+    n = px.size
+    u = (px + f32(0.5)) / f32(width)
+    v = (py + f32(0.5)) / f32(height)
+    dcam = np.stack([(u - f32(0.5)) * f32(width) / focal, (v - f32(0.5)) * f32(height) / focal, np.ones(n, f32)], 1)
+    d = ((dcam[:, 0:1] * cam[None, :, 0] + dcam[:, 1:2] * cam[None, :, 1]) + dcam[:, 2:3] * cam[None, :, 2]).astype(f32)
+    d = (d / np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])[:, None]).astype(f32)
+    o = np.broadcast_to(cam[:, 3], (n, 3)).astype(f32)
+    return o, d
+
+
+def ray_box(box, o: np.ndarray, d: np.ndarray):
+    """BoundingBox::ray_intersect (bounding_box.cuh:163-208): (tmin, tmax) per ray, both FLT_MAX on a miss."""
+    with np.errstate(divide='ignore', invalid='ignore'):
+        t0 = ((box[0] - o) / d).astype(f32)
+        t1 = ((box[1] - o) / d).astype(f32)
+    lo, hi = np.minimum(t0, t1), np.maximum(t0, t1)
+    tmin, tmax = lo[:, 0].copy(), hi[:, 0].copy()
+    miss = np.zeros(o.shape[0], bool)
+    for a in (1, 2):
+        miss |= (tmin > hi[:, a]) | (lo[:, a] > tmax)
+        tmin = np.where(lo[:, a] > tmin, lo[:, a], tmin)
+        tmax = np.where(hi[:, a] < tmax, hi[:, a], tmax)
+    big = np.finfo(f32).max
+    return np.where(miss, big, tmin).astype(f32), np.where(miss, big, tmax).astype(f32)
+
+
+def linear_to_srgb(x):
+    """common_device.cuh:55-61."""
+    x = x.astype(f32)
+    return np.where(x < f32(0.0031308), f32(12.92) * x, f32(1.055) * np.power(np.maximum(x, 0), f32(0.41666)) - f32(0.055)).astype(f32)
+
+
 def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov_deg: float, spp: int = 8,
            depth_mode: bool = False, min_transmittance: float = 1e-7, fov_axis: int = 0,
            background=(1.0, 1.0, 1.0, 0.0)) -> Dict[str, np.ndarray]:
@@ -387,33 +434,13 @@ def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov
     :693-752 (samples), :754-955 (composite), :1721-1754 (shade); render_buffer.cu:236-275
     (accumulate), :542-570 (tonemap, linear, identity curve)."""
     cam = np.asarray(camera_matrix, f32)
-    res = (width, height)
-    focal = f32(fov_to_focal(1, fov_deg) * f32(res[fov_axis]))          # calc_focal_length, zoom 1
-    ys, xs = np.meshgrid(np.arange(height), np.arange(width), indexing='ij')
-    px, py = xs.ravel().astype(f32), ys.ravel().astype(f32)
-    n = px.size
-    # pixel_to_ray, snap_to_pixel_centers: offset = fract(0.5 - v + v) = 0.5 (common_device.cuh:260-307)
-    u = (px + f32(0.5)) / f32(width)
-    v = (py + f32(0.5)) / f32(height)
-    dcam = np.stack([(u - f32(0.5)) * f32(width) / focal, (v - f32(0.5)) * f32(height) / focal, np.ones(n, f32)], 1)
-    d = ((dcam[:, 0:1] * cam[None, :, 0] + dcam[:, 1:2] * cam[None, :, 1]) + dcam[:, 2:3] * cam[None, :, 2]).astype(f32)
-    d = (d / np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])[:, None]).astype(f32)
-    o = np.broadcast_to(cam[:, 3], (n, 3)).astype(f32)
+    o, d = pixel_rays(cam, width, height, fov_deg, fov_axis)
+    n = o.shape[0]
     cam_fwd = cam[:, 2]
     depth_scale = f32(1.0 / m.scale)
     with np.errstate(divide='ignore', invalid='ignore'):
         idir = (f32(1) / d).astype(f32)
-        t0 = (m.render_aabb[0] - o) / d
-        t1 = (m.render_aabb[1] - o) / d
-    # BoundingBox::ray_intersect (bounding_box.cuh:163-208), entry distance only
-    lo, hi = np.minimum(t0, t1), np.maximum(t0, t1)
-    tmin, tmax = lo[:, 0].copy(), hi[:, 0].copy()
-    miss = np.zeros(n, bool)
-    for a in (1, 2):
-        miss |= (tmin > hi[:, a]) | (lo[:, a] > tmax)
-        tmin = np.where(lo[:, a] > tmin, lo[:, a], tmin)
-        tmax = np.where(hi[:, a] < tmax, hi[:, a], tmax)
-    tmin = np.where(miss, np.finfo(f32).max, tmin).astype(f32)
+    tmin, _ = ray_box(m.render_aabb, o, d)
     accum = np.zeros((n, 4), f32)
     depth_out = np.zeros(n, f32)
     pix = np.arange(n, dtype=np.uint64)

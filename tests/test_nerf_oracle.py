@@ -1,9 +1,12 @@
 """CPU: the NeRF-render oracle (oracle/nerf.py) against analytic cases and known answers.
 
-The reference renderer (pyngp) is not runnable here and ships no test vectors, so the restatement is
-checked against properties of the published algorithm instead ("parity unpinned"):
-hash-grid layout numbers, Morton codes, the (0,1)-sequence property of the Owen-scrambled Sobol
-jitter, occupancy pooling, empty space, and a closed-form transmittance for a zero network.
+The reference renderer (pyngp) is not runnable here and ships no test vectors.  Its host-callable header code
+is: the jitter sequence, colour transfer, focal length, camera-matrix conversion, ray generation and box
+intersection of the oracle are pinned against it (bottom of this file, fixture tests/golden/nerf_host.json made by
+tests/golden/gen/make_nerf_goldens.py).  The device-only parts (hash grid, SH, MLPs, marching, compositing) are
+checked against properties of the published algorithm instead ("parity partly pinned"):
+hash-grid layout numbers, Morton codes, the (0,1)-sequence property of the Owen-scrambled Sobol jitter, occupancy
+pooling, empty space, and a closed-form transmittance for a zero network.
 """
 import numpy as np
 import pytest
@@ -149,3 +152,56 @@ def test_opaque_scene_saturates_and_depth_mode_is_consistent():
     # ball centre, the surface of the radius-0.28 ball about 1.12
     assert 1.05 / 0.33 < c[0] / c[3] < 1.25 / 0.33 and c[0] == c[1] == c[2]
     assert np.array_equal(dep[..., 3] > 0, a > 0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Pinned pieces: tests/golden/nerf_host.json holds the outputs of the reference's own host-callable functions
+# (instant-ngp headers compiled in place by oracle/build_ref.py, harness oracle/ngp_ref/ngp_host.cu).
+# ------------------------------------------------------------------------------------------------------------
+import json
+import os
+
+HOST = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'nerf_host.json')))
+
+
+def test_jitter_sequence_matches_the_reference_bit_for_bit():
+    rec = np.array(HOST['ld_random_val'], dtype=np.float64)
+    got = nerf.ld_random_val(rec[:, 0].astype(np.uint64), rec[:, 1].astype(np.uint64))
+    assert np.array_equal(got.astype(f32), rec[:, 2].astype(f32))
+
+
+def test_colour_transfer_and_focal_length_match_the_reference():
+    rec = np.array(HOST['srgb'], dtype=np.float64).astype(f32)
+    np.testing.assert_allclose(nerf.srgb_to_linear(rec[:, 0]), rec[:, 1], rtol=3e-7, atol=1e-9)       # powf: <= 2 ulp
+    np.testing.assert_allclose(nerf.linear_to_srgb(rec[:, 0]), rec[:, 2], rtol=3e-7, atol=1e-9)
+    for res, deg, focal in HOST['fov_to_focal']:
+        assert abs(float(nerf.fov_to_focal(int(res), deg)) - focal) <= 2e-7 * focal
+
+
+def test_camera_matrix_conversion_matches_the_reference():
+    m = model(syn.nerf_scene(0, 1))
+    got = nerf.nerf_matrix_to_ngp(m, np.array(HOST['nerf_matrix'], f32).reshape(3, 4))
+    assert np.array_equal(got, np.array(HOST['ngp_matrix'], f32).reshape(3, 4))
+
+
+def test_rays_and_box_intersection_match_the_reference():
+    R = HOST['rays']
+    cam = np.array(R['camera'], f32).reshape(3, 4)
+    o, d = nerf.pixel_rays(cam, R['width'], R['height'], R['fov'])
+    boxes = [np.array([[b[0]] * 3, [b[1]] * 3], f32) for b in R['boxes']]
+    t1 = nerf.ray_box(boxes[0], o, d)
+    t4 = nerf.ray_box(boxes[1], o, d)
+    n_hit = 0
+    for s in R['samples']:
+        i = s['y'] * R['width'] + s['x']                       # snap_to_pixel_centers: the sample index does not matter
+        assert np.array_equal(o[i], np.array(s['o'], f32))
+        np.testing.assert_allclose(d[i], np.array(s['d'], f32), rtol=0, atol=2e-7)
+        for got, key in ((t1, 't_box1'), (t4, 't_box4')):
+            ref = np.array(s[key], f32)
+            if ref[0] > 1e30:
+                assert got[0][i] > 1e30 and got[1][i] > 1e30
+            else:
+                n_hit += key == 't_box1'
+                np.testing.assert_allclose([got[0][i], got[1][i]], ref, rtol=2e-6, atol=2e-6)
+        assert bool(nerf._contains(boxes[1], o[i:i + 1])[0]) == bool(s['in_box4'])
+    assert n_hit >= 100
