@@ -15,6 +15,41 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = '/root/reference/instant-ngp'
 
 
+# testbed_nerf.cu keeps its marching helpers local to the translation unit (and marks most of them __device__);
+# the whole file needs the GUI / Testbed headers.  These definitions are therefore lifted out AT BUILD TIME into a
+# temporary include (deleted after the compile; never committed), with `__device__` widened to
+# `__host__ __device__` so that the harness can call them on the CPU.  The function bodies are untouched.
+HELPERS = ['NERF_RENDERING_NEAR_DISTANCE', 'NERF_STEPS', 'NERF_CASCADES', 'SQRT3', 'STEPSIZE', 'MIN_CONE_STEPSIZE',
+           'MAX_CONE_STEPSIZE', 'grid_mip_offset', 'calc_dt', 'distance_to_next_voxel', 'advance_to_next_voxel',
+           'warp_position', 'unwarp_position', 'warp_direction', 'warp_dt', 'unwarp_dt', 'cascaded_grid_idx_at',
+           'density_grid_occupied_at', 'mip_from_pos', 'mip_from_dt']
+
+
+TCNN_HELPERS = ['fast_hash', 'grid_index']      # tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:82-116
+
+
+def lift_helpers(cu_path: str, names=None) -> str:
+    import re
+    lines = open(cu_path).read().split('\n')
+    out = []
+    for name in (names or HELPERS):
+        pat = re.compile(r'^(inline |static )?(constexpr )?(__host__ )?(__device__ )[\w:<>, &\*]*\b' + name + r'\(')
+        start = next(i for i, ln in enumerate(lines) if pat.match(ln))
+        if lines[start - 1].startswith('template'):
+            out.append(lines[start - 1])
+        depth, i = 0, start
+        while True:
+            depth += lines[i].count('{') - lines[i].count('}')
+            if depth == 0 and '{' in ''.join(lines[start:i + 1]):
+                break
+            i += 1
+        body = lines[start:i + 1]
+        if '__host__' not in body[0]:
+            body[0] = body[0].replace('__device__', '__host__ __device__', 1)
+        out.extend(body + [''])
+    return '\n'.join(out)
+
+
 def build(verbose: bool = True) -> str:
     """Returns the path of the binary, or '' when the reference tree is absent (e.g. on the GPU box)."""
     if not os.path.isdir(os.path.join(REF, 'include', 'neural-graphics-primitives')):
@@ -30,9 +65,23 @@ def build(verbose: bool = True) -> str:
            os.path.join(tcnn, 'include'), os.path.join(tcnn, 'dependencies'), os.path.join(tcnn, 'dependencies', 'fmt', 'include')]
     cmd = ['nvcc', '-std=c++14', '-arch=sm_80', '--extended-lambda', '--expt-relaxed-constexpr', '-w', '-x', 'cu',
            '-DFMT_HEADER_ONLY', '-DTCNN_MIN_GPU_ARCH=80', '-DNGP_VERSION="ref"'] + [f'-I{i}' for i in inc] + [src, '-o', out]
+    tmp_inc = os.path.join(out_dir, 'tmp_include')
+    os.makedirs(tmp_inc, exist_ok=True)
+    lifted = os.path.join(tmp_inc, 'testbed_nerf_helpers.inc')
+    with open(lifted, 'w') as f:
+        f.write(lift_helpers(os.path.join(REF, 'src', 'testbed_nerf.cu')))
+    lifted2 = os.path.join(tmp_inc, 'tcnn_grid_helpers.inc')
+    with open(lifted2, 'w') as f:
+        f.write(lift_helpers(os.path.join(tcnn, 'include', 'tiny-cuda-nn', 'encodings', 'grid.h'), TCNN_HELPERS))
+    cmd.insert(-3, f'-I{tmp_inc}')
     if verbose:
         print(' '.join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+    try:
+        subprocess.run(cmd, check=True)
+    finally:
+        os.remove(lifted)
+        os.remove(lifted2)
+        os.rmdir(tmp_inc)
     return out
 
 

@@ -9,10 +9,15 @@ is the reference's host-callable header code, compiled in place by oracle/build_
 (oracle/ngp_ref/ngp_host.cu -> oracle/_ref/ngp_host); its outputs are stored in
 tests/golden/nerf_host.json and pin, in tests/test_nerf_oracle.py:
     ld_random_val (bit-exact), srgb_to_linear / linear_to_srgb, fov_to_focal, nerf_matrix_to_ngp (bit-exact),
-    pixel_rays (= pixel_to_ray + normalisation), ray_box / _contains (= BoundingBox::ray_intersect / contains).
-UNPINNED (device-only code in the reference: hash grid, SH encoding, fused MLPs, occupancy marching,
-compositing): restated from the sources and checked against analytic cases (empty occupancy -> nothing
-rendered, zero network -> closed-form transmittance, hash/index known answers).
+    pixel_rays (= pixel_to_ray + normalisation), ray_box / _contains (= BoundingBox::ray_intersect / contains),
+    and -- from definitions that build_ref.py lifts out of testbed_nerf.cu / tcnn's grid.h at build time, widening
+    __device__ to __host__ __device__ without touching the bodies -- the step-size constants, calc_dt, mip_from_pos,
+    mip_from_dt, cascaded_grid_idx (bit-exact), occupied_bits (bit-exact), distance_to_next_voxel,
+    advance_to_next_voxel, the position / direction / dt warps, morton3d, fast_hash and grid_index (bit-exact).
+UNPINNED (device kernels in the reference): the trilinear hash-grid interpolation around those indices, the SH
+encoding, the fused MLPs and the compositing loop: restated from the sources and checked against analytic cases
+(empty occupancy -> nothing rendered, zero network -> closed-form transmittance, constant table -> constant
+encoding).
 One deliberate numerical difference: tiny-cuda-nn's fully fused MLP accumulates in fp16 inside
 wmma fragments (fully_fused_mlp.cu:67-69); here, and in csrc/ptk_nerf.cu, products of fp16
 operands are accumulated in fp32 and rounded to fp16 once per layer.
@@ -190,6 +195,25 @@ def ld_random_val(index, seed):
 # ------------------------------------------------------------------------------------------------
 # network                                              nerf_network.h:101-136
 # ------------------------------------------------------------------------------------------------
+def fast_hash(c) -> np.ndarray:
+    """tcnn/include/tiny-cuda-nn/encodings/grid.h:82-98 for 3 dimensions (uint32 wrap-around arithmetic)."""
+    primes = (np.uint64(1), np.uint64(2654435761), np.uint64(805459861))
+    return _u32(c[0] * primes[0]) ^ _u32(c[1] * primes[1]) ^ _u32(c[2] * primes[2])
+
+
+def grid_index(c, res: int, size: int) -> np.ndarray:
+    """grid.h:100-116 (GridType::Hash): entry of grid vertex c = (cx, cy, cz) (uint64 arrays holding uint32 values)
+    inside a level with `size` entries: dense strides while stride <= size, the hash when the level does not fit."""
+    stride, index, d = 1, np.zeros(c[0].shape[0], np.uint64), 0
+    while d < 3 and stride <= size:
+        index = _u32(index + _u32(c[d] * np.uint64(stride)))
+        stride = (stride * res) & 0xFFFFFFFF
+        d += 1
+    if size < stride:
+        index = fast_hash(c)
+    return index % np.uint64(size)
+
+
 def hash_encode(m: NerfModel, x: np.ndarray) -> np.ndarray:
     """x [n,3] fp32 in the unit cube of the training box -> fp16 [n,32].
     tcnn/include/tiny-cuda-nn/encodings/grid.h:81-116 (index / hash), :139-275 (kernel_grid, linear
@@ -197,7 +221,6 @@ def hash_encode(m: NerfModel, x: np.ndarray) -> np.ndarray:
     scales, ress, offs = m.layout
     n = x.shape[0]
     out = np.zeros((n, N_LEVELS * N_FEAT), np.float16)
-    primes = (np.uint64(1), np.uint64(2654435761), np.uint64(805459861))
     for lv in range(N_LEVELS):
         scale, res = scales[lv], int(ress[lv])
         size = int(offs[lv + 1] - offs[lv])
@@ -216,15 +239,7 @@ def hash_encode(m: NerfModel, x: np.ndarray) -> np.ndarray:
                 else:
                     wt = wt * (f32(1) - w[:, d])
                     c.append(g[:, d])
-            # grid_index: dense strides while stride <= size, hash when the level does not fit
-            stride, index, d = 1, np.zeros(n, np.uint64), 0
-            while d < 3 and stride <= size:
-                index = _u32(index + _u32(c[d] * np.uint64(stride)))
-                stride *= res
-                d += 1
-            if size < stride:
-                index = _u32(c[0] * primes[0]) ^ _u32(c[1] * primes[1]) ^ _u32(c[2] * primes[2])
-            index = (index % np.uint64(size)).astype(np.int64) + offs[lv]
+            index = grid_index(c, res, size).astype(np.int64) + offs[lv]
             val = m.grid[index].astype(f32)
             acc = (acc + (wt[:, None] * val).astype(np.float16)).astype(np.float16)
         out[:, lv * N_FEAT:(lv + 1) * N_FEAT] = acc
@@ -300,13 +315,23 @@ def mip_from_dt(dt, pos):
     return np.where(d < 1, mip, np.minimum(CASCADES - 1, np.maximum(e, mip))).astype(np.int64)
 
 
-def occupied(m: NerfModel, pos, mip):
+def cascaded_grid_idx(pos, mip):
+    """cascaded_grid_idx_at (:312-331): Morton index of the occupancy cell of `pos` in cascade `mip`."""
     scale = np.ldexp(f32(1), -mip).astype(f32)
     p = (pos - f32(0.5)) * scale[:, None] + f32(0.5)
     i = np.clip((p * f32(GRID)).astype(np.int32), 0, GRID - 1).astype(np.uint32)
-    idx = morton3d(i[:, 0], i[:, 1], i[:, 2]).astype(np.int64)
-    byte = m.bitfield[idx // 8 + mip * (GRID ** 3 // 8)]
+    return morton3d(i[:, 0], i[:, 1], i[:, 2]).astype(np.int64)
+
+
+def occupied_bits(bitfield, pos, mip):
+    """density_grid_occupied_at (:333-336)."""
+    idx = cascaded_grid_idx(pos, mip)
+    byte = bitfield[idx // 8 + mip * (GRID ** 3 // 8)]
     return (byte >> (idx % 8).astype(np.uint8)) & 1 > 0
+
+
+def occupied(m: NerfModel, pos, mip):
+    return occupied_bits(m.bitfield, pos, mip)
 
 
 def distance_to_next_voxel(pos, d, idir, res):
@@ -314,6 +339,17 @@ def distance_to_next_voxel(pos, d, idir, res):
     sg = np.copysign(f32(1), d)
     tt = (np.floor(p + f32(0.5) + f32(0.5) * sg) - p) * idir
     return np.maximum(np.fmin(np.fmin(tt[:, 0], tt[:, 1]), tt[:, 2]) / res.astype(f32), f32(0))   # device min() drops NaN
+
+
+def advance_to_next_voxel(t, cone, pos, d, idir, res):
+    """:195-207: regular stepping past the current empty cell: do { t += calc_dt(t) } while (t < t_target)."""
+    target = (t + distance_to_next_voxel(pos, d, idir, res)).astype(f32)
+    tk = t.astype(f32).copy()
+    adv = np.ones(tk.shape[0], bool)
+    while adv.any():
+        tk[adv] = (tk[adv] + calc_dt(tk[adv], cone)).astype(f32)
+        adv = adv & (tk < target)
+    return tk
 
 
 def _dot3(a, b):
@@ -350,13 +386,7 @@ def _skip_empty(m: NerfModel, o, d, idir, t, alive):
         if k.size == 0:
             continue
         res = (GRID >> mip).astype(np.int64)
-        target = (t[k] + distance_to_next_voxel(p, d[k], idir[k], res)).astype(f32)
-        tk = t[k].copy()
-        adv = np.ones(k.size, bool)                    # do { t += dt } while (t < target)
-        while adv.any():
-            tk[adv] = (tk[adv] + calc_dt(tk[adv], m.cone_angle)).astype(f32)
-            adv = adv & (tk < target)
-        t[k] = tk
+        t[k] = advance_to_next_voxel(t[k], m.cone_angle, p, d[k], idir[k], res)
     return t, alive, pos, dt
 
 

@@ -7,7 +7,14 @@
 //                                  include/neural-graphics-primitives/common_device.cuh:31-61,260-307,470-472
 //   BoundingBox::ray_intersect / contains   include/neural-graphics-primitives/bounding_box.cuh:163-220
 //   NerfDataset::nerf_matrix_to_ngp         include/neural-graphics-primitives/nerf_loader.h:113-131
-// The hash grid, SH encoding, MLPs and the marching loop are __device__-only / .cu-local in the reference and
+//   calc_dt, mip_from_pos, mip_from_dt, cascaded_grid_idx_at, density_grid_occupied_at, distance_to_next_voxel,
+//   advance_to_next_voxel, warp_position / unwarp_position / warp_direction / warp_dt / unwarp_dt and the step-size
+//   constants                      src/testbed_nerf.cu:46-62,77-92,185-207,261-336,443-457 -- local to that .cu and
+//                                  mostly __device__: oracle/build_ref.py lifts these definitions at build time into a
+//                                  temporary include with __device__ widened to __host__ __device__ (bodies untouched)
+//   tcnn::morton3D / morton3D_invert / logistic    tiny-cuda-nn/include/tiny-cuda-nn/common_device.h:52-54,339-363
+//   tcnn fast_hash / grid_index    tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:82-116 (lifted the same way)
+// The hash-grid encoding, SH encoding, the fused MLPs and compositing are device kernels in the reference and
 // cannot run without a GPU; those parts of the oracle stay unpinned.
 // Built by oracle/build_ref.py into oracle/_ref/ngp_host (git-ignored).
 #include <neural-graphics-primitives/common.h>
@@ -15,12 +22,31 @@
 #include <neural-graphics-primitives/common_device.cuh>
 #include <neural-graphics-primitives/bounding_box.cuh>
 #include <neural-graphics-primitives/nerf_loader.h>
+#include <neural-graphics-primitives/nerf.h>
+#include <tiny-cuda-nn/common_device.h>
+#include <tiny-cuda-nn/encodings/grid.h>
 
 #include <cstdio>
 #include <vector>
 
-using namespace ngp;
 using namespace Eigen;
+using namespace tcnn;
+
+NGP_NAMESPACE_BEGIN
+#include "testbed_nerf_helpers.inc"
+NGP_NAMESPACE_END
+
+namespace lifted {   // tcnn's __device__ index functions, widened to __host__ __device__ (bodies untouched)
+#include "tcnn_grid_helpers.inc"
+}
+
+using namespace ngp;
+
+static uint32_t lcg_state = 12345u;
+static float rnd() {   // uniform in [0, 1)
+  lcg_state = lcg_state * 1664525u + 1013904223u;
+  return (float)(lcg_state >> 8) * (1.0f / 16777216.0f);
+}
 
 static void vec3(const char* key, const Vector3f& v, bool comma = true) {
   printf("\"%s\": [%.9g, %.9g, %.9g]%s", key, v.x(), v.y(), v.z(), comma ? ", " : "");
@@ -88,6 +114,80 @@ int main() {
         printf("\"t_box1\": [%.9g, %.9g], \"t_box4\": [%.9g, %.9g], \"in_box4\": %d}", t1.x(), t1.y(), t4.x(), t4.y(),
                (int)b4.contains(ray.o));
       }
-  printf("]}\n}\n");
+  printf("]},\n");
+  // ---- marching helpers (testbed_nerf.cu) ----
+  printf("\"constants\": {\"near\": %.9g, \"stepsize\": %.9g, \"min_cone_stepsize\": %.9g, \"max_cone_stepsize\": %.9g, \"cascades\": %u},\n",
+         NERF_RENDERING_NEAR_DISTANCE(), STEPSIZE(), MIN_CONE_STEPSIZE(), MAX_CONE_STEPSIZE(), NERF_CASCADES());
+  printf("\"calc_dt\": [");
+  {
+    const float ts[] = {0.05f, 0.3f, 0.5f, 1.f, 2.f, 5.f, 20.f, 200.f};
+    const float cones[] = {0.f, 1.f / 256.f};
+    for (int c = 0; c < 2; ++c)
+      for (int i = 0; i < 8; ++i)
+        printf("%s[%.9g, %.9g, %.9g]", (c || i) ? ", " : "", ts[i], cones[c], calc_dt(ts[i], cones[c]));
+  }
+  printf("],\n\"warp\": [");
+  {
+    const BoundingBox box(Vector3f(-1.5f, -1.5f, -1.5f), Vector3f(2.5f, 2.5f, 2.5f));
+    for (int i = 0; i < 12; ++i) {
+      const Vector3f p(rnd() * 4.f - 1.5f, rnd() * 4.f - 1.5f, rnd() * 4.f - 1.5f);
+      const float dt = MIN_CONE_STEPSIZE() * (1.f + rnd() * 100.f);
+      const Vector3f w = warp_position(p, box), u = unwarp_position(w, box), wd = warp_direction(p);
+      printf("%s{", i ? ", " : "");
+      vec3("p", p); vec3("warped", w); vec3("unwarped", u); vec3("warp_direction", wd);
+      printf("\"dt\": %.9g, \"warp_dt\": %.9g, \"unwarp_dt\": %.9g}", dt, warp_dt(dt), unwarp_dt(warp_dt(dt)));
+    }
+  }
+  printf("],\n\"morton\": [");
+  for (int i = 0; i < 24; ++i) {
+    const uint32_t x = (uint32_t)(rnd() * 128.f), y = (uint32_t)(rnd() * 128.f), z = (uint32_t)(rnd() * 128.f);
+    const uint32_t m = tcnn::morton3D(x, y, z);
+    printf("%s[%u, %u, %u, %u, %u]", i ? ", " : "", x, y, z, m, tcnn::morton3D_invert(m >> 1));
+  }
+  printf("],\n\"logistic\": [");
+  for (int i = 0; i < 9; ++i) printf("%s[%.9g, %.9g]", i ? ", " : "", -8.f + 2.f * i, tcnn::logistic(-8.f + 2.f * i));
+  printf("],\n\"grid_index\": [");
+  {
+    // the 16 levels of the base config at aabb_scale 1: resolution, entries of the level (hashmap_size argument)
+    const uint32_t ress[] = {16, 23, 31, 43, 59, 81, 112, 154, 213, 295, 407, 562, 777, 1073, 1483, 2048};
+    bool first_gi = true;
+    for (int lv = 0; lv < 16; ++lv) {
+      const uint64_t dense = (uint64_t)ress[lv] * ress[lv] * ress[lv];
+      const uint32_t size = (uint32_t)std::min<uint64_t>((dense + 7) / 8 * 8, 1u << 19);
+      for (int k = 0; k < 6; ++k) {
+        uint32_t pg[3] = {(uint32_t)(rnd() * ress[lv]), (uint32_t)(rnd() * ress[lv]), (uint32_t)(rnd() * ress[lv])};
+        if (k == 5) { pg[0] = ress[lv] - 1; pg[1] = ress[lv] - 1; pg[2] = ress[lv] - 1; }
+        printf("%s[%u, %u, %u, %u, %u, %u, %u]", first_gi ? "" : ", ", ress[lv], size, pg[0], pg[1], pg[2],
+               lifted::grid_index<3, 2>(GridType::Hash, 0, size, ress[lv], pg), lifted::fast_hash<3>(pg));
+        first_gi = false;
+      }
+    }
+  }
+  // occupancy bitfield with a reproducible pattern: byte i = (i * 2654435761) >> 13, 8 cascades
+  std::vector<uint8_t> bits((size_t)NERF_CASCADES() * 128 * 128 * 128 / 8);
+  for (size_t i = 0; i < bits.size(); ++i) bits[i] = (uint8_t)(((uint32_t)i * 2654435761u) >> 13);
+  printf("],\n\"march\": [\n");
+  for (int i = 0; i < 160; ++i) {
+    // positions across the cascades (cascade c covers [0.5 - 2^(c-1), 0.5 + 2^(c-1)])
+    const float half = 0.5f * (float)(1 << (i % 4));
+    const Vector3f pos(0.5f + (rnd() * 2.f - 1.f) * half, 0.5f + (rnd() * 2.f - 1.f) * half, 0.5f + (rnd() * 2.f - 1.f) * half);
+    Vector3f dir(rnd() * 2.f - 1.f, rnd() * 2.f - 1.f, rnd() * 2.f - 1.f);
+    if (i % 16 == 5) dir.x() = 0.f;              // axis-parallel rays: idir = inf
+    if (i % 16 == 11) { dir.y() = 0.f; dir.z() = 0.f; dir.x() = 1.f; }
+    dir = (1.0f / dir.norm()) * dir;
+    const Vector3f idir = dir.cwiseInverse();
+    const float t = 0.05f + rnd() * 6.f;
+    const float cone = (i & 1) ? 1.f / 256.f : 0.f;
+    const float dt = calc_dt(t, cone);
+    const int mp = mip_from_pos(pos), md = mip_from_dt(dt, pos);
+    const uint32_t res = NERF_GRIDSIZE() >> md;
+    printf("%s{", i ? ",\n" : "");
+    vec3("pos", pos); vec3("dir", dir);
+    printf("\"t\": %.9g, \"cone\": %.9g, \"dt\": %.9g, \"mip_from_pos\": %d, \"mip_from_dt\": %d, \"grid_idx\": %u, \"occupied\": %d, "
+           "\"res\": %u, \"dist\": %.9g, \"advance\": %.9g}",
+           t, cone, dt, mp, md, cascaded_grid_idx_at(pos, (uint32_t)md), (int)density_grid_occupied_at(pos, bits.data(), (uint32_t)md),
+           res, distance_to_next_voxel(pos, dir, idir, res), advance_to_next_voxel(t, cone, pos, dir, idir, res));
+  }
+  printf("]\n}\n");
   return 0;
 }

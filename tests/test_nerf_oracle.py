@@ -1,9 +1,11 @@
 """CPU: the NeRF-render oracle (oracle/nerf.py) against analytic cases and known answers.
 
 The reference renderer (pyngp) is not runnable here and ships no test vectors.  Its host-callable header code
-is: the jitter sequence, colour transfer, focal length, camera-matrix conversion, ray generation and box
-intersection of the oracle are pinned against it (bottom of this file, fixture tests/golden/nerf_host.json made by
-tests/golden/gen/make_nerf_goldens.py).  The device-only parts (hash grid, SH, MLPs, marching, compositing) are
+is, and so are the small marching / indexing functions once lifted out of their .cu / template headers: the jitter
+sequence, colour transfer, focal length, camera-matrix conversion, ray generation, box intersection, step sizes,
+cascade choice, occupancy lookup, empty-space stepping, Morton codes, hash and grid index of the oracle are pinned
+against them (bottom of this file, fixture tests/golden/nerf_host.json made by
+tests/golden/gen/make_nerf_goldens.py).  The device kernels (interpolation, SH, MLPs, compositing) are
 checked against properties of the published algorithm instead ("parity partly pinned"):
 hash-grid layout numbers, Morton codes, the (0,1)-sequence property of the Owen-scrambled Sobol jitter, occupancy
 pooling, empty space, and a closed-form transmittance for a zero network.
@@ -205,3 +207,78 @@ def test_rays_and_box_intersection_match_the_reference():
                 np.testing.assert_allclose([got[0][i], got[1][i]], ref, rtol=2e-6, atol=2e-6)
         assert bool(nerf._contains(boxes[1], o[i:i + 1])[0]) == bool(s['in_box4'])
     assert n_hit >= 100
+
+
+def test_marching_helpers_match_the_reference():
+    """calc_dt, mip_from_pos / mip_from_dt, cascaded_grid_idx_at, density_grid_occupied_at, distance_to_next_voxel,
+    advance_to_next_voxel, the warps, Morton codes and the constants: the reference's own definitions
+    (testbed_nerf.cu, lifted at build time by oracle/build_ref.py) evaluated on the host."""
+    c = HOST['constants']
+    assert f32(c['near']) == nerf.NEAR and f32(c['stepsize']) == nerf.STEPSIZE and c['cascades'] == nerf.CASCADES
+    assert f32(c['max_cone_stepsize']) == nerf.MAX_STEPSIZE
+    rec = np.array(HOST['calc_dt'], f32)
+    assert np.array_equal(nerf.calc_dt(rec[:, 0], rec[:, 1]), rec[:, 2])
+    mo = np.array(HOST['morton'], dtype=np.int64)
+    code = nerf.morton3d(mo[:, 0].astype(np.uint32), mo[:, 1].astype(np.uint32), mo[:, 2].astype(np.uint32))
+    assert np.array_equal(code.astype(np.int64), mo[:, 3])
+    assert np.array_equal(nerf.morton3d_invert(code >> np.uint32(1)).astype(np.int64), mo[:, 4])
+    lg = np.array(HOST['logistic'], f32)
+    np.testing.assert_allclose(f32(1) / (f32(1) + np.exp(-lg[:, 0])), lg[:, 1], rtol=3e-7)
+    # warps: position (relative to the aabb), direction, dt
+    box = np.array([[-1.5] * 3, [2.5] * 3], f32)
+    span = nerf.STEPSIZE * f32(1 << (nerf.CASCADES - 1)) - nerf.STEPSIZE
+    for w in HOST['warp']:
+        p = np.array(w['p'], f32)
+        np.testing.assert_allclose((p - box[0]) / (box[1] - box[0]), np.array(w['warped'], f32), rtol=0, atol=1e-7)
+        np.testing.assert_allclose((p + f32(1)) * f32(0.5), np.array(w['warp_direction'], f32), rtol=0, atol=1e-7)
+        wdt = (f32(w['dt']) - nerf.STEPSIZE) / span
+        assert abs(wdt - w['warp_dt']) <= 1e-6 * max(1.0, abs(w['warp_dt']))
+        assert abs((f32(w['warp_dt']) * span + nerf.STEPSIZE) - w['unwarp_dt']) <= 1e-7
+    # the empty-space walk
+    M = HOST['march']
+    pos = np.array([m['pos'] for m in M], f32)
+    d = np.array([m['dir'] for m in M], f32)
+    t = np.array([m['t'] for m in M], f32)
+    cone = np.array([m['cone'] for m in M], f32)
+    with np.errstate(divide='ignore'):
+        idir = (f32(1) / d).astype(f32)
+    dt = nerf.calc_dt(t, cone)
+    assert np.array_equal(dt, np.array([m['dt'] for m in M], f32))
+    assert np.array_equal(nerf.mip_from_pos(pos), np.array([m['mip_from_pos'] for m in M]))
+    mip = nerf.mip_from_dt(dt, pos)
+    assert np.array_equal(mip, np.array([m['mip_from_dt'] for m in M]))
+    assert len(set(mip.tolist())) >= 4
+    assert np.array_equal(nerf.cascaded_grid_idx(pos, mip), np.array([m['grid_idx'] for m in M]))
+    n_bytes = nerf.CASCADES * 128 ** 3 // 8
+    bits = ((np.arange(n_bytes, dtype=np.uint64) * np.uint64(2654435761) & np.uint64(0xFFFFFFFF)) >> np.uint64(13)).astype(np.uint8)
+    occ = nerf.occupied_bits(bits, pos, mip)
+    assert np.array_equal(occ, np.array([m['occupied'] for m in M]) > 0) and 0.2 < occ.mean() < 0.8
+    res = (128 >> mip).astype(np.int64)
+    assert np.array_equal(res, np.array([m['res'] for m in M]))
+    with np.errstate(invalid='ignore'):
+        dist = nerf.distance_to_next_voxel(pos, d, idir, res)
+    np.testing.assert_allclose(dist, np.array([m['dist'] for m in M], f32), rtol=1e-6, atol=1e-7)
+    for c0 in (0.0, 1.0 / 256.0):                   # cone angle is one scalar per model in the oracle
+        k = cone == f32(c0)
+        with np.errstate(invalid='ignore'):
+            adv = nerf.advance_to_next_voxel(t[k], f32(c0), pos[k], d[k], idir[k], res[k])
+        np.testing.assert_allclose(adv, np.array([m['advance'] for m in M], f32)[k], rtol=2e-7, atol=0)
+
+
+def test_hash_and_grid_index_match_tiny_cuda_nn():
+    """fast_hash / grid_index of tiny-cuda-nn (encodings/grid.h:82-116, lifted at build time) on every level of the base
+    configuration: dense levels, the first hashed level, and the finest one; corner vertex included."""
+    rec = np.array(HOST['grid_index'], dtype=np.uint64)
+    seen_dense = seen_hash = 0
+    for res, size, x, y, z, idx2, h in rec:
+        c = (np.array([x], np.uint64), np.array([y], np.uint64), np.array([z], np.uint64))
+        assert int(nerf.fast_hash(c)[0]) == int(h)
+        assert int(nerf.grid_index(c, int(res), int(size))[0]) * 2 == int(idx2)       # x N_FEATURES_PER_LEVEL, feature 0
+        dense = int(res) ** 3 <= int(size)
+        seen_dense += dense
+        seen_hash += not dense
+    assert seen_dense >= 12 and seen_hash >= 48
+    # and the layout the oracle derives has these level sizes
+    _, ress, offs = nerf.grid_layout(1)
+    assert [int(r) for r in ress] == sorted({int(r[0]) for r in rec})
+    assert [int(offs[i + 1] - offs[i]) for i in range(16)] == [int(rec[6 * i][1]) for i in range(16)]
