@@ -25,7 +25,11 @@ HELPERS = ['NERF_RENDERING_NEAR_DISTANCE', 'NERF_STEPS', 'NERF_CASCADES', 'SQRT3
            'density_grid_occupied_at', 'mip_from_pos', 'mip_from_dt']
 
 
-TCNN_HELPERS = ['fast_hash', 'grid_index']      # tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:82-116
+TCNN_HELPERS = ['fast_hash', 'grid_index', 'kernel_grid']   # tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:82-116,135-340
+TCNN_DEVICE_FUNS = ['identity_fun', 'identity_derivative', 'smoothstep', 'smoothstep_derivative']   # common_device.h:379-397
+TCNN_SH = ['kernel_sh']                                      # encodings/spherical_harmonics.h:46-150
+# The two kernels are lifted as ordinary host functions (`__global__` -> `__host__`); the harness supplies
+# threadIdx / blockIdx / blockDim as host variables through macros, so their bodies stay untouched as well.
 
 
 def lift_helpers(cu_path: str, names=None) -> str:
@@ -33,8 +37,11 @@ def lift_helpers(cu_path: str, names=None) -> str:
     lines = open(cu_path).read().split('\n')
     out = []
     for name in (names or HELPERS):
-        pat = re.compile(r'^(inline |static )?(constexpr )?(__host__ )?(__device__ )[\w:<>, &\*]*\b' + name + r'\(')
-        start = next(i for i, ln in enumerate(lines) if pat.match(ln))
+        pat = re.compile(r'^(inline |static )?(constexpr )?(__host__ )?(__device__ |__global__ )[\w:<>, &\*]*\b' + name + r'\(')
+        cands = [i for i, ln in enumerate(lines) if pat.match(ln)]
+        if name == 'pos_fract':            # three overloads: the (pos, pos_derivative, pos_grid) one is what kernel_grid calls
+            cands = [i for i in cands if 'pos_derivative' in lines[i] and 'pos_2nd_derivative' not in lines[i]]
+        start = cands[0]
         if lines[start - 1].startswith('template'):
             out.append(lines[start - 1])
         depth, i = 0, start
@@ -44,7 +51,9 @@ def lift_helpers(cu_path: str, names=None) -> str:
                 break
             i += 1
         body = lines[start:i + 1]
-        if '__host__' not in body[0]:
+        if '__global__' in body[0]:
+            body[0] = body[0].replace('__global__', '__host__', 1)
+        elif '__host__' not in body[0]:
             body[0] = body[0].replace('__device__', '__host__ __device__', 1)
         out.extend(body + [''])
     return '\n'.join(out)
@@ -72,7 +81,12 @@ def build(verbose: bool = True) -> str:
         f.write(lift_helpers(os.path.join(REF, 'src', 'testbed_nerf.cu')))
     lifted2 = os.path.join(tmp_inc, 'tcnn_grid_helpers.inc')
     with open(lifted2, 'w') as f:
-        f.write(lift_helpers(os.path.join(tcnn, 'include', 'tiny-cuda-nn', 'encodings', 'grid.h'), TCNN_HELPERS))
+        tinc = os.path.join(tcnn, 'include', 'tiny-cuda-nn')
+        f.write(lift_helpers(os.path.join(tinc, 'common_device.h'), TCNN_DEVICE_FUNS + ['pos_fract']))
+        f.write('\n')
+        f.write(lift_helpers(os.path.join(tinc, 'encodings', 'grid.h'), TCNN_HELPERS))
+        f.write('\n')
+        f.write(lift_helpers(os.path.join(tinc, 'encodings', 'spherical_harmonics.h'), TCNN_SH))
     cmd.insert(-3, f'-I{tmp_inc}')
     if verbose:
         print(' '.join(cmd), file=sys.stderr)

@@ -13,11 +13,12 @@ tests/golden/nerf_host.json and pin, in tests/test_nerf_oracle.py:
     and -- from definitions that build_ref.py lifts out of testbed_nerf.cu / tcnn's grid.h at build time, widening
     __device__ to __host__ __device__ without touching the bodies -- the step-size constants, calc_dt, mip_from_pos,
     mip_from_dt, cascaded_grid_idx (bit-exact), occupied_bits (bit-exact), distance_to_next_voxel,
-    advance_to_next_voxel, the position / direction / dt warps, morton3d, fast_hash and grid_index (bit-exact).
-UNPINNED (device kernels in the reference): the trilinear hash-grid interpolation around those indices, the SH
-encoding, the fused MLPs and the compositing loop: restated from the sources and checked against analytic cases
-(empty occupancy -> nothing rendered, zero network -> closed-form transmittance, constant table -> constant
-encoding).
+    advance_to_next_voxel, the position / direction / dt warps, morton3d, fast_hash and grid_index (bit-exact),
+    hash_encode (= tcnn kernel_grid run as a host loop: bit-exact given the same level scales; the scales themselves
+    agree to 2e-7, two of sixteen differ in the last bit between math libraries) and sh_encode (= kernel_sh).
+UNPINNED (cannot run without a GPU): the fused MLPs (wmma fragments) and the compositing kernel: restated from
+the sources and checked against analytic cases (empty occupancy -> nothing rendered, zero network -> closed-form
+transmittance).
 One deliberate numerical difference: tiny-cuda-nn's fully fused MLP accumulates in fp16 inside
 wmma fragments (fully_fused_mlp.cu:67-69); here, and in csrc/ptk_nerf.cu, products of fp16
 operands are accumulated in fp32 and rounded to fp16 once per layer.

@@ -14,8 +14,11 @@
 //                                  temporary include with __device__ widened to __host__ __device__ (bodies untouched)
 //   tcnn::morton3D / morton3D_invert / logistic    tiny-cuda-nn/include/tiny-cuda-nn/common_device.h:52-54,339-363
 //   tcnn fast_hash / grid_index    tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:82-116 (lifted the same way)
-// The hash-grid encoding, SH encoding, the fused MLPs and compositing are device kernels in the reference and
-// cannot run without a GPU; those parts of the oracle stay unpinned.
+//   tcnn kernel_grid (hash-grid forward: level scale, pos_fract, trilinear interpolation in fp16) and kernel_sh
+//                                  encodings/grid.h:135-340, encodings/spherical_harmonics.h:46-150, common_device.h:379-431:
+//                                  the __global__ kernels are lifted as host functions, thread indices via macros
+// The fused MLPs (wmma fragments) and the compositing kernel cannot run without a GPU; those parts of the oracle stay
+// unpinned.
 // Built by oracle/build_ref.py into oracle/_ref/ngp_host (git-ignored).
 #include <neural-graphics-primitives/common.h>
 #include <neural-graphics-primitives/random_val.cuh>
@@ -36,8 +39,37 @@ NGP_NAMESPACE_BEGIN
 #include "testbed_nerf_helpers.inc"
 NGP_NAMESPACE_END
 
-namespace lifted {   // tcnn's __device__ index functions, widened to __host__ __device__ (bodies untouched)
+// tcnn's __device__ index / interpolation functions widened to __host__ __device__, and its hash-grid and SH encoding
+// kernels as plain host functions (bodies untouched): renamed through macros so that they do not collide with the
+// originals that grid.h declares, with the CUDA thread indices supplied as host variables.
+namespace lifted {
+static uint3 h_tid = {0, 0, 0}, h_bid = {0, 0, 0};
+static dim3 h_bdim(1, 1, 1);
+#define threadIdx lifted::h_tid
+#define blockIdx lifted::h_bid
+#define blockDim lifted::h_bdim
+#define fast_hash lifted_fast_hash
+#define grid_index lifted_grid_index
+#define pos_fract lifted_pos_fract
+#define identity_fun lifted_identity_fun
+#define identity_derivative lifted_identity_derivative
+#define smoothstep lifted_smoothstep
+#define smoothstep_derivative lifted_smoothstep_derivative
+#define kernel_grid lifted_kernel_grid
+#define kernel_sh lifted_kernel_sh
 #include "tcnn_grid_helpers.inc"
+#undef threadIdx
+#undef blockIdx
+#undef blockDim
+#undef fast_hash
+#undef grid_index
+#undef pos_fract
+#undef identity_fun
+#undef identity_derivative
+#undef smoothstep
+#undef smoothstep_derivative
+#undef kernel_grid
+#undef kernel_sh
 }
 
 using namespace ngp;
@@ -158,10 +190,66 @@ int main() {
         uint32_t pg[3] = {(uint32_t)(rnd() * ress[lv]), (uint32_t)(rnd() * ress[lv]), (uint32_t)(rnd() * ress[lv])};
         if (k == 5) { pg[0] = ress[lv] - 1; pg[1] = ress[lv] - 1; pg[2] = ress[lv] - 1; }
         printf("%s[%u, %u, %u, %u, %u, %u, %u]", first_gi ? "" : ", ", ress[lv], size, pg[0], pg[1], pg[2],
-               lifted::grid_index<3, 2>(GridType::Hash, 0, size, ress[lv], pg), lifted::fast_hash<3>(pg));
+               lifted::lifted_grid_index<3, 2>(GridType::Hash, 0, size, ress[lv], pg), lifted::lifted_fast_hash<3>(pg));
         first_gi = false;
       }
     }
+  }
+  // ---- hash-grid and SH encodings: the reference kernels run as host loops ----
+  {
+    const float pls = std::exp(std::log(2048.f * 1.f / 16.f) / (16 - 1));      // testbed.cu:2243, aabb_scale 1
+    const float l2 = std::log2(pls);
+    GridOffsetTable table;
+    uint32_t off = 0;
+    printf("],\n\"encoding\": {\"log2_per_level_scale\": %.9g, \"levels\": [", l2);
+    for (uint32_t lv = 0; lv < 16; ++lv) {
+      const float scale = exp2f(lv * l2) * 16 - 1.0f;
+      const uint32_t res = (uint32_t)ceil(scale) + 1;
+      const uint64_t dense = (uint64_t)res * res * res;
+      const uint32_t size = (uint32_t)std::min<uint64_t>((dense + 7) / 8 * 8, 1u << 19);     // grid.h:898-930
+      table.data[lv] = off;
+      off += size;
+      printf("%s[%.9g, %u, %u]", lv ? ", " : "", scale, res, size);
+    }
+    table.data[16] = off;
+    table.size = 17;
+    // table values: a reproducible pattern in [-0.5, 0.5), exactly representable before the fp16 rounding
+    std::vector<__half> grid((size_t)off * 2);
+    for (size_t i = 0; i < grid.size(); ++i)
+      grid[i] = __float2half((float)((((uint32_t)i * 2654435761u) >> 16) & 0xFFFFu) / 65536.f - 0.5f);
+    const uint32_t n = 48;
+    std::vector<float> pts(n * 3), dirs(n * 3);
+    for (uint32_t i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) {
+        pts[i * 3 + k] = rnd();
+        dirs[i * 3 + k] = rnd();
+      }
+    pts[0] = pts[1] = pts[2] = 0.f;                               // corners and an exact vertex of level 0
+    pts[3] = pts[4] = pts[5] = 0.99999f;
+    pts[6] = 3.5f / 15.f; pts[7] = 4.5f / 15.f; pts[8] = 6.5f / 15.f;
+    std::vector<__half> enc((size_t)32 * n), sh((size_t)16 * n);
+    MatrixView<const float> pos_view(pts.data(), 1, 3), dir_view(dirs.data(), 1, 3);
+    MatrixView<__half> sh_view(sh.data(), 1, 16);
+    for (uint32_t i = 0; i < n; ++i) {
+      lifted::h_tid.x = i;
+      for (uint32_t lv = 0; lv < 16; ++lv) {
+        lifted::h_bid.y = lv;
+        lifted::lifted_kernel_grid<__half, 3, 2>(n, 32, table, 16, l2, 0.f, 1000.f, nullptr, InterpolationType::Linear,
+                                                 GridType::Hash, grid.data(), pos_view, enc.data(), nullptr);
+      }
+      lifted::h_bid.y = 0;
+      lifted::lifted_kernel_sh<__half>(n, 4, 0, dir_view, sh_view);
+    }
+    printf("], \"total_entries\": %u, \"samples\": [\n", off);
+    for (uint32_t i = 0; i < n; ++i) {
+      printf("%s{\"pos\": [%.9g, %.9g, %.9g], \"dir01\": [%.9g, %.9g, %.9g], \"enc\": [", i ? ",\n" : "", pts[i * 3], pts[i * 3 + 1],
+             pts[i * 3 + 2], dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2]);
+      for (int f = 0; f < 32; ++f) printf("%s%.9g", f ? ", " : "", __half2float(enc[i + (size_t)f * n]));
+      printf("], \"sh\": [");
+      for (int f = 0; f < 16; ++f) printf("%s%.9g", f ? ", " : "", __half2float(sh[(size_t)i * 16 + f]));
+      printf("]}");
+    }
+    printf("]},\n\"unused\": [");
   }
   // occupancy bitfield with a reproducible pattern: byte i = (i * 2654435761) >> 13, 8 cascades
   std::vector<uint8_t> bits((size_t)NERF_CASCADES() * 128 * 128 * 128 / 8);

@@ -3,9 +3,9 @@
 The reference renderer (pyngp) is not runnable here and ships no test vectors.  Its host-callable header code
 is, and so are the small marching / indexing functions once lifted out of their .cu / template headers: the jitter
 sequence, colour transfer, focal length, camera-matrix conversion, ray generation, box intersection, step sizes,
-cascade choice, occupancy lookup, empty-space stepping, Morton codes, hash and grid index of the oracle are pinned
-against them (bottom of this file, fixture tests/golden/nerf_host.json made by
-tests/golden/gen/make_nerf_goldens.py).  The device kernels (interpolation, SH, MLPs, compositing) are
+cascade choice, occupancy lookup, empty-space stepping, Morton codes, hash and grid index, and the hash-grid / SH
+encoding kernels (run as host loops) of the oracle are pinned against them (bottom of this file, fixture
+tests/golden/nerf_host.json made by tests/golden/gen/make_nerf_goldens.py).  The MLPs and the compositing loop are
 checked against properties of the published algorithm instead ("parity partly pinned"):
 hash-grid layout numbers, Morton codes, the (0,1)-sequence property of the Owen-scrambled Sobol jitter, occupancy
 pooling, empty space, and a closed-form transmittance for a zero network.
@@ -282,3 +282,39 @@ def test_hash_and_grid_index_match_tiny_cuda_nn():
     _, ress, offs = nerf.grid_layout(1)
     assert [int(r) for r in ress] == sorted({int(r[0]) for r in rec})
     assert [int(offs[i + 1] - offs[i]) for i in range(16)] == [int(rec[6 * i][1]) for i in range(16)]
+
+
+def test_hash_grid_and_sh_encodings_match_the_tiny_cuda_nn_kernels():
+    """kernel_grid (level scale, pos_fract, grid_index, trilinear interpolation accumulated in fp16) and kernel_sh of
+    tiny-cuda-nn, lifted as host functions by oracle/build_ref.py and run on a 6.1 M-entry table with a reproducible
+    pattern: the oracle's hash_encode / sh_encode must give the same fp16 values."""
+    E = HOST['encoding']
+    scales, ress, offs = nerf.grid_layout(1)
+    lv = np.array(E['levels'], dtype=np.float64)
+    np.testing.assert_allclose(scales, lv[:, 0].astype(f32), rtol=2e-7)
+    assert np.array_equal(ress, lv[:, 1].astype(np.int64)) and np.array_equal(np.diff(offs), lv[:, 2].astype(np.int64))
+    assert int(offs[-1]) == E['total_entries']
+    i = np.arange(2 * E['total_entries'], dtype=np.uint64)
+    pat = (((i * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)) >> np.uint64(16)) & np.uint64(0xFFFF)
+    grid = (pat.astype(f32) / f32(65536) - f32(0.5)).astype(np.float16).reshape(-1, 2)
+    sc = syn.nerf_scene(0, 1, zero_network=True)
+    bits = nerf.bitfield_from_density_grid(sc['density_grid'], sc['max_cascade'])
+    m = nerf.NerfModel(1, grid, sc['w_density'], sc['w_rgb'], bits)
+    S = E['samples']
+    pos = np.array([s['pos'] for s in S], f32)
+    ref = np.array([s['enc'] for s in S], f32)
+    # (a) with the oracle's own level scales: two of the 16 differ from the harness's in the last float bit (exp / log /
+    # exp2 come from different math libraries -- the GPU's exp2f is a third one), which moves a few values by one fp16 ulp
+    enc = nerf.hash_encode(m, pos).astype(f32)
+    assert np.abs(enc - ref).max() <= 5e-4 and (enc == ref).mean() > 0.95
+    # (b) with the harness's scales the interpolation must agree bit for bit: same vertices, same weights, same fp16
+    # accumulation order
+    m.layout = (lv[:, 0].astype(f32), m.layout[1], m.layout[2])
+    enc = nerf.hash_encode(m, pos).astype(f32)
+    assert np.array_equal(enc, ref)
+    assert np.abs(ref).max() > 0.3 and ref[:, 20:].std() > 0.05            # hashed levels carry signal too
+    d01 = np.array([s['dir01'] for s in S], f32)
+    sh = nerf.sh_encode(d01).astype(f32)
+    sh_ref = np.array([s['sh'] for s in S], f32)
+    assert sh.shape == sh_ref.shape == (len(S), 16)
+    assert np.abs(sh - sh_ref).max() <= 1e-3 and (sh == sh_ref).mean() > 0.97     # fp16 outputs, fma contraction differences
