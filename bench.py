@@ -416,7 +416,7 @@ def run_ours(args, rank, world, local_rank):
             cf = CpuFrame(seq, th)
             t0 = time.perf_counter()
             n_f = 0
-            while n_f < 2 and (n_f == 0 or time.perf_counter() - t0 < 15):
+            while n_f < 8 and (n_f == 0 or time.perf_counter() - t0 < 12):     # bounded sample: about 12-15 s of CPU work
                 cf.step(n_f)
                 n_f += 1
             dt = time.perf_counter() - t0
