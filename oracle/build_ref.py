@@ -22,7 +22,9 @@ REF = '/root/reference/instant-ngp'
 HELPERS = ['NERF_RENDERING_NEAR_DISTANCE', 'NERF_STEPS', 'NERF_CASCADES', 'SQRT3', 'STEPSIZE', 'MIN_CONE_STEPSIZE',
            'MAX_CONE_STEPSIZE', 'grid_mip_offset', 'calc_dt', 'distance_to_next_voxel', 'advance_to_next_voxel',
            'warp_position', 'unwarp_position', 'warp_direction', 'warp_dt', 'unwarp_dt', 'cascaded_grid_idx_at',
-           'density_grid_occupied_at', 'mip_from_pos', 'mip_from_dt']
+           'density_grid_occupied_at', 'mip_from_pos', 'mip_from_dt',
+           # compositing: the activations (all overloads) and the kernel itself, lifted as a host function
+           'network_to_rgb*', 'network_to_density', 'network_to_density_derivative', 'composite_kernel_nerf']
 
 
 TCNN_HELPERS = ['fast_hash', 'grid_index', 'kernel_grid']   # tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:82-116,135-340
@@ -37,11 +39,19 @@ def lift_helpers(cu_path: str, names=None) -> str:
     lines = open(cu_path).read().split('\n')
     out = []
     for name in (names or HELPERS):
+        every = name.endswith('*')
+        name = name.rstrip('*')
         pat = re.compile(r'^(inline |static )?(constexpr )?(__host__ )?(__device__ |__global__ )[\w:<>, &\*]*\b' + name + r'\(')
         cands = [i for i, ln in enumerate(lines) if pat.match(ln)]
         if name == 'pos_fract':            # three overloads: the (pos, pos_derivative, pos_grid) one is what kernel_grid calls
             cands = [i for i in cands if 'pos_derivative' in lines[i] and 'pos_2nd_derivative' not in lines[i]]
-        start = cands[0]
+        for start in (cands if every else cands[:1]):
+            out.extend(_one_definition(lines, start))
+    return '\n'.join(out)
+
+
+def _one_definition(lines, start):
+        out = []
         if lines[start - 1].startswith('template'):
             out.append(lines[start - 1])
         depth, i = 0, start
@@ -56,7 +66,7 @@ def lift_helpers(cu_path: str, names=None) -> str:
         elif '__host__' not in body[0]:
             body[0] = body[0].replace('__device__', '__host__ __device__', 1)
         out.extend(body + [''])
-    return '\n'.join(out)
+        return out
 
 
 def build(verbose: bool = True) -> str:

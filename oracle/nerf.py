@@ -15,10 +15,11 @@ tests/golden/nerf_host.json and pin, in tests/test_nerf_oracle.py:
     mip_from_dt, cascaded_grid_idx (bit-exact), occupied_bits (bit-exact), distance_to_next_voxel,
     advance_to_next_voxel, the position / direction / dt warps, morton3d, fast_hash and grid_index (bit-exact),
     hash_encode (= tcnn kernel_grid run as a host loop: bit-exact given the same level scales; the scales themselves
-    agree to 2e-7, two of sixteen differ in the last bit between math libraries) and sh_encode (= kernel_sh).
-UNPINNED (cannot run without a GPU): the fused MLPs (wmma fragments) and the compositing kernel: restated from
-the sources and checked against analytic cases (empty occupancy -> nothing rendered, zero network -> closed-form
-transmittance).
+    agree to 2e-7, two of sixteen differ in the last bit between math libraries), sh_encode (= kernel_sh) and
+    composite_sample (= the sample loop of composite_kernel_nerf with its activations, run as a host function).
+UNPINNED (cannot run without a GPU): the fused MLPs (wmma fragments) and the kernels that only glue these pieces
+together (ray init / compaction order, shade, accumulate, tonemap): restated from the sources and checked against
+analytic cases (empty occupancy -> nothing rendered, zero network -> closed-form transmittance).
 One deliberate numerical difference: tiny-cuda-nn's fully fused MLP accumulates in fp16 inside
 wmma fragments (fully_fused_mlp.cu:67-69); here, and in csrc/ptk_nerf.cu, products of fp16
 operands are accumulated in fp32 and rounded to fp16 once per layer.
@@ -453,6 +454,36 @@ def linear_to_srgb(x):
     return np.where(x < f32(0.0031308), f32(12.92) * x, f32(1.055) * np.power(np.maximum(x, 0), f32(0.41666)) - f32(0.055)).astype(f32)
 
 
+def composite_sample(rgba, maxw, dep, k, out, wpos, wdt, aabb, origin, cam, depth_scale, depth_mode: bool,
+                     min_transmittance) -> np.ndarray:
+    """One iteration of composite_kernel_nerf's sample loop (testbed_nerf.cu:797-954) for the rays `k`: `out` [n,4] raw
+    network outputs (rgb, density), `wpos` / `wdt` the warped position / step the network saw.  Updates rgba, maxw
+    (payload.max_weight) and dep in place and returns which of the rays terminated (alpha above 1 - min_transmittance;
+    their colour is then normalised by alpha).  Activations: logistic rgb, exponential density (network_to_rgb /
+    network_to_density, :209-259)."""
+    diag = aabb[1] - aabb[0]
+    cam_fwd = cam[:, 2]
+    upos = (aabb[0] + wpos * diag).astype(f32)                                      # unwarp_position
+    udt = (wdt * (STEPSIZE * f32(1 << (CASCADES - 1)) - STEPSIZE) + STEPSIZE).astype(f32)   # unwarp_dt
+    T = f32(1) - rgba[k, 3]
+    alpha = f32(1) - np.exp(-np.exp(out[:, 3]) * udt).astype(f32)
+    weight = (alpha * T).astype(f32)
+    if depth_mode:
+        val = _dot3(upos - origin, cam_fwd) * depth_scale
+        rgb = np.repeat(val[:, None], 3, 1)
+    else:
+        rgb = (f32(1) / (f32(1) + np.exp(-out[:, :3]))).astype(f32)                # Logistic
+    rgba[k, :3] += rgb * weight[:, None]
+    rgba[k, 3] += weight
+    better = weight > maxw[k]
+    maxw[k[better]] = weight[better]
+    dep[k[better]] = _dot3(upos[better] - cam[:, 3], cam_fwd)
+    done = rgba[k, 3] > f32(1.0 - min_transmittance)
+    kd = k[done]
+    rgba[kd] = rgba[kd] / rgba[kd, 3:4]
+    return done
+
+
 def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov_deg: float, spp: int = 8,
            depth_mode: bool = False, min_transmittance: float = 1e-7, fov_axis: int = 0,
            background=(1.0, 1.0, 1.0, 0.0)) -> Dict[str, np.ndarray]:
@@ -497,26 +528,9 @@ def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov
             wdt = ((dt[k] - STEPSIZE) / (STEPSIZE * f32(1 << (CASCADES - 1)) - STEPSIZE)).astype(f32)   # warp_dt
             out = network(m, wpos, ((d[k] + f32(1)) * f32(0.5)).astype(f32), want_rgb=not depth_mode).astype(f32)
             t[k] = (t[k] + dt[k]).astype(f32)
-            # composite_kernel_nerf
-            upos = (m.aabb[0] + wpos * diag).astype(f32)
-            udt = (wdt * (STEPSIZE * f32(1 << (CASCADES - 1)) - STEPSIZE) + STEPSIZE).astype(f32)
-            T = f32(1) - rgba[k, 3]
-            alpha = f32(1) - np.exp(-np.exp(out[:, 3]) * udt).astype(f32)
-            weight = (alpha * T).astype(f32)
-            if depth_mode:
-                val = _dot3(upos - o[k], cam_fwd) * depth_scale
-                rgb = np.repeat(val[:, None], 3, 1)
-            else:
-                rgb = (f32(1) / (f32(1) + np.exp(-out[:, :3]))).astype(f32)            # Logistic
-            rgba[k, :3] += rgb * weight[:, None]
-            rgba[k, 3] += weight
-            better = weight > maxw[k]
-            maxw[k[better]] = weight[better]
-            dep[k[better]] = _dot3(upos[better] - cam[:, 3], cam_fwd)
-            done = rgba[k, 3] > f32(1.0 - min_transmittance)
-            kd = k[done]
-            rgba[kd] = rgba[kd] / rgba[kd, 3:4]
-            alive[kd] = False
+            done = composite_sample(rgba, maxw, dep, k, out, wpos, wdt, m.aabb, o[k], cam, depth_scale, depth_mode,
+                                    min_transmittance)
+            alive[k[done]] = False
             steps += 1
         # compaction keeps finished rays only when alpha > 0.001 (:1771); shade_kernel_nerf
         hit = rgba[:, 3] > f32(0.001)

@@ -17,8 +17,9 @@
 //   tcnn kernel_grid (hash-grid forward: level scale, pos_fract, trilinear interpolation in fp16) and kernel_sh
 //                                  encodings/grid.h:135-340, encodings/spherical_harmonics.h:46-150, common_device.h:379-431:
 //                                  the __global__ kernels are lifted as host functions, thread indices via macros
-// The fused MLPs (wmma fragments) and the compositing kernel cannot run without a GPU; those parts of the oracle stay
-// unpinned.
+//   composite_kernel_nerf + network_to_rgb / network_to_density   src/testbed_nerf.cu:209-259,754-960 (lifted as a
+//                                  host function; __expf -> expf)
+// The fused MLPs (wmma fragments) cannot run without a GPU; that part of the oracle stays unpinned.
 // Built by oracle/build_ref.py into oracle/_ref/ngp_host (git-ignored).
 #include <neural-graphics-primitives/common.h>
 #include <neural-graphics-primitives/random_val.cuh>
@@ -35,16 +36,27 @@
 using namespace Eigen;
 using namespace tcnn;
 
+namespace lifted {   // CUDA thread indices for the kernels that run here as host functions
+static uint3 h_tid = {0, 0, 0}, h_bid = {0, 0, 0};
+static dim3 h_bdim(1, 1, 1);
+}
+
 NGP_NAMESPACE_BEGIN
+#define threadIdx lifted::h_tid
+#define blockIdx lifted::h_bid
+#define blockDim lifted::h_bdim
+#define __expf expf          // the fast-math intrinsic has no host version; expf is its exact counterpart
 #include "testbed_nerf_helpers.inc"
+#undef __expf
+#undef threadIdx
+#undef blockIdx
+#undef blockDim
 NGP_NAMESPACE_END
 
 // tcnn's __device__ index / interpolation functions widened to __host__ __device__, and its hash-grid and SH encoding
 // kernels as plain host functions (bodies untouched): renamed through macros so that they do not collide with the
 // originals that grid.h declares, with the CUDA thread indices supplied as host variables.
 namespace lifted {
-static uint3 h_tid = {0, 0, 0}, h_bid = {0, 0, 0};
-static dim3 h_bdim(1, 1, 1);
 #define threadIdx lifted::h_tid
 #define blockIdx lifted::h_bid
 #define blockDim lifted::h_bdim
@@ -250,6 +262,62 @@ int main() {
       printf("]}");
     }
     printf("]},\n\"unused\": [");
+  }
+  // ---- compositing: the reference kernel over R rays x up to 6 samples, Shade and Depth modes ----
+  printf("], \"composite\": [");
+  for (int mode = 0; mode < 2; ++mode) {
+    const uint32_t R = 24, S = 6;
+    const BoundingBox aabb(Vector3f::Constant(-0.5f), Vector3f::Constant(1.5f));
+    Matrix<float, 3, 4> cam;
+    cam << 0.9f, -0.1f, 0.3f, 0.4f, 0.05f, 0.95f, -0.2f, -0.7f, -0.3f, 0.2f, 0.9f, 0.6f;
+    std::vector<Array4f> rgba(R, Array4f::Zero());
+    std::vector<float> depth(R, 0.f);
+    std::vector<NerfPayload> pay(R);
+    std::vector<NerfCoordinate> coords((size_t)R * S, NerfCoordinate(Vector3f::Zero(), Vector3f::Zero(), 0.f));
+    std::vector<network_precision_t> out((size_t)4 * R * S);
+    printf("%s{\"depth_mode\": %d, \"aabb\": [-0.5, 1.5], \"depth_scale\": %.9g, \"min_transmittance\": 1e-7, \"camera\": [", mode ? ", " : "",
+           mode, 1.f / 0.33f);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) printf("%s%.9g", (r || c) ? ", " : "", cam(r, c));
+    printf("], \"rays\": [\n");
+    for (uint32_t i = 0; i < R; ++i) {
+      pay[i].origin = cam.col(3);
+      pay[i].dir = Vector3f(0.f, 0.f, 1.f);
+      pay[i].t = 0.f;
+      pay[i].max_weight = 0.f;
+      pay[i].idx = i;
+      pay[i].n_steps = (uint16_t)(1 + (i % S));
+      pay[i].alive = (i % 11) != 10;
+      // some rays start partly composited (a later compaction round)
+      if (i % 3 == 1) rgba[i] = Array4f(0.1f * rnd(), 0.1f * rnd(), 0.1f * rnd(), 0.3f * rnd());
+      printf("%s{\"n_steps\": %u, \"alive\": %d, \"rgba0\": [%.9g, %.9g, %.9g, %.9g], \"samples\": [", i ? ",\n" : "", (unsigned)pay[i].n_steps,
+             (int)pay[i].alive, rgba[i].x(), rgba[i].y(), rgba[i].z(), rgba[i].w());
+      for (uint32_t j = 0; j < S; ++j) {
+        const Vector3f wpos(rnd(), rnd(), rnd());
+        const float dt = MIN_CONE_STEPSIZE() * (1.f + 30.f * rnd());
+        NerfCoordinate& c = coords[i + (size_t)j * R];
+        c.pos.p = wpos;
+        c.dt = warp_dt(dt);
+        float raw[4] = {rnd() * 6.f - 3.f, rnd() * 6.f - 3.f, rnd() * 6.f - 3.f, (i % 4 == 3) ? 6.f + 6.f * rnd() : rnd() * 8.f - 2.f};
+        for (int k = 0; k < 4; ++k) {
+          out[i + (size_t)j * R + (size_t)k * R * S] = (network_precision_t)raw[k];
+          raw[k] = (float)out[i + (size_t)j * R + (size_t)k * R * S];
+        }
+        printf("%s[%.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g]", j ? ", " : "", wpos.x(), wpos.y(), wpos.z(), c.dt, raw[0], raw[1], raw[2], raw[3]);
+      }
+      printf("]}");
+    }
+    for (uint32_t i = 0; i < R; ++i) {
+      lifted::h_tid.x = i;
+      composite_kernel_nerf(R, R * S, 0, aabb, 0.f, 0, 0, nullptr, cam, Vector2f(100.f, 100.f), 1.f / 0.33f, rgba.data(), depth.data(),
+                            pay.data(), PitchedPtr<NerfCoordinate>(coords.data(), 1), out.data(), 16, S,
+                            mode ? ERenderMode::Depth : ERenderMode::Shade, nullptr, ENerfActivation::Logistic,
+                            ENerfActivation::Exponential, -1, 1e-7f);
+    }
+    printf("], \"result\": [\n");
+    for (uint32_t i = 0; i < R; ++i)
+      printf("%s[%.9g, %.9g, %.9g, %.9g, %.9g, %d, %u, %.9g]", i ? ", " : "", rgba[i].x(), rgba[i].y(), rgba[i].z(), rgba[i].w(), depth[i],
+             (int)pay[i].alive, (unsigned)pay[i].n_steps, pay[i].max_weight);
+    printf("]}");
   }
   // occupancy bitfield with a reproducible pattern: byte i = (i * 2654435761) >> 13, 8 cascades
   std::vector<uint8_t> bits((size_t)NERF_CASCADES() * 128 * 128 * 128 / 8);

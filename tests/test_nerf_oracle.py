@@ -4,9 +4,9 @@ The reference renderer (pyngp) is not runnable here and ships no test vectors.  
 is, and so are the small marching / indexing functions once lifted out of their .cu / template headers: the jitter
 sequence, colour transfer, focal length, camera-matrix conversion, ray generation, box intersection, step sizes,
 cascade choice, occupancy lookup, empty-space stepping, Morton codes, hash and grid index, and the hash-grid / SH
-encoding kernels (run as host loops) of the oracle are pinned against them (bottom of this file, fixture
-tests/golden/nerf_host.json made by tests/golden/gen/make_nerf_goldens.py).  The MLPs and the compositing loop are
-checked against properties of the published algorithm instead ("parity partly pinned"):
+encoding kernels and the compositing kernel (run as host loops) of the oracle are pinned against them (bottom of
+this file, fixture tests/golden/nerf_host.json made by tests/golden/gen/make_nerf_goldens.py).  The MLPs and the
+glue between the pieces are checked against properties of the published algorithm instead ("parity partly pinned"):
 hash-grid layout numbers, Morton codes, the (0,1)-sequence property of the Owen-scrambled Sobol jitter, occupancy
 pooling, empty space, and a closed-form transmittance for a zero network.
 """
@@ -318,3 +318,44 @@ def test_hash_grid_and_sh_encodings_match_the_tiny_cuda_nn_kernels():
     sh_ref = np.array([s['sh'] for s in S], f32)
     assert sh.shape == sh_ref.shape == (len(S), 16)
     assert np.abs(sh - sh_ref).max() <= 1e-3 and (sh == sh_ref).mean() > 0.97     # fp16 outputs, fma contraction differences
+
+
+def test_compositing_matches_the_reference_kernel():
+    """composite_kernel_nerf (lifted as a host function; __expf -> expf) over 24 rays x up to 6 samples, shade and
+    depth mode, with partly composited and dead rays: final rgba, depth, max weight, termination flag and step
+    count against oracle.composite_sample applied sample by sample."""
+    for C in HOST['composite']:
+        cam = np.array(C['camera'], f32).reshape(3, 4)
+        aabb = np.array([[C['aabb'][0]] * 3, [C['aabb'][1]] * 3], f32)
+        rays = C['rays']
+        n = len(rays)
+        rgba = np.array([r['rgba0'] for r in rays], f32)
+        maxw, dep = np.zeros(n, f32), np.zeros(n, f32)
+        alive = np.array([bool(r['alive']) for r in rays])
+        steps_done = np.zeros(n, np.int64)
+        terminated = np.zeros(n, bool)
+        origin = np.broadcast_to(cam[:, 3], (n, 3)).astype(f32)
+        for j in range(6):
+            k = np.nonzero(alive & np.array([j < r['n_steps'] for r in rays]))[0]
+            if k.size == 0:
+                continue
+            smp = np.array([rays[i]['samples'][j] for i in k], f32)
+            done = nerf.composite_sample(rgba, maxw, dep, k, smp[:, 4:8], smp[:, 0:3], smp[:, 3], aabb, origin[k], cam,
+                                         f32(C['depth_scale']), bool(C['depth_mode']), C['min_transmittance'])
+            steps_done[k] = j + 1
+            terminated[k[done]] = True
+            alive[k[done]] = False
+        ref = np.array(C['result'], dtype=np.float64)
+        live = np.array([bool(r['alive']) for r in rays])
+        np.testing.assert_allclose(rgba[live], ref[live, :4].astype(f32), rtol=2e-6, atol=2e-7)
+        np.testing.assert_allclose(dep[live], ref[live, 4].astype(f32), rtol=2e-6, atol=2e-7)
+        # alpha = 1 - exp(-sigma dt) cancels for thin samples: one ulp of exp (numpy vs libm) is 6e-8 absolute
+        np.testing.assert_allclose(maxw[live], ref[live, 7].astype(f32), rtol=2e-6, atol=3e-7)
+        # dead rays are untouched; a ray that broke out of the loop early is marked dead with j = index of the
+        # terminating sample (payload.n_steps = j + current_step, :957-960)
+        assert np.array_equal(rgba[~live], np.array([r['rgba0'] for r in rays], f32)[~live])
+        early = terminated & (steps_done < 6 + 1)
+        for i in np.nonzero(live)[0]:
+            if terminated[i]:
+                assert ref[i, 5] == 0 and int(ref[i, 6]) == steps_done[i] - 1
+        assert terminated.sum() >= 4 and (live & ~terminated).sum() >= 4 and early.any()
