@@ -24,7 +24,10 @@ HELPERS = ['NERF_RENDERING_NEAR_DISTANCE', 'NERF_STEPS', 'NERF_CASCADES', 'SQRT3
            'warp_position', 'unwarp_position', 'warp_direction', 'warp_dt', 'unwarp_dt', 'cascaded_grid_idx_at',
            'density_grid_occupied_at', 'mip_from_pos', 'mip_from_dt',
            # compositing: the activations (all overloads) and the kernel itself, lifted as a host function
-           'network_to_rgb*', 'network_to_density', 'network_to_density_derivative', 'composite_kernel_nerf']
+           'network_to_rgb*', 'network_to_density', 'network_to_density_derivative', 'composite_kernel_nerf',
+           # start of a ray and end of a sample pass: ray init, jittered first advance, shade
+           'calc_cone_angle', 'advance_pos_nerf', 'init_rays_with_payload_kernel_nerf', 'shade_kernel_nerf']
+RENDER_BUFFER_HELPERS = ['accumulate_kernel']            # src/render_buffer.cu:236-271
 
 
 TCNN_HELPERS = ['fast_hash', 'grid_index', 'kernel_grid']   # tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:82-116,135-340
@@ -89,6 +92,8 @@ def build(verbose: bool = True) -> str:
     lifted = os.path.join(tmp_inc, 'testbed_nerf_helpers.inc')
     with open(lifted, 'w') as f:
         f.write(lift_helpers(os.path.join(REF, 'src', 'testbed_nerf.cu')))
+        f.write('\n')
+        f.write(lift_helpers(os.path.join(REF, 'src', 'render_buffer.cu'), RENDER_BUFFER_HELPERS))
     lifted2 = os.path.join(tmp_inc, 'tcnn_grid_helpers.inc')
     with open(lifted2, 'w') as f:
         tinc = os.path.join(tcnn, 'include', 'tiny-cuda-nn')

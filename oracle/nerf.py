@@ -16,10 +16,12 @@ tests/golden/nerf_host.json and pin, in tests/test_nerf_oracle.py:
     advance_to_next_voxel, the position / direction / dt warps, morton3d, fast_hash and grid_index (bit-exact),
     hash_encode (= tcnn kernel_grid run as a host loop: bit-exact given the same level scales; the scales themselves
     agree to 2e-7, two of sixteen differ in the last bit between math libraries), sh_encode (= kernel_sh) and
-    composite_sample (= the sample loop of composite_kernel_nerf with its activations, run as a host function).
-UNPINNED (cannot run without a GPU): the fused MLPs (wmma fragments) and the kernels that only glue these pieces
-together (ray init / compaction order, shade, accumulate, tonemap): restated from the sources and checked against
-analytic cases (empty occupancy -> nothing rendered, zero network -> closed-form transmittance).
+    composite_sample (= the sample loop of composite_kernel_nerf with its activations, run as a host function),
+    first_advance (= init_rays_with_payload_kernel_nerf + advance_pos_nerf), shade and accumulate
+    (= shade_kernel_nerf, accumulate_kernel).
+UNPINNED (cannot run without a GPU, or writes to a CUDA surface): the fused MLPs (wmma fragments), the compaction
+threshold and the tonemap / background blend: restated from the sources and checked against analytic cases (empty
+occupancy -> nothing rendered, zero network -> closed-form transmittance).
 One deliberate numerical difference: tiny-cuda-nn's fully fused MLP accumulates in fp16 inside
 wmma fragments (fully_fused_mlp.cu:67-69); here, and in csrc/ptk_nerf.cu, products of fp16
 operands are accumulated in fp32 and rounded to fp16 once per layer.
@@ -484,6 +486,36 @@ def composite_sample(rgba, maxw, dep, k, out, wpos, wdt, aabb, origin, cam, dept
     return done
 
 
+def first_advance(m: NerfModel, o, d, idir, tmin, s: int):
+    """Start of every ray for sample pass `s`: init_rays_with_payload_kernel_nerf (:1864-1889: start at the box entry
+    or the near distance, + 1e-6; dead when that point is outside the render box) followed by advance_pos_nerf
+    (:606-657: jitter by a fraction of the step from the Sobol sequence seeded by the pixel, then skip empty space).
+    Returns (t_init, alive_init, t, alive)."""
+    n = o.shape[0]
+    t0 = (np.maximum(tmin, NEAR) + f32(1e-6)).astype(f32)
+    start = (o + d * t0[:, None]).astype(f32)
+    alive0 = _contains(m.render_aabb, start)
+    dt0 = calc_dt(t0, m.cone_angle)
+    pix = np.arange(n, dtype=np.uint64)
+    t = (t0 + ld_random_val(np.full(n, s, np.uint64), pix * np.uint64(786433)) * dt0).astype(f32)
+    t, alive, _, _ = _skip_empty(m, o, d, idir, t, alive0.copy())
+    return t0, alive0, t, alive
+
+
+def shade(rgba, dep, depth_mode: bool = False):
+    """shade_kernel_nerf (:1721-1754) into a cleared frame buffer: colours to linear (Shade mode), depth kept where
+    alpha > 0.2.  -> (frame [n,4], depth [n])."""
+    frame = rgba.astype(f32).copy()
+    if not depth_mode:
+        frame[:, :3] = srgb_to_linear(rgba[:, :3])
+    return frame, np.where(rgba[:, 3] > f32(0.2), dep, f32(0)).astype(f32)
+
+
+def accumulate(accum, frame, s: int):
+    """accumulate_kernel, linear colour space (render_buffer.cu:236-271): running mean over the sample passes."""
+    return ((accum * f32(s) + frame) / f32(s + 1)).astype(f32)
+
+
 def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov_deg: float, spp: int = 8,
            depth_mode: bool = False, min_transmittance: float = 1e-7, fov_axis: int = 0,
            background=(1.0, 1.0, 1.0, 0.0)) -> Dict[str, np.ndarray]:
@@ -507,13 +539,7 @@ def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov
     depth_out = np.zeros(n, f32)
     pix = np.arange(n, dtype=np.uint64)
     for s in range(spp):
-        t = (np.maximum(tmin, NEAR) + f32(1e-6)).astype(f32)
-        start = (o + d * t[:, None]).astype(f32)
-        alive = _contains(m.render_aabb, start)
-        # advance_pos_nerf: jitter the start by a fraction of the step, then skip empty space
-        dt0 = calc_dt(t, m.cone_angle)
-        t = (t + ld_random_val(np.full(n, s, np.uint64), pix * np.uint64(786433)) * dt0).astype(f32)
-        t, alive, _, _ = _skip_empty(m, o, d, idir, t, alive)
+        _, _, t, alive = first_advance(m, o, d, idir, tmin, s)
         rgba = np.zeros((n, 4), f32)
         dep = np.zeros(n, f32)
         maxw = np.zeros(n, f32)
@@ -532,15 +558,10 @@ def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov
                                     min_transmittance)
             alive[k[done]] = False
             steps += 1
-        # compaction keeps finished rays only when alpha > 0.001 (:1771); shade_kernel_nerf
+        # compaction keeps finished rays only when alpha > 0.001 (:1771)
         hit = rgba[:, 3] > f32(0.001)
-        frame = np.zeros((n, 4), f32)
-        frame[hit] = rgba[hit]
-        if not depth_mode:
-            frame[hit, :3] = srgb_to_linear(rgba[hit, :3])
-        dbuf = np.where(hit & (rgba[:, 3] > f32(0.2)), dep, f32(0))
-        # accumulate_kernel (linear colour space): running mean over samples
-        accum = ((accum * f32(s) + frame) / f32(s + 1)).astype(f32)
+        frame, dbuf = shade(np.where(hit[:, None], rgba, f32(0)), np.where(hit, dep, f32(0)), depth_mode)
+        accum = accumulate(accum, frame, s)
         depth_out = dbuf
     # tonemap_kernel: background (sRGB -> linear) weighted by (1 - alpha) * bg.alpha, exposure 0, identity curve
     bg = np.asarray(background, f32)

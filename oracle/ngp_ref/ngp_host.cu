@@ -19,6 +19,8 @@
 //                                  the __global__ kernels are lifted as host functions, thread indices via macros
 //   composite_kernel_nerf + network_to_rgb / network_to_density   src/testbed_nerf.cu:209-259,754-960 (lifted as a
 //                                  host function; __expf -> expf)
+//   init_rays_with_payload_kernel_nerf, advance_pos_nerf, shade_kernel_nerf   src/testbed_nerf.cu:606-657,1721-1754,
+//                                  1781-1890; accumulate_kernel   src/render_buffer.cu:236-271 (same lifting)
 // The fused MLPs (wmma fragments) cannot run without a GPU; that part of the oracle stays unpinned.
 // Built by oracle/build_ref.py into oracle/_ref/ngp_host (git-ignored).
 #include <neural-graphics-primitives/common.h>
@@ -27,6 +29,7 @@
 #include <neural-graphics-primitives/bounding_box.cuh>
 #include <neural-graphics-primitives/nerf_loader.h>
 #include <neural-graphics-primitives/nerf.h>
+#include <neural-graphics-primitives/envmap.cuh>
 #include <tiny-cuda-nn/common_device.h>
 #include <tiny-cuda-nn/encodings/grid.h>
 
@@ -42,11 +45,16 @@ static dim3 h_bdim(1, 1, 1);
 }
 
 NGP_NAMESPACE_BEGIN
+// read_envmap is __device__-only; the ray-init kernel only calls it when an environment map is given (never here)
+template <typename T>
+Eigen::Array4f host_read_envmap(const T*, const Eigen::Vector2i, const Eigen::Vector3f&) { return Eigen::Array4f::Zero(); }
 #define threadIdx lifted::h_tid
 #define blockIdx lifted::h_bid
 #define blockDim lifted::h_bdim
 #define __expf expf          // the fast-math intrinsic has no host version; expf is its exact counterpart
+#define read_envmap host_read_envmap
 #include "testbed_nerf_helpers.inc"
+#undef read_envmap
 #undef __expf
 #undef threadIdx
 #undef blockIdx
@@ -322,6 +330,81 @@ int main() {
   // occupancy bitfield with a reproducible pattern: byte i = (i * 2654435761) >> 13, 8 cascades
   std::vector<uint8_t> bits((size_t)NERF_CASCADES() * 128 * 128 * 128 / 8);
   for (size_t i = 0; i < bits.size(); ++i) bits[i] = (uint8_t)(((uint32_t)i * 2654435761u) >> 13);
+  // ---- start of a ray: init kernel + jittered first advance over that occupancy pattern (two sample indices) ----
+  printf("], \"ray_start\": {");
+  {
+    const Vector2i res(16, 10);
+    const float fov = 40.f;
+    const float f = fov_to_focal_length(1, fov) * (float)res.x();
+    Matrix<float, 3, 4> cam;            // camera outside the unit cube, looking at its centre (NGP convention)
+    cam << 0.948683f, -0.094916f, 0.301511f, -0.4f,
+           0.f,        0.953463f, 0.301511f, -0.4f,
+          -0.316228f, -0.284747f, 0.904534f, -2.2f;
+    const BoundingBox box(Vector3f::Constant(0.f), Vector3f::Constant(1.f));
+    printf("\"width\": %d, \"height\": %d, \"fov\": %.9g, \"camera\": [", res.x(), res.y(), fov);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) printf("%s%.9g", (r || c) ? ", " : "", cam(r, c));
+    printf("], \"passes\": [");
+    for (uint32_t spp = 0; spp < 2; ++spp) {
+      const uint32_t n = (uint32_t)(res.x() * res.y());
+      std::vector<NerfPayload> pay(n);
+      std::vector<Array4f> fb(n, Array4f::Zero());
+      std::vector<float> db(n, 0.f);
+      for (int y = 0; y < res.y(); ++y)
+        for (int x = 0; x < res.x(); ++x) {
+          lifted::h_tid.x = (uint32_t)x; lifted::h_tid.y = (uint32_t)y;
+          init_rays_with_payload_kernel_nerf(spp, pay.data(), res, Vector2f(f, f), cam, cam, Vector4f::Zero(), Vector2f(0.5f, 0.5f),
+                                             Vector3f(0.f, 0.f, 1.f), true, box, Matrix3f::Identity(), 1.0f, 0.0f, CameraDistortion{}, nullptr,
+                                             Vector2i::Zero(), fb.data(), db.data(), nullptr, Vector2i::Zero(), ERenderMode::Shade);
+        }
+      lifted::h_tid.y = 0;
+      std::vector<float> t_init(n);
+      std::vector<int> alive_init(n);
+      for (uint32_t i = 0; i < n; ++i) { t_init[i] = pay[i].alive ? pay[i].t : 0.f; alive_init[i] = pay[i].alive; }
+      for (uint32_t i = 0; i < n; ++i) {
+        lifted::h_tid.x = i;
+        advance_pos_nerf(n, box, Matrix3f::Identity(), cam.col(2), Vector2f(f, f), spp, pay.data(), bits.data(), 0, 0.f);
+      }
+      printf("%s[", spp ? ", " : "");
+      for (uint32_t i = 0; i < n; ++i)
+        printf("%s[%d, %.9g, %d, %.9g]", i ? ", " : "", alive_init[i], t_init[i], (int)pay[i].alive, pay[i].alive ? pay[i].t : 0.f);
+      printf("]");
+    }
+    printf("]},\n");
+  }
+  // ---- end of a sample pass: shade (sRGB -> linear into the frame buffer) and the running mean over samples ----
+  {
+    const uint32_t n = 12;
+    std::vector<Array4f> rgba(n), fb(n, Array4f::Zero()), acc(n, Array4f::Zero());
+    std::vector<float> dep(n), dbuf(n, 0.f);
+    std::vector<NerfPayload> pay(n);
+    printf("\"shade\": {\"passes\": [");
+    for (uint32_t spp = 0; spp < 3; ++spp) {
+      for (uint32_t i = 0; i < n; ++i) {
+        const float a = (i % 4 == 0) ? 0.1f * rnd() : (i % 4 == 1 ? 1.0f : rnd());
+        rgba[i] = Array4f(rnd() * a, rnd() * a, rnd() * a, a);
+        dep[i] = 1.f + rnd();
+        pay[i].idx = n - 1 - i;                                  // scattered write through payload.idx
+        fb[i] = Array4f::Zero();
+        dbuf[i] = 0.f;
+      }
+      printf("%s{\"rgba\": [", spp ? ", " : "");
+      for (uint32_t i = 0; i < n; ++i) printf("%s[%.9g, %.9g, %.9g, %.9g, %.9g]", i ? ", " : "", rgba[i].x(), rgba[i].y(), rgba[i].z(), rgba[i].w(), dep[i]);
+      for (uint32_t i = 0; i < n; ++i) {
+        lifted::h_tid.x = i;
+        shade_kernel_nerf(n, rgba.data(), dep.data(), pay.data(), ERenderMode::Shade, false, fb.data(), dbuf.data());
+      }
+      for (uint32_t i = 0; i < n; ++i) {
+        lifted::h_tid.x = i; lifted::h_tid.y = 0;
+        accumulate_kernel(Vector2i((int)n, 1), fb.data(), acc.data(), (float)spp, EColorSpace::Linear);
+      }
+      printf("], \"frame\": [");
+      for (uint32_t i = 0; i < n; ++i) printf("%s[%.9g, %.9g, %.9g, %.9g, %.9g]", i ? ", " : "", fb[i].x(), fb[i].y(), fb[i].z(), fb[i].w(), dbuf[i]);
+      printf("], \"accumulated\": [");
+      for (uint32_t i = 0; i < n; ++i) printf("%s[%.9g, %.9g, %.9g, %.9g]", i ? ", " : "", acc[i].x(), acc[i].y(), acc[i].z(), acc[i].w());
+      printf("]}");
+    }
+    printf("]},\n\"unused2\": [");
+  }
   printf("],\n\"march\": [\n");
   for (int i = 0; i < 160; ++i) {
     // positions across the cascades (cascade c covers [0.5 - 2^(c-1), 0.5 + 2^(c-1)])

@@ -4,9 +4,10 @@ The reference renderer (pyngp) is not runnable here and ships no test vectors.  
 is, and so are the small marching / indexing functions once lifted out of their .cu / template headers: the jitter
 sequence, colour transfer, focal length, camera-matrix conversion, ray generation, box intersection, step sizes,
 cascade choice, occupancy lookup, empty-space stepping, Morton codes, hash and grid index, and the hash-grid / SH
-encoding kernels and the compositing kernel (run as host loops) of the oracle are pinned against them (bottom of
-this file, fixture tests/golden/nerf_host.json made by tests/golden/gen/make_nerf_goldens.py).  The MLPs and the
-glue between the pieces are checked against properties of the published algorithm instead ("parity partly pinned"):
+encoding kernels, and the ray-init / first-advance / compositing / shade / accumulate kernels (run as host loops) of
+the oracle are pinned against them (bottom of this file, fixture tests/golden/nerf_host.json made by
+tests/golden/gen/make_nerf_goldens.py).  The MLPs, compaction and tonemap are checked against properties of the
+published algorithm instead ("parity partly pinned"):
 hash-grid layout numbers, Morton codes, the (0,1)-sequence property of the Owen-scrambled Sobol jitter, occupancy
 pooling, empty space, and a closed-form transmittance for a zero network.
 """
@@ -359,3 +360,43 @@ def test_compositing_matches_the_reference_kernel():
             if terminated[i]:
                 assert ref[i, 5] == 0 and int(ref[i, 6]) == steps_done[i] - 1
         assert terminated.sum() >= 4 and (live & ~terminated).sum() >= 4 and early.any()
+
+
+def test_ray_start_matches_the_reference_kernels():
+    """init_rays_with_payload_kernel_nerf + advance_pos_nerf (lifted as host functions) on a 16x10 view of the unit cube
+    filled with the reproducible occupancy pattern, sample passes 0 and 1: start distance, liveness after the box test,
+    and the jittered, empty-space-skipped first sample distance of oracle.first_advance."""
+    R = HOST['ray_start']
+    cam = np.array(R['camera'], f32).reshape(3, 4)
+    o, d = nerf.pixel_rays(cam, R['width'], R['height'], R['fov'])
+    with np.errstate(divide='ignore'):
+        idir = (f32(1) / d).astype(f32)
+    n_bytes = nerf.CASCADES * 128 ** 3 // 8
+    bits = ((np.arange(n_bytes, dtype=np.uint64) * np.uint64(2654435761) & np.uint64(0xFFFFFFFF)) >> np.uint64(13)).astype(np.uint8)
+    sc = syn.nerf_scene(0, 1, zero_network=True)
+    m = nerf.NerfModel(1, sc['grid'], sc['w_density'], sc['w_rgb'], bits)
+    assert m.cone_angle == 0 and np.array_equal(m.render_aabb, np.array([[0] * 3, [1] * 3], f32))
+    tmin, _ = nerf.ray_box(m.render_aabb, o, d)
+    for s, rec in enumerate(R['passes']):
+        rec = np.array(rec, dtype=np.float64)
+        t0, alive0, t, alive = nerf.first_advance(m, o, d, idir, tmin, s)
+        assert np.array_equal(alive0, rec[:, 0] > 0) and 0.3 < alive0.mean() < 0.7
+        np.testing.assert_allclose(t0[alive0], rec[alive0, 1].astype(f32), rtol=3e-7)
+        assert np.array_equal(alive, rec[:, 2] > 0)
+        np.testing.assert_allclose(t[alive], rec[alive, 3].astype(f32), rtol=5e-7)
+        assert (t[alive] > t0[alive]).mean() > 0.9                  # the jitter / skipping moved them
+    assert not np.array_equal(np.array(R['passes'][0])[:, 3], np.array(R['passes'][1])[:, 3])
+
+
+def test_shade_and_accumulate_match_the_reference_kernels():
+    """shade_kernel_nerf (scattered through payload.idx, sRGB -> linear, depth above alpha 0.2) and accumulate_kernel
+    (running mean, linear colour space) over three sample passes."""
+    accum = np.zeros((12, 4), f32)
+    for s, P in enumerate(HOST['shade']['passes']):
+        rec = np.array(P['rgba'], f32)
+        frame, dbuf = nerf.shade(rec[:, :4], rec[:, 4])
+        ref = np.array(P['frame'], f32)[::-1]                        # payload.idx = n - 1 - i in the harness
+        np.testing.assert_allclose(frame, ref[:, :4], rtol=3e-7, atol=1e-9)
+        assert np.array_equal(dbuf, ref[:, 4]) and (dbuf == 0).any() and (dbuf > 0).any()
+        accum = nerf.accumulate(accum[::-1], frame, s)[::-1]          # the buffers are indexed by pixel = n - 1 - i
+        np.testing.assert_allclose(accum, np.array(P['accumulated'], f32), rtol=5e-7, atol=1e-9)
