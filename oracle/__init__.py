@@ -22,7 +22,7 @@ its host-callable header code is compiled in place (oracle/build_ref.py ->
 oracle/_ref/ngp_host) and pins the jitter, colour transfer, camera conversion,
 ray generation, box test, step sizes, cascade / cell / table indices, occupancy
 lookup, empty-space stepping, hash-grid and SH encodings, ray start, the
-compositing loop, shade and accumulate of oracle/nerf.py
-(tests/golden/nerf_host.json); the MLPs, the compaction threshold and the
-tonemap of that row stay "parity unpinned".
+compositing loop, shade, accumulate, compaction and tonemap of oracle/nerf.py
+(tests/golden/nerf_host.json); the fused MLPs and the order in which render()
+combines the pieces stay "parity unpinned".
 """

@@ -26,8 +26,9 @@ HELPERS = ['NERF_RENDERING_NEAR_DISTANCE', 'NERF_STEPS', 'NERF_CASCADES', 'SQRT3
            # compositing: the activations (all overloads) and the kernel itself, lifted as a host function
            'network_to_rgb*', 'network_to_density', 'network_to_density_derivative', 'composite_kernel_nerf',
            # start of a ray and end of a sample pass: ray init, jittered first advance, shade
-           'calc_cone_angle', 'advance_pos_nerf', 'init_rays_with_payload_kernel_nerf', 'shade_kernel_nerf']
-RENDER_BUFFER_HELPERS = ['accumulate_kernel']            # src/render_buffer.cu:236-271
+           'calc_cone_angle', 'advance_pos_nerf', 'init_rays_with_payload_kernel_nerf', 'shade_kernel_nerf',
+           'compact_kernel_nerf']
+RENDER_BUFFER_HELPERS = ['accumulate_kernel', 'tonemap*', 'tonemap_kernel']   # src/render_buffer.cu:236-345,542-569
 
 
 TCNN_HELPERS = ['fast_hash', 'grid_index', 'kernel_grid']   # tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:82-116,135-340

@@ -17,11 +17,11 @@ tests/golden/nerf_host.json and pin, in tests/test_nerf_oracle.py:
     hash_encode (= tcnn kernel_grid run as a host loop: bit-exact given the same level scales; the scales themselves
     agree to 2e-7, two of sixteen differ in the last bit between math libraries), sh_encode (= kernel_sh) and
     composite_sample (= the sample loop of composite_kernel_nerf with its activations, run as a host function),
-    first_advance (= init_rays_with_payload_kernel_nerf + advance_pos_nerf), shade and accumulate
-    (= shade_kernel_nerf, accumulate_kernel).
-UNPINNED (cannot run without a GPU, or writes to a CUDA surface): the fused MLPs (wmma fragments), the compaction
-threshold and the tonemap / background blend: restated from the sources and checked against analytic cases (empty
-occupancy -> nothing rendered, zero network -> closed-form transmittance).
+    first_advance (= init_rays_with_payload_kernel_nerf + advance_pos_nerf), shade, accumulate, the compaction
+    threshold and tonemap (= shade_kernel_nerf, accumulate_kernel, compact_kernel_nerf, tonemap_kernel).
+UNPINNED: the fused MLPs (wmma fragments, no host form) and the ORDER in which render() strings the pinned pieces
+together (restated from render_nerf / NerfTracer, testbed_nerf.cu:2035-2330); checked against analytic cases
+(empty occupancy -> nothing rendered, zero network -> closed-form transmittance).
 One deliberate numerical difference: tiny-cuda-nn's fully fused MLP accumulates in fp16 inside
 wmma fragments (fully_fused_mlp.cu:67-69); here, and in csrc/ptk_nerf.cu, products of fp16
 operands are accumulated in fp32 and rounded to fp16 once per layer.
@@ -516,6 +516,20 @@ def accumulate(accum, frame, s: int):
     return ((accum * f32(s) + frame) / f32(s + 1)).astype(f32)
 
 
+COMPACTION_MIN_ALPHA = f32(0.001)      # compact_kernel_nerf (:1773): finished rays below this never reach the frame
+
+
+def tonemap(accum, background=(1.0, 1.0, 1.0, 0.0)):
+    """tonemap_kernel (render_buffer.cu:542-569) for linear in / linear out, exposure 0, identity curve, no clamp: the
+    background (given in sRGB) is blended in behind, weighted by (1 - alpha) * background alpha."""
+    bg = np.asarray(background, f32)
+    w = (f32(1) - accum[:, 3]) * bg[3]
+    outp = accum.astype(f32).copy()
+    outp[:, :3] += srgb_to_linear(bg[:3])[None] * w[:, None]
+    outp[:, 3] += w
+    return outp
+
+
 def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov_deg: float, spp: int = 8,
            depth_mode: bool = False, min_transmittance: float = 1e-7, fov_axis: int = 0,
            background=(1.0, 1.0, 1.0, 0.0)) -> Dict[str, np.ndarray]:
@@ -559,16 +573,11 @@ def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov
             alive[k[done]] = False
             steps += 1
         # compaction keeps finished rays only when alpha > 0.001 (:1771)
-        hit = rgba[:, 3] > f32(0.001)
+        hit = rgba[:, 3] > COMPACTION_MIN_ALPHA
         frame, dbuf = shade(np.where(hit[:, None], rgba, f32(0)), np.where(hit, dep, f32(0)), depth_mode)
         accum = accumulate(accum, frame, s)
         depth_out = dbuf
-    # tonemap_kernel: background (sRGB -> linear) weighted by (1 - alpha) * bg.alpha, exposure 0, identity curve
-    bg = np.asarray(background, f32)
-    w = (f32(1) - accum[:, 3]) * bg[3]
-    outp = accum.copy()
-    outp[:, :3] += srgb_to_linear(bg[:3])[None] * w[:, None]
-    outp[:, 3] += w
+    outp = tonemap(accum, background)
     return dict(rgba=outp.reshape(height, width, 4), depth=depth_out.reshape(height, width))
 
 

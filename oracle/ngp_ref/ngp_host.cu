@@ -21,6 +21,8 @@
 //                                  host function; __expf -> expf)
 //   init_rays_with_payload_kernel_nerf, advance_pos_nerf, shade_kernel_nerf   src/testbed_nerf.cu:606-657,1721-1754,
 //                                  1781-1890; accumulate_kernel   src/render_buffer.cu:236-271 (same lifting)
+//   compact_kernel_nerf (atomicAdd -> a host counter)   src/testbed_nerf.cu:1756-1779; tonemap + tonemap_kernel
+//                                  (surf2Dwrite -> a host array)   src/render_buffer.cu:273-345,542-569
 // The fused MLPs (wmma fragments) cannot run without a GPU; that part of the oracle stays unpinned.
 // Built by oracle/build_ref.py into oracle/_ref/ngp_host (git-ignored).
 #include <neural-graphics-primitives/common.h>
@@ -36,12 +38,18 @@
 #include <cstdio>
 #include <vector>
 
+#include <vector_types.h>
+
 using namespace Eigen;
 using namespace tcnn;
 
 namespace lifted {   // CUDA thread indices for the kernels that run here as host functions
 static uint3 h_tid = {0, 0, 0}, h_bid = {0, 0, 0};
 static dim3 h_bdim(1, 1, 1);
+// stand-ins for the two device-only facilities the lifted kernels touch: a surface write and an atomic counter
+static std::vector<float4> host_surface;
+static int host_surface_w = 0;
+static uint32_t host_atomic_add(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p += v; return o; }
 }
 
 NGP_NAMESPACE_BEGIN
@@ -53,7 +61,11 @@ Eigen::Array4f host_read_envmap(const T*, const Eigen::Vector2i, const Eigen::Ve
 #define blockDim lifted::h_bdim
 #define __expf expf          // the fast-math intrinsic has no host version; expf is its exact counterpart
 #define read_envmap host_read_envmap
+#define atomicAdd lifted::host_atomic_add
+#define surf2Dwrite(v, s, xb, y) (lifted::host_surface[(size_t)(y) * lifted::host_surface_w + (xb) / sizeof(float4)] = (v))
 #include "testbed_nerf_helpers.inc"
+#undef surf2Dwrite
+#undef atomicAdd
 #undef read_envmap
 #undef __expf
 #undef threadIdx
@@ -403,7 +415,55 @@ int main() {
       for (uint32_t i = 0; i < n; ++i) printf("%s[%.9g, %.9g, %.9g, %.9g]", i ? ", " : "", acc[i].x(), acc[i].y(), acc[i].z(), acc[i].w());
       printf("]}");
     }
-    printf("]},\n\"unused2\": [");
+    printf("]},\n");
+  }
+  // ---- compaction (which finished rays reach the frame) and tonemap (background blend, exposure 0, identity curve) ----
+  {
+    const uint32_t n = 16;
+    std::vector<Array4f> src(n), dst(n), fin(n);
+    std::vector<float> sd(n, 1.f), dd(n), fd(n);
+    std::vector<NerfPayload> sp(n), dp(n), fp(n);
+    uint32_t counter = 0, final_counter = 0;
+    printf("\"compaction\": {\"rays\": [");
+    for (uint32_t i = 0; i < n; ++i) {
+      const float a = (i % 4 == 0) ? 0.0005f + 0.001f * rnd() : rnd();
+      src[i] = Array4f(a, a, a, (i == 5) ? 0.001f : a);
+      sp[i].alive = (i % 5 == 2);
+      sp[i].idx = i;
+      printf("%s[%d, %.9g]", i ? ", " : "", (int)sp[i].alive, src[i].w());
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+      lifted::h_tid.x = i;
+      compact_kernel_nerf(n, src.data(), sd.data(), sp.data(), dst.data(), dd.data(), dp.data(), fin.data(), fd.data(), fp.data(), &counter,
+                          &final_counter);
+    }
+    printf("], \"still_alive\": [");
+    for (uint32_t i = 0; i < counter; ++i) printf("%s%u", i ? ", " : "", dp[i].idx);
+    printf("], \"final\": [");
+    for (uint32_t i = 0; i < final_counter; ++i) printf("%s%u", i ? ", " : "", fp[i].idx);
+    printf("]},\n\"tonemap\": [");
+    const Array4f bgs[2] = {Array4f(255.f, 255.f, 255.f, 0.f), Array4f(0.2f, 0.5f, 0.8f, 1.0f)};     // pixtrack's default; an opaque one
+    for (int b = 0; b < 2; ++b) {
+      std::vector<Array4f> acc(n);
+      for (uint32_t i = 0; i < n; ++i) {
+        const float a = (i % 3 == 0) ? 1.f : rnd();
+        acc[i] = Array4f(rnd() * a, rnd() * a, 3.f * rnd() * a, a);
+      }
+      lifted::host_surface.assign(n, float4{0, 0, 0, 0});
+      lifted::host_surface_w = (int)n;
+      lifted::h_tid.y = 0;
+      for (uint32_t i = 0; i < n; ++i) {
+        lifted::h_tid.x = i;
+        tonemap_kernel(Vector2i((int)n, 1), 0.0f, bgs[b], acc.data(), EColorSpace::Linear, EColorSpace::Linear, ETonemapCurve::Identity, false, 0);
+      }
+      printf("%s{\"background\": [%.9g, %.9g, %.9g, %.9g], \"accumulated\": [", b ? ", " : "", bgs[b].x(), bgs[b].y(), bgs[b].z(), bgs[b].w());
+      for (uint32_t i = 0; i < n; ++i) printf("%s[%.9g, %.9g, %.9g, %.9g]", i ? ", " : "", acc[i].x(), acc[i].y(), acc[i].z(), acc[i].w());
+      printf("], \"out\": [");
+      for (uint32_t i = 0; i < n; ++i)
+        printf("%s[%.9g, %.9g, %.9g, %.9g]", i ? ", " : "", lifted::host_surface[i].x, lifted::host_surface[i].y, lifted::host_surface[i].z, lifted::host_surface[i].w);
+      printf("]}");
+    }
+    printf("],\n\"unused2\": [");
   }
   printf("],\n\"march\": [\n");
   for (int i = 0; i < 160; ++i) {

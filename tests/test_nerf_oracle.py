@@ -4,10 +4,10 @@ The reference renderer (pyngp) is not runnable here and ships no test vectors.  
 is, and so are the small marching / indexing functions once lifted out of their .cu / template headers: the jitter
 sequence, colour transfer, focal length, camera-matrix conversion, ray generation, box intersection, step sizes,
 cascade choice, occupancy lookup, empty-space stepping, Morton codes, hash and grid index, and the hash-grid / SH
-encoding kernels, and the ray-init / first-advance / compositing / shade / accumulate kernels (run as host loops) of
-the oracle are pinned against them (bottom of this file, fixture tests/golden/nerf_host.json made by
-tests/golden/gen/make_nerf_goldens.py).  The MLPs, compaction and tonemap are checked against properties of the
-published algorithm instead ("parity partly pinned"):
+encoding kernels, and the ray-init / first-advance / compositing / shade / accumulate / compaction / tonemap kernels
+(run as host loops) of the oracle are pinned against them (bottom of this file, fixture
+tests/golden/nerf_host.json made by tests/golden/gen/make_nerf_goldens.py).  The MLPs and the order in which render()
+combines the pieces are checked against properties of the published algorithm instead ("parity partly pinned"):
 hash-grid layout numbers, Morton codes, the (0,1)-sequence property of the Owen-scrambled Sobol jitter, occupancy
 pooling, empty space, and a closed-form transmittance for a zero network.
 """
@@ -400,3 +400,19 @@ def test_shade_and_accumulate_match_the_reference_kernels():
         assert np.array_equal(dbuf, ref[:, 4]) and (dbuf == 0).any() and (dbuf > 0).any()
         accum = nerf.accumulate(accum[::-1], frame, s)[::-1]          # the buffers are indexed by pixel = n - 1 - i
         np.testing.assert_allclose(accum, np.array(P['accumulated'], f32), rtol=5e-7, atol=1e-9)
+
+
+def test_compaction_threshold_and_tonemap_match_the_reference_kernels():
+    """compact_kernel_nerf (atomic counters replaced by host counters) and tonemap_kernel (surface write replaced by a
+    host array), linear in / linear out, exposure 0, identity curve."""
+    C = HOST['compaction']
+    rays = np.array(C['rays'], dtype=np.float64)
+    alive, alpha = rays[:, 0] > 0, rays[:, 1].astype(f32)
+    assert sorted(C['still_alive']) == np.nonzero(alive)[0].tolist()
+    assert sorted(C['final']) == np.nonzero(~alive & (alpha > nerf.COMPACTION_MIN_ALPHA))[0].tolist()
+    assert (alpha[~alive] <= nerf.COMPACTION_MIN_ALPHA).sum() >= 3          # incl. one ray at exactly 0.001
+    for T in HOST['tonemap']:
+        acc = np.array(T['accumulated'], f32)
+        out = nerf.tonemap(acc, T['background'])
+        np.testing.assert_allclose(out, np.array(T['out'], f32), rtol=3e-7, atol=1e-9)
+    assert np.array_equal(np.array(HOST['tonemap'][0]['out'], f32), np.array(HOST['tonemap'][0]['accumulated'], f32))   # alpha-0 background
