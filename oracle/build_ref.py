@@ -27,7 +27,7 @@ HELPERS = ['NERF_RENDERING_NEAR_DISTANCE', 'NERF_STEPS', 'NERF_CASCADES', 'SQRT3
            'network_to_rgb*', 'network_to_density', 'network_to_density_derivative', 'composite_kernel_nerf',
            # start of a ray and end of a sample pass: ray init, jittered first advance, shade
            'calc_cone_angle', 'advance_pos_nerf', 'init_rays_with_payload_kernel_nerf', 'shade_kernel_nerf',
-           'compact_kernel_nerf']
+           'compact_kernel_nerf', 'generate_next_nerf_network_inputs']
 RENDER_BUFFER_HELPERS = ['accumulate_kernel', 'tonemap*', 'tonemap_kernel']   # src/render_buffer.cu:236-345,542-569
 
 

@@ -17,8 +17,9 @@ tests/golden/nerf_host.json and pin, in tests/test_nerf_oracle.py:
     hash_encode (= tcnn kernel_grid run as a host loop: bit-exact given the same level scales; the scales themselves
     agree to 2e-7, two of sixteen differ in the last bit between math libraries), sh_encode (= kernel_sh) and
     composite_sample (= the sample loop of composite_kernel_nerf with its activations, run as a host function),
-    first_advance (= init_rays_with_payload_kernel_nerf + advance_pos_nerf), shade, accumulate, the compaction
-    threshold and tonemap (= shade_kernel_nerf, accumulate_kernel, compact_kernel_nerf, tonemap_kernel).
+    first_advance (= init_rays_with_payload_kernel_nerf + advance_pos_nerf), next_sample (= the marching kernel
+    generate_next_nerf_network_inputs), shade, accumulate, the compaction threshold and tonemap (= shade_kernel_nerf,
+    accumulate_kernel, compact_kernel_nerf, tonemap_kernel).
 UNPINNED: the fused MLPs (wmma fragments, no host form) and the ORDER in which render() strings the pinned pieces
 together (restated from render_nerf / NerfTracer, testbed_nerf.cu:2035-2330); checked against analytic cases
 (empty occupancy -> nothing rendered, zero network -> closed-form transmittance).
@@ -502,6 +503,21 @@ def first_advance(m: NerfModel, o, d, idir, tmin, s: int):
     return t0, alive0, t, alive
 
 
+def next_sample(m: NerfModel, o, d, idir, t, alive):
+    """One iteration of generate_next_nerf_network_inputs' sample loop (:693-752) for all live rays: skip empty space,
+    emit the network input of the sample found (warped position / direction / step) and step past it.  Rays that
+    leave the render box die.  Returns (t, alive, k, wpos, wdir, wdt) with k the indices of the rays that produced a
+    sample."""
+    t, alive, pos, dt = _skip_empty(m, o, d, idir, t, alive)
+    k = np.nonzero(alive)[0]
+    diag = m.aabb[1] - m.aabb[0]
+    wpos = ((pos[k] - m.aabb[0]) / diag).astype(f32)                       # warp_position
+    wdt = ((dt[k] - STEPSIZE) / (STEPSIZE * f32(1 << (CASCADES - 1)) - STEPSIZE)).astype(f32)   # warp_dt
+    wdir = ((d[k] + f32(1)) * f32(0.5)).astype(f32)                        # warp_direction
+    t[k] = (t[k] + dt[k]).astype(f32)
+    return t, alive, k, wpos, wdir, wdt
+
+
 def shade(rgba, dep, depth_mode: bool = False):
     """shade_kernel_nerf (:1721-1754) into a cleared frame buffer: colours to linear (Shade mode), depth kept where
     alpha > 0.2.  -> (frame [n,4], depth [n])."""
@@ -559,15 +575,10 @@ def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov
         maxw = np.zeros(n, f32)
         steps = 1
         while alive.any() and steps < MARCH_ITER:
-            t, alive, pos, dt = _skip_empty(m, o, d, idir, t, alive)
-            k = np.nonzero(alive)[0]
+            t, alive, k, wpos, wdir, wdt = next_sample(m, o, d, idir, t, alive)
             if k.size == 0:
                 break
-            diag = m.aabb[1] - m.aabb[0]
-            wpos = ((pos[k] - m.aabb[0]) / diag).astype(f32)                       # warp_position
-            wdt = ((dt[k] - STEPSIZE) / (STEPSIZE * f32(1 << (CASCADES - 1)) - STEPSIZE)).astype(f32)   # warp_dt
-            out = network(m, wpos, ((d[k] + f32(1)) * f32(0.5)).astype(f32), want_rgb=not depth_mode).astype(f32)
-            t[k] = (t[k] + dt[k]).astype(f32)
+            out = network(m, wpos, wdir, want_rgb=not depth_mode).astype(f32)
             done = composite_sample(rgba, maxw, dep, k, out, wpos, wdt, m.aabb, o[k], cam, depth_scale, depth_mode,
                                     min_transmittance)
             alive[k[done]] = False

@@ -21,6 +21,7 @@
 //                                  host function; __expf -> expf)
 //   init_rays_with_payload_kernel_nerf, advance_pos_nerf, shade_kernel_nerf   src/testbed_nerf.cu:606-657,1721-1754,
 //                                  1781-1890; accumulate_kernel   src/render_buffer.cu:236-271 (same lifting)
+//   generate_next_nerf_network_inputs (the marching kernel)   src/testbed_nerf.cu:693-752
 //   compact_kernel_nerf (atomicAdd -> a host counter)   src/testbed_nerf.cu:1756-1779; tonemap + tonemap_kernel
 //                                  (surf2Dwrite -> a host array)   src/render_buffer.cu:273-345,542-569
 // The fused MLPs (wmma fragments) cannot run without a GPU; that part of the oracle stays unpinned.
@@ -380,6 +381,27 @@ int main() {
       for (uint32_t i = 0; i < n; ++i)
         printf("%s[%d, %.9g, %d, %.9g]", i ? ", " : "", alive_init[i], t_init[i], (int)pay[i].alive, pay[i].alive ? pay[i].t : 0.f);
       printf("]");
+      if (spp == 1) {
+        // the marching kernel on top of pass 1: up to 4 samples per ray (generate_next_nerf_network_inputs)
+        const uint32_t S = 4;
+        std::vector<NerfCoordinate> coords((size_t)n * S, NerfCoordinate(Vector3f::Zero(), Vector3f::Zero(), 0.f));
+        for (uint32_t i = 0; i < n; ++i) {
+          lifted::h_tid.x = i;
+          generate_next_nerf_network_inputs(n, box, Matrix3f::Identity(), box, Vector2f(f, f), cam.col(2), pay.data(),
+                                            PitchedPtr<NerfCoordinate>(coords.data(), 1), S, bits.data(), 0, 0.f, nullptr);
+        }
+        printf("], \"march_from_pass_1\": [");
+        for (uint32_t i = 0; i < n; ++i) {
+          printf("%s{\"alive\": %d, \"n_steps\": %u, \"t\": %.9g, \"samples\": [", i ? ", " : "", (int)pay[i].alive, (unsigned)pay[i].n_steps,
+                 pay[i].alive ? pay[i].t : 0.f);
+          for (uint32_t j = 0; pay[i].alive && j < pay[i].n_steps; ++j) {
+            const NerfCoordinate& c = coords[i + (size_t)j * n];
+            printf("%s[%.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g]", j ? ", " : "", c.pos.p.x(), c.pos.p.y(), c.pos.p.z(), c.dt, c.dir.d.x(),
+                   c.dir.d.y(), c.dir.d.z());
+          }
+          printf("]}");
+        }
+      }
     }
     printf("]},\n");
   }

@@ -416,3 +416,37 @@ def test_compaction_threshold_and_tonemap_match_the_reference_kernels():
         out = nerf.tonemap(acc, T['background'])
         np.testing.assert_allclose(out, np.array(T['out'], f32), rtol=3e-7, atol=1e-9)
     assert np.array_equal(np.array(HOST['tonemap'][0]['out'], f32), np.array(HOST['tonemap'][0]['accumulated'], f32))   # alpha-0 background
+
+
+def test_marching_kernel_matches_the_reference():
+    """generate_next_nerf_network_inputs (lifted as a host function) continuing sample pass 1 of the ray-start fixture
+    for up to 4 samples per ray: the network inputs (warped position, direction, step), the distance reached and which
+    rays left the box, against oracle.next_sample applied four times."""
+    R = HOST['ray_start']
+    cam = np.array(R['camera'], f32).reshape(3, 4)
+    o, d = nerf.pixel_rays(cam, R['width'], R['height'], R['fov'])
+    with np.errstate(divide='ignore'):
+        idir = (f32(1) / d).astype(f32)
+    n_bytes = nerf.CASCADES * 128 ** 3 // 8
+    bits = ((np.arange(n_bytes, dtype=np.uint64) * np.uint64(2654435761) & np.uint64(0xFFFFFFFF)) >> np.uint64(13)).astype(np.uint8)
+    sc = syn.nerf_scene(0, 1, zero_network=True)
+    m = nerf.NerfModel(1, sc['grid'], sc['w_density'], sc['w_rgb'], bits)
+    tmin, _ = nerf.ray_box(m.render_aabb, o, d)
+    _, _, t, alive = nerf.first_advance(m, o, d, idir, tmin, 1)
+    M = R['march_from_pass_1']
+    produced = np.zeros(len(M), np.int64)
+    for j in range(4):
+        t, alive, k, wpos, wdir, wdt = nerf.next_sample(m, o, d, idir, t, alive)
+        for a, i in enumerate(k):
+            ref = np.array(M[i]['samples'][j], f32)
+            np.testing.assert_allclose(wpos[a], ref[0:3], rtol=0, atol=1e-6)       # one ulp of t (2.4e-7 at t = 2.5) times |d|
+            assert abs(float(wdt[a]) - float(ref[3])) <= 1e-6
+            np.testing.assert_allclose(wdir[a], ref[4:7], rtol=0, atol=1e-7)
+        produced[k] += 1
+    for i, r in enumerate(M):
+        if r['alive']:
+            # a ray that left the box mid-way keeps its payload alive with n_steps < 4 (the compositing kernel retires it)
+            assert produced[i] == r['n_steps']
+            if r['n_steps'] == 4:
+                assert abs(float(t[i]) - r['t']) <= 5e-7 * r['t']
+    assert (produced == 4).sum() >= 60 and ((produced > 0) & (produced < 4)).any()
