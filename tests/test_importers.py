@@ -1,5 +1,6 @@
-"""Importers: PixLoc checkpoint layout and instant-ngp msgpack snapshot layout (synthetic files written in the
-reference's formats; the real assets are not in the container)."""
+"""Importers: PixLoc checkpoint layout (pinned on the reference model's own state dict, last test) and instant-ngp
+msgpack snapshot layout (synthetic files written in the reference's format; the real assets are not in the
+container)."""
 import numpy as np
 import pytest
 import torch
@@ -109,3 +110,45 @@ def test_loaders_build_working_adapters(tmp_path):
     ref = onerf.render(m, cam, 32, 24, 50.0, spp=2)['rgba']
     assert ref[..., 3].max() > 0.9
     assert (np.abs(got - ref).max(-1) > 4e-3).mean() < 0.02
+
+
+def test_importer_consumes_the_reference_models_state_dict_layout():
+    """tests/golden/pixloc_checkpoint_layout.json lists every key / shape / dtype of
+    `TwoViewRefiner(pixloc_megadepth conf).state_dict()` from the unmodified reference
+    (tests/golden/gen/make_checkpoint_layout.py).  A checkpoint with exactly those entries goes through
+    split_pixloc_checkpoint and the weight packer, every floating-point extractor tensor is consumed, and the synthetic
+    weights the other tests use have the same layout."""
+    import json
+    import os
+    from pixtrack_b200.extractor import pack_weights
+    fix = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'pixloc_checkpoint_layout.json')))
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for key, shape, dtype in fix['state_dict']:
+        if dtype == 'int64':
+            sd[key] = torch.zeros(shape, dtype=torch.int64)
+        elif key.endswith('running_var'):
+            sd[key] = torch.rand(shape, generator=g) + 0.5
+        else:
+            sd[key] = torch.randn(shape, generator=g) * 0.05
+    ext, oconf, consts = importers.split_pixloc_checkpoint({'conf': {'model': fix['conf_model']}, 'model': sd},
+                                                           importers.R9_OPTIMIZER_OVERRIDES)
+    assert len(consts) == 3 and all(tuple(c.shape) == (6,) for c in consts)
+    assert oconf['num_iters'] == 150 and oconf['pad'] == 1 and oconf['lambda_'] == 0.01 and oconf['damping'] == {'type': 'constant'}
+    packed = pack_weights(ext, 'cpu')
+    assert len(packed['conv_w']) == len(packed['conv_b']) == 20 and len(packed['head_w']) == 3
+    assert [tuple(w.shape) for w in packed['head_w']] == [(33, 32), (129, 64), (129, 512)]
+    assert tuple(packed['conv_w'][0].shape) == (64, 28) and tuple(packed['conv_w'][-1].shape) == (9, 32, 128)
+    # every floating-point tensor of the extractor is used by the packer (decoder convs carry no bias: BatchNorm follows)
+    used = set()
+    for b, idxs in enumerate(([0, 2], [1, 3], [1, 3, 5, 7], [1, 3, 5, 7], [1, 3, 5, 7])):
+        for i in idxs:
+            used |= {f'encoder.{b}.{i}.weight', f'encoder.{b}.{i}.bias'}
+    for i in range(4):
+        used |= {f'decoder.{i}.layers.0.weight'} | {f'decoder.{i}.layers.1.{n}' for n in ('weight', 'bias', 'running_mean', 'running_var')}
+    for l in range(3):
+        used |= {f'{h}.{l}.0.{n}' for h in ('adaptation', 'uncertainty') for n in ('weight', 'bias')}
+    assert used == {k for k, v in ext.items() if v.is_floating_point()}
+    # the synthetic generator mirrors the layout exactly
+    syn_sd = syn.unet_weights(0)
+    assert {k: tuple(v.shape) for k, v in syn_sd.items()} == {k: tuple(v.shape) for k, v in ext.items()}
