@@ -25,7 +25,9 @@ together (restated from render_nerf / NerfTracer, testbed_nerf.cu:2035-2330); ch
 (empty occupancy -> nothing rendered, zero network -> closed-form transmittance).
 One deliberate numerical difference: tiny-cuda-nn's fully fused MLP accumulates in fp16 inside
 wmma fragments (fully_fused_mlp.cu:67-69); here, and in csrc/ptk_nerf.cu, products of fp16
-operands are accumulated in fp32 and rounded to fp16 once per layer.
+operands are accumulated in fp32 and rounded to fp16 once per layer.  FP16_ACCUMULATE = True emulates the
+reference's running fp16 sum; on the test scenes the rendered RGBA moves by at most 8e-4 (mean 1e-5), inside the
+4e-3 the GPU tests allow (tests/test_nerf_oracle.py, last test).
 
 Paths cited: `ngp/` = instant-ngp/, `tcnn/` = instant-ngp/dependencies/tiny-cuda-nn/.
 """
@@ -278,8 +280,20 @@ def sh_encode(d01: np.ndarray) -> np.ndarray:
     return o.astype(np.float16)
 
 
+FP16_ACCUMULATE = False     # True: emulate the reference's fp16 wmma accumulators (only to measure the difference)
+
+
 def _layer(x16: np.ndarray, w16: np.ndarray, relu: bool) -> np.ndarray:
-    y = x16.astype(f32) @ w16.astype(f32).T           # fp16 operands, fp32 accumulate (see header)
+    if FP16_ACCUMULATE:
+        # fully_fused_mlp.cu:67-69,125-140: 16x16x16 wmma steps with __half accumulator fragments -- every K block
+        # of 16 adds its (exact) partial dot product to an fp16 running sum
+        x, w = x16.astype(f32), w16.astype(f32)
+        acc = np.zeros((x.shape[0], w.shape[0]), np.float16)
+        for k0 in range(0, x.shape[1], 16):
+            acc = (acc.astype(f32) + x[:, k0:k0 + 16] @ w[:, k0:k0 + 16].T).astype(np.float16)
+        y = acc.astype(f32)
+    else:
+        y = x16.astype(f32) @ w16.astype(f32).T       # fp16 operands, fp32 accumulate (see header)
     if relu:
         y = np.maximum(y, 0)
     return y.astype(np.float16)
