@@ -55,22 +55,22 @@ def lift_helpers(cu_path: str, names=None) -> str:
 
 
 def _one_definition(lines, start):
-        out = []
-        if lines[start - 1].startswith('template'):
-            out.append(lines[start - 1])
-        depth, i = 0, start
-        while True:
-            depth += lines[i].count('{') - lines[i].count('}')
-            if depth == 0 and '{' in ''.join(lines[start:i + 1]):
-                break
-            i += 1
-        body = lines[start:i + 1]
-        if '__global__' in body[0]:
-            body[0] = body[0].replace('__global__', '__host__', 1)
-        elif '__host__' not in body[0]:
-            body[0] = body[0].replace('__device__', '__host__ __device__', 1)
-        out.extend(body + [''])
-        return out
+    out = []
+    if lines[start - 1].startswith('template'):
+        out.append(lines[start - 1])
+    depth, i = 0, start
+    while True:
+        depth += lines[i].count('{') - lines[i].count('}')
+        if depth == 0 and '{' in ''.join(lines[start:i + 1]):
+            break
+        i += 1
+    body = lines[start:i + 1]
+    if '__global__' in body[0]:
+        body[0] = body[0].replace('__global__', '__host__', 1)
+    elif '__host__' not in body[0]:
+        body[0] = body[0].replace('__device__', '__host__ __device__', 1)
+    out.extend(body + [''])
+    return out
 
 
 def build(verbose: bool = True) -> str:
