@@ -470,3 +470,25 @@ def test_fp32_versus_fp16_mlp_accumulation_stays_inside_the_render_tolerance():
     assert 0 < d.max() < 2e-3 and d.mean() < 1e-4
     ua, ub = (a[..., :3] * 255).astype(np.uint8).astype(int), (b[..., :3] * 255).astype(np.uint8).astype(int)
     assert np.abs(ua - ub).max() <= 1
+
+
+def test_product_host_side_camera_code_matches_the_reference_too():
+    """The renderer's HOST half lives in pixtrack_b200/nerf.py (camera-matrix conversion, focal length, background to
+    linear): checked directly against the reference outputs of the fixture, without going through the oracle."""
+    from types import SimpleNamespace
+    from pixtrack_b200.nerf import NerfTestbed, RenderMode
+    fake = SimpleNamespace(scale=0.33, offset=np.array([0.5, 0.5, 0.5], f32), _camera=None)
+    NerfTestbed.set_nerf_camera_matrix(fake, np.array(HOST['nerf_matrix'], f32).reshape(3, 4))
+    assert np.array_equal(fake._camera, np.array(HOST['ngp_matrix'], f32).reshape(3, 4))
+    for res, deg, focal in HOST['fov_to_focal']:
+        fake = SimpleNamespace(snap_to_pixel_centers=True, exposure=0.0, _camera=np.zeros((3, 4), f32),
+                               render_aabb=SimpleNamespace(min=np.zeros(3), max=np.ones(3)), fov_axis=0, fov=deg, scale=0.33,
+                               nerf=SimpleNamespace(rendering_min_transmittance=1e-7), background_color=[0.2, 0.5, 0.8, 1.0],
+                               render_mode=RenderMode.Shade)
+        v = NerfTestbed._view(fake, int(res), 7, 8)
+        # the reference computes fov_to_focal_length(1, fov) * res; the fixture holds fov_to_focal_length(res, fov)
+        assert abs(v.focal - focal) <= 3e-7 * focal
+        assert abs(v.depth_scale - 1 / 0.33) < 1e-6 and v.depth_mode == 0 and (v.width, v.height, v.spp) == (int(res), 7, 8)
+        srgb = {round(r[0], 6): r[1] for r in HOST['srgb']}
+        lin = nerf.srgb_to_linear(np.array([0.2, 0.5, 0.8], f32))
+        assert np.allclose([v.background[i] for i in range(3)], lin, rtol=1e-6) and v.background[3] == 1.0
