@@ -14,10 +14,18 @@
  *    void*; NULL = legacy default stream) and never synchronise the device;
  *  - return value 0 = ok, negative = error; `ptk_last_error()` gives the text
  *    of the last error on the calling thread; nothing throws across the ABI;
- *  - a PtkContext owns a small device workspace, so at most one call per
- *    context may be in flight on different streams at a time
- *    (thread-compatible, not thread-safe -- like the reference's single
- *    Python caller).  Create one context per device / per worker.
+ *  - a PtkContext holds the device index, the SM count and a small default
+ *    LM workspace.  Only ptk_lm_run uses a workspace (the partial sums and
+ *    barrier counters of CTAs that share a problem): launches that pass their
+ *    own `PtkLmProblem.workspace` may be in flight concurrently on any number
+ *    of streams; launches that leave it NULL share the context's and must
+ *    then be stream-ordered with respect to each other.  No other entry point
+ *    keeps per-context device state, so extractor plans, samplers, renders and
+ *    masks of one context may overlap freely (each PtkExtractor / PtkNerf owns
+ *    its buffers).  Host-side, calls are thread-compatible, not thread-safe --
+ *    like the reference's single Python caller;
+ *  - every entry point that allocates or launches makes the context's device
+ *    current for the duration of the call and restores the caller's;
  *  - batch strides (`*_bstride`) are in ELEMENTS between consecutive
  *    problems; 0 means "shared by all problems of the batch".
  */
@@ -30,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PTK_ABI_VERSION 1
+#define PTK_ABI_VERSION 2
 
 /* error codes */
 #define PTK_OK 0
@@ -108,6 +116,10 @@ typedef struct PtkLmProblem {
   float grad_stop;    /* conf.grad_stop_criteria                                  */
   float dt_stop;      /* conf.dt_stop_criteria                                    */
   float dR_stop;      /* conf.dR_stop_criteria (degrees)                          */
+  void* workspace;    /* ZERO-INITIALISED device scratch of >= ptk_lm_workspace_bytes()
+                         owned by this (prepared) launch, or NULL = the context's shared
+                         workspace.  The kernel leaves it zeroed again.              */
+  int64_t workspace_bytes;
 } PtkLmProblem;
 
 typedef struct PtkLmResult {
@@ -118,6 +130,8 @@ typedef struct PtkLmResult {
 } PtkLmResult;
 
 int ptk_lm_run(PtkContext* ctx, const PtkLmProblem* prob, const PtkLmResult* res, void* stream);
+/* bytes of PtkLmProblem.workspace (host only) */
+int64_t ptk_lm_workspace_bytes(void);
 
 /* Launch geometry the next ptk_lm_run with this problem would use (for
  * benchmarks / tests): CTAs per problem and number of problem groups. */

@@ -11,6 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libpixtrack_b200.so')
 LOG_STRIDE = 64
+ABI_VERSION = 2
 
 c_f32p = C.POINTER(C.c_float)
 c_u8p = C.POINTER(C.c_uint8)
@@ -37,6 +38,7 @@ class LmProblem(C.Structure):
         ('lambda_', C.c_void_p), ('lambda_bstride', C.c_int64),
         ('skip', C.c_void_p),
         ('loss_scale', C.c_float), ('grad_stop', C.c_float), ('dt_stop', C.c_float), ('dR_stop', C.c_float),
+        ('workspace', C.c_void_p), ('workspace_bytes', C.c_int64),
     ]
 
 
@@ -77,6 +79,7 @@ SYMBOLS = {
     'ptk_device_status': (C.c_int, [C.c_void_p]),
     'ptk_lm_run': (C.c_int, [C.c_void_p, C.POINTER(LmProblem), C.POINTER(LmResult), C.c_void_p]),
     'ptk_lm_plan': (C.c_int, [C.c_void_p, C.POINTER(LmProblem), c_i32p, c_i32p]),
+    'ptk_lm_workspace_bytes': (C.c_int64, []),
     'ptk_sample_points': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
@@ -125,7 +128,7 @@ def load():
                 fn = getattr(lib, name)      # AttributeError if the symbol is not exported
                 fn.restype = res
                 fn.argtypes = args
-            if lib.ptk_abi_version() != 1:
+            if lib.ptk_abi_version() != ABI_VERSION:
                 raise PtkError('ABI version mismatch between _lib.py and libpixtrack_b200.so')
             _lib = lib
     return _lib
@@ -143,12 +146,16 @@ def context(device_index: int) -> int:
     if not torch.cuda.is_available():
         # never enter the CUDA runtime without a device (it can block for minutes on a GPU-less host)
         raise PtkError('no CUDA device: pixtrack_b200 runs only on sm_100a GPUs (no CPU fallback)')
+    code = 0
     with _lock:
-        if device_index not in _contexts:
+        h = _contexts.get(device_index)
+        if h is None:
             h = C.c_void_p()
-            check(lib.ptk_create(int(device_index), C.byref(h)))
-            _contexts[device_index] = h
-        return _contexts[device_index]
+            code = lib.ptk_create(int(device_index), C.byref(h))
+            if code == 0:
+                _contexts[device_index] = h
+    check(code)          # outside the lock: check() re-enters load(), which takes it
+    return h
 
 
 def current_stream_ptr(device) -> int:

@@ -66,6 +66,7 @@ extern "C" int ptk_num_sms(const PtkContext* c) { return c ? c->num_sms : 0; }
 // Synchronising health check: 0 = no device-side abort (barrier time-out) recorded.
 extern "C" int ptk_device_status(PtkContext* c) {
   PTK_REQUIRE(c != nullptr, "null context");
+  PtkDeviceGuard guard(c->device);
   int flag = 0;
   PTK_CUDA_CHECK(cudaMemcpy(&flag, c->lm_error, sizeof(int), cudaMemcpyDeviceToHost));
   if (flag != 0) {
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(256) chw_to_hwc_kernel(const float* __restrict
 extern "C" int ptk_chw_to_hwc(PtkContext* ctx, const float* src, float* dst, int32_t C, int32_t H, int32_t W,
                               int32_t normalize, void* stream) {
   PTK_REQUIRE(ctx && src && dst, "null argument");
+  PtkDeviceGuard guard(ctx->device);
   PTK_REQUIRE(C >= 1 && C <= 1024 && H >= 1 && W >= 1, "bad shape");
   const long long HW = (long long)H * W;
   const size_t smem = (size_t)C * 33 * sizeof(float);

@@ -20,6 +20,22 @@ struct PtkContext {
 
 void ptk_set_error(const char* fmt, ...);
 
+// LM workspace layout (floats then counters): [PTK_MAX_SMS][2][32] partial sums, PTK_MAX_SMS + 8 counters
+#define PTK_LM_WS_PARTIAL_BYTES (sizeof(float) * PTK_MAX_SMS * 2 * 32)
+#define PTK_LM_WS_BYTES (PTK_LM_WS_PARTIAL_BYTES + sizeof(unsigned int) * (PTK_MAX_SMS + 8))
+
+// Makes ctx->device current for the scope of an entry point (the caller's device is restored on exit).
+struct PtkDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit PtkDeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~PtkDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 #define PTK_CUDA_CHECK(expr)                                                            \
   do {                                                                                  \
     cudaError_t _e = (expr);                                                            \

@@ -992,6 +992,7 @@ int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void
                       int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
                       int32_t Cout, int32_t taps, int32_t relu, void* out, void* pool_out, void* stream) {
   PTK_REQUIRE(ctx && in0 && weights && bias && out, "null argument");
+  PtkDeviceGuard guard(ctx->device);
   PTK_REQUIRE(taps == 9 || taps == 1, "taps must be 9 (3x3, pad 1) or 1 (1x1)");
   PTK_REQUIRE(cin0 > 0 && cin0 % kKChunk == 0 && cin1 >= 0 && cin1 % kKChunk == 0, "C_in must be a multiple of 64");
   PTK_REQUIRE(Cout == 32 || Cout == 64 || Cout == 128 || Cout % 256 == 0, "C_out must be 32, 64, 128 or k*256");

@@ -656,10 +656,18 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
     }
     if (rank == 0 && threadIdx.x < 12) P.r.T[(size_t)b * 12 + threadIdx.x] = sT[threadIdx.x];
     if (rank == 0 && threadIdx.x == 32) {
-      P.r.failed[b] = (uint8_t)((sFailed != 0) || skipped);
+      // a timed-out barrier (sAbort) leaves inconsistent sums behind: the problem is reported as failed
+      P.r.failed[b] = (uint8_t)((sFailed != 0) || skipped || (sAbort != 0));
       P.r.n_iters[b] = skipped ? 0 : min(it, p.num_iters);
     }
-    if (sAbort) break;
+    if (sAbort) {   // ... and so is every problem this group will no longer visit
+      if (rank == 0 && threadIdx.x == 32)
+        for (int bb = b + P.n_groups; bb < p.B; bb += P.n_groups) {
+          P.r.failed[bb] = 1;
+          P.r.n_iters[bb] = 0;
+        }
+      break;
+    }
   }
 
   // self-cleaning workspace: the last CTA to leave zeroes the counters
@@ -717,6 +725,8 @@ extern "C" int ptk_lm_plan(const PtkContext* ctx, const PtkLmProblem* prob, int3
   return PTK_OK;
 }
 
+extern "C" int64_t ptk_lm_workspace_bytes(void) { return (int64_t)PTK_LM_WS_BYTES; }
+
 extern "C" int ptk_lm_run(PtkContext* ctx, const PtkLmProblem* prob, const PtkLmResult* res, void* stream) {
   PTK_REQUIRE(ctx && prob && res, "null context/problem/result");
   const PtkLmProblem& p = *prob;
@@ -742,9 +752,17 @@ extern "C" int ptk_lm_run(PtkContext* ctx, const PtkLmProblem* prob, const PtkLm
   P.a2 = (float)((double)p.loss_scale * (double)p.loss_scale);
   // 0.1f squared in double rounds one ulp above float(0.01); the reference divides by float(0.1**2)
   if (p.loss_scale == 0.1f) P.a2 = 0.01f;
-  P.partials = ctx->lm_partials;
-  P.counters = ctx->lm_counters;
+  if (p.workspace != nullptr) {   // per-launch workspace: concurrent launches on one context are independent
+    PTK_REQUIRE(p.workspace_bytes >= (int64_t)PTK_LM_WS_BYTES, "workspace smaller than ptk_lm_workspace_bytes()");
+    PTK_REQUIRE((uintptr_t)p.workspace % 16 == 0, "workspace must be 16-byte aligned");
+    P.partials = (float*)p.workspace;
+    P.counters = (unsigned int*)((char*)p.workspace + PTK_LM_WS_PARTIAL_BYTES);
+  } else {
+    P.partials = ctx->lm_partials;
+    P.counters = ctx->lm_counters;
+  }
   P.error = ctx->lm_error;
+  PtkDeviceGuard guard(ctx->device);
 
   const dim3 grid(P.G * P.n_groups), block(kThreads);
   void* args[] = {&P};

@@ -57,6 +57,7 @@ __global__ void dilate_apply_kernel(const uint8_t* __restrict__ in, int H, int W
 extern "C" int ptk_query_mask(PtkContext* ctx, const uint8_t* depth_u8, int32_t H, int32_t W, const void* image,
                               int32_t img_dtype, void* out_image, uint8_t* out_mask, uint8_t* workspace, void* stream) {
   PTK_REQUIRE(ctx && depth_u8 && workspace, "null argument");
+  PtkDeviceGuard guard(ctx->device);
   PTK_REQUIRE(H >= 1 && W >= 1 && (long long)H * W * 3 < 2147483647LL, "bad image size");
   PTK_REQUIRE(img_dtype == 0 || img_dtype == 1, "img_dtype must be 0 (fp32) or 1 (uint8)");
   PTK_REQUIRE((image != nullptr) == (out_image != nullptr), "image and out_image must be given together");

@@ -690,6 +690,7 @@ struct PtkNerf {
 
 extern "C" int ptk_nerf_create(PtkContext* ctx, const PtkNerfModel* m, PtkNerf** out) {
   PTK_REQUIRE(ctx && m && out, "null argument");
+  PtkDeviceGuard guard(ctx->device);
   PTK_REQUIRE(m->grid && m->bitfield, "null grid / bitfield");
   for (int i = 0; i < 5; ++i) PTK_REQUIRE(m->weights[i] != nullptr, "null weight matrix");
   PTK_REQUIRE(m->aabb_scale >= 1 && m->aabb_scale <= 128 && (m->aabb_scale & (m->aabb_scale - 1)) == 0,
@@ -812,6 +813,7 @@ extern "C" int ptk_nerf_render(PtkNerf* n, const PtkNerfView* v, float* out_rgba
   PTK_REQUIRE(v->width >= 1 && v->height >= 1 && v->spp >= 1, "width, height, spp must be >= 1");
   PTK_REQUIRE(v->focal > 0.f, "focal must be positive");
   PTK_REQUIRE(out_rgba || out_u8, "no output buffer");
+  PtkDeviceGuard guard(n->ctx->device);
   NerfParams P = n->base;
   for (int i = 0; i < 12; ++i) P.cam[i] = v->camera[i];
   for (int i = 0; i < 3; ++i) {

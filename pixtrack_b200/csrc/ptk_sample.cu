@@ -67,6 +67,7 @@ extern "C" int ptk_sample_points(PtkContext* ctx, const float* map, int64_t stri
                                  int64_t stride_x, int32_t C, int32_t H, int32_t W, const float* pts, int32_t N,
                                  int32_t pad, float* vals, uint8_t* mask, float* grads, void* stream) {
   PTK_REQUIRE(ctx && map && vals && (pts || N == 0), "null argument");
+  PtkDeviceGuard guard(ctx->device);
   PTK_REQUIRE(C >= 1 && H >= 2 && W >= 2 && N >= 0 && pad >= 0, "bad shape");
   if (N == 0) return PTK_OK;
   const long long total = (long long)N * C;

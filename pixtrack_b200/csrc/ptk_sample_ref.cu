@@ -148,6 +148,7 @@ extern "C" int ptk_sample_reference(PtkContext* ctx, const PtkRefLevel* levels, 
                                     int32_t N, const double* host_cam, int32_t n_cam, const double* host_T,
                                     int32_t pad, uint8_t* valid, void* stream) {
   PTK_REQUIRE(ctx && levels && host_cam && host_T && valid && (p3d || N == 0), "null argument");
+  PtkDeviceGuard guard(ctx->device);
   PTK_REQUIRE(n_levels >= 1 && n_levels <= PTK_MAX_LEVELS, "1..PTK_MAX_LEVELS levels");
   PTK_REQUIRE(n_cam == 6 || n_cam == 8 || n_cam == 10, "n_cam must be 6, 8 or 10");
   PTK_REQUIRE(N >= 0 && pad >= 0, "N and pad must be >= 0");

@@ -403,6 +403,7 @@ extern "C" int ptk_extractor_create(PtkContext* ctx, const PtkUnetWeights* w, in
                                     PtkExtractor** out) {
   PTK_REQUIRE(ctx && w && out, "null argument");
   PTK_REQUIRE(H >= 16 && W >= 16, "image must be at least 16x16");
+  PtkDeviceGuard guard(ctx->device);
   PtkExtractor* e = (PtkExtractor*)calloc(1, sizeof(PtkExtractor));
   e->ctx = ctx; e->H = H; e->W = W; e->wts = *w;
   e->eh[0] = H; e->ew[0] = W;
@@ -592,6 +593,7 @@ extern "C" int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img
                                  float* const* feat, float* const* conf, int32_t normalize, void* stream) {
   PTK_REQUIRE(e && image && feat && conf, "null argument");
   PTK_REQUIRE(img_dtype == 0 || img_dtype == 1, "img_dtype must be 0 (fp32) or 1 (uint8)");
+  PtkDeviceGuard guard(e->ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
   static int graph_mode = -1;   // PTK_PLAN_GRAPH=0: always launch kernel by kernel
   if (graph_mode < 0) graph_mode = getenv("PTK_PLAN_GRAPH") ? atoi(getenv("PTK_PLAN_GRAPH")) : 1;
@@ -665,6 +667,7 @@ extern "C" int ptk_extractor_profile(PtkExtractor* e, const void* image, int32_t
                                      float* const* feat, float* const* conf, int32_t normalize, void* stream,
                                      int32_t max_n, float* ms, int32_t* kinds, double* flops, int32_t* n_out) {
   PTK_REQUIRE(e && ms && kinds && flops && n_out, "null argument");
+  PtkDeviceGuard guard(e->ctx->device);
   cudaEvent_t ev[PTK_MAX_LAUNCHES];
   for (int i = 0; i < PTK_MAX_LAUNCHES; ++i) PTK_CUDA_CHECK(cudaEventCreate(&ev[i]));
   e->prof_ev = ev;

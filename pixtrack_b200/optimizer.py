@@ -109,7 +109,7 @@ def query_map_to_hwc(F_q: Tensor, normalize: bool = False) -> Tensor:
     src = _f32c(F_q)
     Cc, H, W = src.shape
     dst = torch.empty((H, W, Cc), dtype=torch.float32, device=src.device)
-    dev = src.device.index or 0
+    dev = src.device.index if src.device.index is not None else torch.cuda.current_device()
     _lib.check(_lib.load().ptk_chw_to_hwc(_lib.context(dev), src.data_ptr(), dst.data_ptr(), Cc, H, W,
                                           1 if normalize else 0, _lib.current_stream_ptr(src.device)))
     return dst
@@ -181,6 +181,11 @@ class LmLaunch:
         self.n_iters = torch.empty((B,), dtype=torch.int32, device=dev)
         self.log = (torch.zeros((B, max(1, num_iters), _lib.LOG_STRIDE), dtype=torch.float32, device=dev)
                     if want_log else None)
+        # own barrier / partial-sum scratch: prepared launches on one device may run concurrently on different streams
+        # (zero-initialised once; the kernel leaves it zeroed)
+        ws_bytes = int(_lib.load().ptk_lm_workspace_bytes())
+        self._workspace = torch.zeros((ws_bytes + 3) // 4, dtype=torch.int32, device=dev)
+        prob.workspace, prob.workspace_bytes = self._workspace.data_ptr(), ws_bytes
         self._res = _lib.LmResult(self.T.data_ptr(), self.failed.data_ptr(), self.n_iters.data_ptr(), _ptr(self.log))
         self._prob, self._keep, self.device = prob, keep, dev
         di = dev.index if dev.index is not None else torch.cuda.current_device()

@@ -24,13 +24,14 @@ def test_library_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f'{n} declared in include/pixtrack_b200.h but not exported'
         assert n in _lib.SYMBOLS, f'{n} has no ctypes prototype in _lib.py'
-    assert lib.ptk_abi_version() == 1
+    assert lib.ptk_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layout_matches_header():
     from pixtrack_b200 import _lib
-    # 10 int32, 9 (pointer, int64) pairs, 1 pointer, 4 floats
-    assert ctypes.sizeof(_lib.LmProblem) == 40 + 9 * 16 + 8 + 16
+    # 10 int32, 9 (pointer, int64) pairs, 1 pointer, 4 floats, workspace pointer + size
+    assert ctypes.sizeof(_lib.LmProblem) == 40 + 9 * 16 + 8 + 16 + 16
+    assert _lib.LmProblem.workspace.offset == 40 + 9 * 16 + 8 + 16
     assert _lib.LmProblem.p3d.offset == 40 and _lib.LmProblem.skip.offset == 40 + 9 * 16
     assert ctypes.sizeof(_lib.LmResult) == 32
 
@@ -49,6 +50,40 @@ def test_product_path_fails_loudly_without_cuda():
                 Camera(torch.ones(8)))
     with pytest.raises(_lib.PtkError):
         sample_points(torch.zeros(4, 8, 8), torch.zeros(3, 2))
+
+
+def test_context_creation_failure_raises_instead_of_deadlocking(monkeypatch):
+    """ptk_create failing (wrong architecture, bad index, allocation failure) must surface as PtkError: check() re-enters
+    load(), which takes the same non-reentrant lock context() holds while creating."""
+    import threading
+    from pixtrack_b200 import _lib
+    lib = _lib.load()
+
+    class FailingLib:
+        def __getattr__(self, name):
+            return getattr(lib, name)
+
+        @staticmethod
+        def ptk_create(device, out):
+            return -3
+
+    monkeypatch.setattr(_lib, '_lib', FailingLib())
+    monkeypatch.setattr(_lib, '_contexts', {})
+    monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)
+    result = []
+
+    def attempt():
+        try:
+            _lib.context(0)
+            result.append('returned')
+        except _lib.PtkError as e:
+            result.append(e)
+    th = threading.Thread(target=attempt, daemon=True)
+    th.start()
+    th.join(20)
+    assert not th.is_alive(), 'context() deadlocked on its own lock'
+    assert len(result) == 1 and isinstance(result[0], _lib.PtkError)
+    assert 0 not in _lib._contexts
 
 
 def test_product_package_never_imports_oracle():
