@@ -28,7 +28,8 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from pixtrack_b200 import synthetic as syn  # noqa: E402
+sys.path.insert(1, os.path.join(ROOT, 'tests'))     # synthetic scene generators (test / bench infrastructure)
+import synthetic as syn  # noqa: E402
 
 N_POINTS, N_VIEWS, RING = 5000, 8, 4
 WORKLOAD = ('C2 frame: 1920x1080 query + 1008x756 re-rendered reference view of one textured object; per frame '

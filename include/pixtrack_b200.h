@@ -227,6 +227,12 @@ int ptk_sample_reference(PtkContext* ctx, const PtkRefLevel* levels, int32_t n_l
 int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
                  int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
                  int32_t Cout, int32_t taps, int32_t relu, void* out, void* stream);
+/* Same, and when pool_out != NULL the epilogue also writes the 2x2 / stride-2 max pool (floor mode) of the result,
+ * fp16 [H/2][W/2][C_out]: the nn.MaxPool2d that opens the next encoder block (unet.py:68-99), fused. */
+int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
+                      int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights,
+                      const float* bias, int32_t Cout, int32_t taps, int32_t relu, void* out, void* pool_out,
+                      void* stream);
 
 typedef struct PtkUnetWeights {
   const void* conv_w[20];   /* [0]: fp32 [64][28] ((ky,kx,c) taps + 1 pad); [1..19]: fp16 [9][C_out][C_in];

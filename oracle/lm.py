@@ -1,9 +1,14 @@
 """CPU oracle for the feature-metric Levenberg-Marquardt pose refinement.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PyTorch fp32 on CPU, using the
+TEST INFRASTRUCTURE (see oracle/__init__.py).  PyTorch fp32, using the
 same library primitives the reference uses (`grid_sample`, `einsum`,
 `linalg.cholesky`) so that (i) results match the reference to rounding and
-(ii) its wall-clock is a fair stand-in for the reference's own CPU path.
+(ii) its wall-clock is a fair stand-in for the reference's own path.  Every
+function follows the device of its inputs: on CPU tensors it is the checker
+and the CPU baseline; on CUDA tensors it is what the reference executes with
+`device='cuda'` (pixtrack/localization/pixloc_pose_refiners.py:35-39): library
+kernels per op, the 6x6 factorisation on the host with a device round trip
+per iteration -- bench.py's `library_baseline` leg times that.
 
 Conventions (all tensors fp32 unless noted):
   pose   : R [3,3], t [3]          world -> camera, p_c = R p + t
@@ -43,7 +48,7 @@ def rodrigues(w: Tensor, eps: float = 1e-7) -> Tensor:
     W = hat(unit)
     th = theta[..., None]
     full = torch.sin(th) * W + (1.0 - torch.cos(th)) * (W @ W)
-    return torch.eye(3, dtype=w.dtype) + torch.where(tiny[..., None], W, full)
+    return torch.eye(3, dtype=w.dtype, device=w.device) + torch.where(tiny[..., None], W, full)
 
 
 def compose(Ra: Tensor, ta: Tensor, Rb: Tensor, tb: Tensor):
@@ -69,7 +74,7 @@ def scale_camera(cam: Tensor, s: Sequence[float]) -> Tensor:
 
 def distort(xy: Tensor, dist: Tensor) -> Tuple[Tensor, Tensor]:
     """Radial (+tangential) model and its validity limit, utils.py:36-69."""
-    ok = torch.ones(xy.shape[:-1], dtype=torch.bool)
+    ok = torch.ones(xy.shape[:-1], dtype=torch.bool, device=xy.device)
     out = xy
     if dist.numel() > 0:
         k1, k2 = dist[0], dist[1]
@@ -154,7 +159,7 @@ def sample_map(F: Tensor, uv: Tensor, pad: int = 1, grads: bool = False):
     val = gs(g)
     if not grads:
         return val, mask, None
-    step = torch.eye(2, dtype=uv.dtype) / span * 2
+    step = torch.eye(2, dtype=uv.dtype, device=uv.device) / span * 2
     fx0, fx1 = gs(g - step[0]), gs(g + step[0])
     fy0, fy1 = gs(g - step[1]), gs(g + step[1])
     dF = torch.stack([(fx1 - fx0) / 2, (fy1 - fy0) / 2], -1)        # N x C x 2
@@ -189,7 +194,7 @@ def residual_jacobian(R: Tensor, t: Tensor, cam: Tensor, p3d: Tensor, F_ref: Ten
         w_unc = (W_ref * cq)[..., 0].masked_fill(~valid, 0.0)       # costs.py:27-32
     res = Fp - F_ref                                                # costs.py:41
     # d p_cam / d delta = [ I | -hat(p_cam) ]   wrappers.py:195-203
-    J_pose = torch.cat([torch.eye(3).expand(p_cam.shape[0], 3, 3), -hat(p_cam)], -1)
+    J_pose = torch.cat([torch.eye(3, dtype=p_cam.dtype, device=p_cam.device).expand(p_cam.shape[0], 3, 3), -hat(p_cam)], -1)
     J_uv = world_to_image_jacobian(cam, p_cam) @ J_pose             # N x 2 x 6
     J = dF @ J_uv                                                   # N x C x 6
     return res, valid, w_unc, J, uv
@@ -210,12 +215,13 @@ def damped_solve(g: Tensor, H: Tensor, lam: Tensor, ok: bool, eps: float = 1e-6)
     `refine_query_pose` turns into success=False; the oracle returns None."""
     H = H + torch.diag_embed((torch.diagonal(H) * lam).clamp(min=eps))
     if not ok:
-        H, g = torch.eye(6), torch.zeros(6)
+        H, g = torch.eye(6).to(H), torch.zeros(6).to(g)
+    H_, g_ = H.cpu(), g.cpu()             # optimization.py:33: the factorisation runs on the host, also for CUDA tensors
     try:
-        L = torch.linalg.cholesky(H)
+        L = torch.linalg.cholesky(H_)
     except RuntimeError:
         return None
-    return -torch.cholesky_solve(g[:, None], L)[:, 0]
+    return (-torch.cholesky_solve(g_[:, None], L)[:, 0]).to(H.device)
 
 
 def damping_lambda(const: Tensor, log_range=(-6.0, 5.0)) -> Tensor:
@@ -291,7 +297,7 @@ def sample_reference(maps: Sequence[Tensor], scales: Sequence[Tuple[float, float
     coordinates to the map dtype only for the interpolation
     (`p2d_feat.to(feats)`, :349-351): pass float64 cam/R/t/p3d to get that."""
     p_cam = p3d @ R.t() + t
-    obs, keep = [], torch.ones(p3d.shape[0], dtype=torch.bool)
+    obs, keep = [], torch.ones(p3d.shape[0], dtype=torch.bool, device=p3d.device)
     for Fm, sc in zip(maps, scales):
         uv, vis = world_to_image(scale_camera(cam, sc), p_cam)
         val, inb, _ = sample_map(Fm, uv.to(Fm.dtype), pad)

@@ -81,15 +81,18 @@ def resize_max_edge(image: np.ndarray, target: int) -> Tuple[np.ndarray, Tuple[f
     return cv2.resize(image, (w2, h2), interpolation=cv2.INTER_LINEAR), (s, s)
 
 
-def extract(sd: Dict[str, Tensor], image: np.ndarray, scale_image: int = 1, resize: int = 1024):
+def extract(sd: Dict[str, Tensor], image: np.ndarray, scale_image: int = 1, resize: int = 1024, device=None):
     """PixTrackFeatureExtractor.__call__ (feature_extractor.py:34-59): resize
     only if the longer edge exceeds resize//scale_image; /255; HWC->CHW;
-    returns (features [C,H,W] list, scales list, confidences [1,H,W] list)."""
+    returns (features [C,H,W] list, scales list, confidences [1,H,W] list).
+    `device`: where the network runs (`image_tensor.to(self.device)`, :47); `sd` must live there."""
     sr = (1.0, 1.0)
-    target = resize // scale_image
-    if max(image.shape[:2]) > target:
+    target = resize // scale_image if resize is not None else None
+    if resize is not None and max(image.shape[:2]) > target:
         image, sr = resize_max_edge(image, target)
     x = torch.from_numpy(np.ascontiguousarray(image.transpose(2, 0, 1)) / 255.).float()[None]
+    if device is not None:
+        x = x.to(device)
     feats, confs = unet_forward(sd, x)
     scales = [(sr[0] / 2 ** s, sr[1] / 2 ** s) for s in OUTPUT_SCALES]
     return [f[0] for f in feats], scales, [c[0] for c in confs]

@@ -89,6 +89,9 @@ SYMBOLS = {
     'ptk_conv_f16': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_void_p, C.c_void_p]),
+    'ptk_conv_f16_pool': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ptk_extractor_create': (C.c_int, [C.c_void_p, C.POINTER(UnetWeights), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     'ptk_extractor_destroy': (None, [C.c_void_p]),
     'ptk_extractor_level_shape': (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_i32p, c_i32p]),

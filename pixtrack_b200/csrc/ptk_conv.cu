@@ -988,7 +988,7 @@ static int pick_block_n(int Cout, int m_tiles, int num_sms) {
 }
 
 // ptk_conv_f16 plus an optional fused 2x2 max pool of the result (the extractor plan's encoder blocks)
-int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
+extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
                       int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
                       int32_t Cout, int32_t taps, int32_t relu, void* out, void* pool_out, void* stream) {
   PTK_REQUIRE(ctx && in0 && weights && bias && out, "null argument");

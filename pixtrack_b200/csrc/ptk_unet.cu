@@ -11,12 +11,6 @@
 
 #include "ptk_common.cuh"
 
-extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H,
-                            int32_t W, int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights,
-                            const float* bias, int32_t Cout, int32_t taps, int32_t relu, void* out, void* stream);
-int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
-                      int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
-                      int32_t Cout, int32_t taps, int32_t relu, void* out, void* pool_out, void* stream);
 
 namespace {
 

@@ -65,21 +65,23 @@ def pack_weights(sd: Dict[str, Tensor], device) -> Dict[str, List[Tensor]]:
 
 
 def conv_f16(x0: Tensor, weights: Tensor, bias: Tensor, relu: bool = True, x1: Optional[Tensor] = None,
-             out_hw: Optional[Tuple[int, int]] = None, taps: int = 9) -> Tensor:
+             out_hw: Optional[Tuple[int, int]] = None, taps: int = 9, pool: bool = False):
     """One tcgen05 convolution layer (test / building-block entry).  x0 [H0,W0,C0] fp16 channels-last,
     optional x1 [H1,W1,C1]; weights fp16 [taps][C_out][C0+C1]; returns fp16 [H,W,C_out] with
-    (H, W) = out_hw or x0's size (larger inputs are cropped to it)."""
+    (H, W) = out_hw or x0's size (larger inputs are cropped to it).  pool=True also returns the fused 2x2 max pool
+    [H//2, W//2, C_out] (the encoder's nn.MaxPool2d written by the epilogue): (out, pooled)."""
     assert x0.is_cuda and x0.dtype == torch.float16 and x0.is_contiguous()
     H, W = out_hw if out_hw is not None else x0.shape[:2]
     Cout = weights.shape[1]
     out = torch.empty((H, W, Cout), dtype=torch.float16, device=x0.device)
+    pooled = torch.empty((H // 2, W // 2, Cout), dtype=torch.float16, device=x0.device) if pool else None
     dev = x0.device.index if x0.device.index is not None else torch.cuda.current_device()
-    _lib.check(_lib.load().ptk_conv_f16(
+    _lib.check(_lib.load().ptk_conv_f16_pool(
         _lib.context(dev), x0.data_ptr(), x0.shape[2], None if x1 is None else x1.data_ptr(),
         0 if x1 is None else x1.shape[2], H, W, x0.shape[0], x0.shape[1], 0 if x1 is None else x1.shape[0],
         0 if x1 is None else x1.shape[1], weights.data_ptr(), bias.data_ptr(), Cout, taps, 1 if relu else 0,
-        out.data_ptr(), _lib.current_stream_ptr(x0.device)))
-    return out
+        out.data_ptr(), None if pooled is None else pooled.data_ptr(), _lib.current_stream_ptr(x0.device)))
+    return (out, pooled) if pool else out
 
 
 class _Plan:

@@ -26,6 +26,22 @@ def _as_tensor(x, like: Tensor = None) -> Tensor:
     return x
 
 
+def rotation_angle(Ra: Tensor, Rb: Tensor) -> Tensor:
+    """Geodesic angle in radians between rotations [...,3,3], accurate near zero: atan2(|vee(M - M^T)| / 2,
+    (tr M - 1) / 2) with M = Ra Rb^T in float64.  (acos of the trace alone -- Pose.magnitude, wrappers.py:208-218 -- has
+    a noise floor of sqrt(2 eps) = 3e-4..5e-4 rad on float32 matrices, far above the 1e-4 rad parity bound.)"""
+    M = Ra.double() @ Rb.double().transpose(-1, -2)
+    v = torch.stack([M[..., 2, 1] - M[..., 1, 2], M[..., 0, 2] - M[..., 2, 0], M[..., 1, 0] - M[..., 0, 1]], -1)
+    return torch.atan2(0.5 * v.norm(dim=-1), 0.5 * (M.diagonal(dim1=-2, dim2=-1).sum(-1) - 1.0))
+
+
+def pose_distance(Ta: Tensor, Tb: Tensor) -> Tuple[Tensor, Tensor]:
+    """(rotation angle in rad, translation distance) between 12-vectors [R row-major, t]."""
+    Ta, Tb = Ta.double(), Tb.double()
+    return (rotation_angle(Ta[..., :9].reshape(Ta.shape[:-1] + (3, 3)), Tb[..., :9].reshape(Tb.shape[:-1] + (3, 3))),
+            (Ta[..., 9:] - Tb[..., 9:]).norm(dim=-1))
+
+
 class _Wrapper:
     def __init__(self, data: Tensor):
         self._data = _as_tensor(data)

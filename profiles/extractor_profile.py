@@ -8,7 +8,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pixtrack_b200 import synthetic as syn  # noqa: E402
+import os as _os, sys as _sys  # noqa: E401,E402
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), 'tests'))  # scene generators live with the tests
+import synthetic as syn  # noqa: E402
 from pixtrack_b200.extractor import B200FeatureExtractor  # noqa: E402
 
 torch.set_grad_enabled(False)

@@ -1,6 +1,8 @@
 import sys; sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np, torch
-from pixtrack_b200 import synthetic as syn
+import os as _os, sys as _sys  # noqa: E401,E402
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), 'tests'))  # scene generators live with the tests
+import synthetic as syn  # noqa: E402
 from pixtrack_b200.nerf import NerfTestbed, occupancy_bitfield
 sc = syn.nerf_scene(11, 2)
 bits = occupancy_bitfield(sc['density_grid'], sc['max_cascade'])

@@ -10,7 +10,9 @@ import os, sys, json, time
 import numpy as np, torch, torch.nn.functional as tF
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import lm, unet
-from pixtrack_b200 import synthetic as syn
+import os as _os, sys as _sys  # noqa: E401,E402
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))), 'tests'))  # scene generators live with the tests
+import synthetic as syn  # noqa: E402
 
 torch.set_grad_enabled(False)
 STOP = dict(num_iters=150, grad_stop=1e-4, dt_stop=5e-3, dR_stop=5e-2)

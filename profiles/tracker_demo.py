@@ -14,7 +14,9 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
-from pixtrack_b200 import synthetic as syn  # noqa: E402
+import os as _os, sys as _sys  # noqa: E401,E402
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), 'tests'))  # scene generators live with the tests
+import synthetic as syn  # noqa: E402
 from pixtrack_b200.extractor import B200FeatureExtractor  # noqa: E402
 from pixtrack_b200.geometry import Camera  # noqa: E402
 from pixtrack_b200.nerf import NerfTestbed, get_nerf_image, occupancy_bitfield  # noqa: E402

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import torch
 
-from pixtrack_b200 import synthetic as syn
+import synthetic as syn
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 

@@ -12,7 +12,7 @@ interp_sparse_observations`, `BaseRefiner.refine_pose_using_features`,
 `UNet._forward`, `PixTrackFeatureExtractor.__call__`.
 
 Inputs are NOT stored (a 640x480x16 map is 20 MB): tests regenerate them from
-`pixtrack_b200.synthetic` with the seeds recorded here; each fixture carries
+`tests/synthetic.py` with the seeds recorded here; each fixture carries
 an input checksum so RNG drift is detected instead of mis-reported as a
 parity failure.  Stand-ins used to import the reference: `omegaconf` (this
 directory), empty `h5py`, `torch._six.string_classes`; torchvision's vgg19 is
@@ -53,7 +53,9 @@ from pixtrack.localization.pixloc_pose_refiners import PoseTrackerRefiner  # noq
 from pixtrack.localization.feature_extractor import PixTrackFeatureExtractor  # noqa: E402
 from pixtrack.localization.tracker import DebugTracker  # noqa: E402
 
-from pixtrack_b200 import synthetic as syn  # noqa: E402
+import os as _os, sys as _sys  # noqa: E401,E402
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))), 'tests'))  # scene generators live with the tests
+import synthetic as syn  # noqa: E402
 
 
 def checksum(*tensors):

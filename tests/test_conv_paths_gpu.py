@@ -1,0 +1,114 @@
+"""GPU: every tcgen05 convolution kernel path the 1024x576 / 1008x756 extractor plans dispatch to, in isolation,
+against an fp32 convolution of the SAME fp16-rounded operands (so the only differences are the fp32 summation order
+and the fp16 rounding of the output).
+
+Dispatch (pixtrack_b200/csrc/ptk_conv.cu, ptk_conv_f16_pool): the persistent halo kernel conv_halo_kernel<N>,
+N = 32 / 64 / 128, takes 3x3 layers whose 16x16 tiles fill >= 80 % of their last wave of 148 SMs -- the shapes below
+are chosen to land there (143 tiles of 16x16 for 170x200 / 171x203 maps) with ragged right / bottom tiles; everything
+else goes to conv_tc_kernel.  The benchmark's plans use: halo<64> (64->64 full resolution, pooled), halo<128>
+(128/256-channel blocks, pooled, several C_out groups), halo<32> with two inputs (last decoder block: 64 upsampled +
+64 skip channels -> 32), halo<64> with two inputs (decoder 64+128 -> 64), and the fused 2x2 max pool on odd sizes
+(the 1008x756 plan pools 189 -> 94).
+"""
+import pytest
+import torch
+import torch.nn.functional as tF
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+D = 'cuda:0'
+
+
+def _ref(x, w, b, relu, x1=None, hw=None):
+    H, W = hw if hw else x.shape[:2]
+    xs = [x.float().permute(2, 0, 1)[None][:, :, :H, :W]]
+    if x1 is not None:
+        xs.append(x1.float().permute(2, 0, 1)[None][:, :, :H, :W])
+    y = tF.conv2d(torch.cat(xs, 1), w.float(), b, padding=1)
+    return tF.relu(y) if relu else y
+
+
+def _case(cin, cout, H, W, seed, cin1=0, grow=(0, 0)):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(H, W, cin, generator=g).half().to(D)
+    x1 = torch.randn(H + grow[0], W + grow[1], cin1, generator=g).half().to(D) if cin1 else None
+    w = (torch.randn(cout, cin + cin1, 3, 3, generator=g) / (3 * (cin + cin1) ** 0.5)).half().to(D)
+    b = torch.randn(cout, generator=g).to(D)
+    return x, x1, w, b
+
+
+def _check(y, ref_nchw, what):
+    ref = ref_nchw[0].permute(1, 2, 0)
+    err = (y.float() - ref).abs().max().item()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item()), (what, err)
+
+
+# (cin, cout, H, W): 11 x 13 = 143 tiles of 16x16 (x C_out / 128 groups) -> halo kernel; ragged edges on both axes
+HALO_SHAPES = [
+    (64, 32, 170, 200),      # conv_halo_kernel<32>
+    (64, 64, 170, 200),      # conv_halo_kernel<64>, weights resident in shared memory
+    (128, 128, 170, 200),    # conv_halo_kernel<128>, weights resident
+    (128, 256, 170, 200),    # conv_halo_kernel<128>, two C_out groups (286 tiles = 2 waves), weights streamed
+    (256, 256, 171, 203),    # conv_halo_kernel<128>, 4 K chunks, odd sizes
+    (192, 64, 172, 198),     # 3 K chunks
+]
+
+
+@pytest.mark.parametrize('cin,cout,H,W', HALO_SHAPES)
+@pytest.mark.parametrize('relu', [True, False])
+def test_halo_kernels_single_input(cin, cout, H, W, relu):
+    from pixtrack_b200.extractor import conv_f16, pack_conv3x3
+    x, _, w, b = _case(cin, cout, H, W, seed=cin * 11 + cout)
+    y = conv_f16(x, pack_conv3x3(w), b, relu=relu)
+    torch.cuda.synchronize()
+    _check(y, _ref(x, w, b, relu), (cin, cout, H, W))
+
+
+@pytest.mark.parametrize('cin,cout,H,W', [(64, 64, 170, 200), (128, 128, 170, 200), (128, 256, 171, 203),
+                                          (64, 64, 189, 252),      # the 1008x756 plan's odd 189 -> 94 pool
+                                          (64, 128, 40, 56)])       # small map: conv_tc_kernel 16x8 tiles + pool
+def test_fused_max_pool(cin, cout, H, W):
+    from pixtrack_b200.extractor import conv_f16, pack_conv3x3
+    x, _, w, b = _case(cin, cout, H, W, seed=cin * 13 + cout + H)
+    y, p = conv_f16(x, pack_conv3x3(w), b, relu=True, pool=True)
+    torch.cuda.synchronize()
+    ref = _ref(x, w, b, True)
+    _check(y, ref, 'conv')
+    # the pool is taken of the fp16-rounded outputs (max commutes with rounding): exact against pooling `y`
+    want = tF.max_pool2d(y.float().permute(2, 0, 1)[None], 2, 2)[0].permute(1, 2, 0)
+    assert tuple(p.shape) == (H // 2, W // 2, cout)
+    assert torch.equal(p.float(), want)
+
+
+@pytest.mark.parametrize('cin0,cin1,cout,H,W,grow', [
+    (64, 64, 32, 170, 200, (0, 0)),       # last decoder block: halo<32>, upsampled + skip
+    (64, 128, 64, 170, 200, (1, 1)),      # decoder block 2: halo<64>, skip one row / column larger (cropped)
+    (64, 256, 64, 171, 203, (1, 0)),      # decoder block 1 shape class on a big map
+    (128, 128, 128, 170, 200, (0, 3)),    # halo<128> with a second input
+])
+def test_halo_kernels_two_inputs_with_crop(cin0, cin1, cout, H, W, grow):
+    from pixtrack_b200.extractor import conv_f16, pack_conv3x3
+    x, x1, w, b = _case(cin0, cout, H, W, seed=cin0 + cin1 * 3 + cout, cin1=cin1, grow=grow)
+    y = conv_f16(x, pack_conv3x3(w), b, relu=True, x1=x1, out_hw=(H, W))
+    torch.cuda.synchronize()
+    _check(y, _ref(x, w, b, True, x1=x1, hw=(H, W)), (cin0, cin1, cout))
+
+
+def test_benchmark_layer_shapes_at_full_resolution():
+    """The two most expensive launches of the 1024x576 plan at their real size: 64->64 (pooled) and the two-input
+    128->32 decoder conv at 576x1024, checked on a random subset of rows (the fp32 reference conv of the whole map is
+    evaluated on the GPU by cuDNN in fp32 with TF32 disabled)."""
+    from pixtrack_b200.extractor import conv_f16, pack_conv3x3
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        H, W = 576, 1024
+        x, _, w, b = _case(64, 64, H, W, seed=101)
+        y, p = conv_f16(x, pack_conv3x3(w), b, relu=True, pool=True)
+        _check(y, _ref(x, w, b, True), 'enc0.1')
+        assert torch.equal(p.float(), tF.max_pool2d(y.float().permute(2, 0, 1)[None], 2, 2)[0].permute(1, 2, 0))
+        x, x1, w, b = _case(64, 32, H, W, seed=102, cin1=64)
+        y = conv_f16(x, pack_conv3x3(w), b, relu=True, x1=x1, out_hw=(H, W))
+        _check(y, _ref(x, w, b, True, x1=x1, hw=(H, W)), 'dec3')
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import lm as olm, nerf as onerf, unet as ounet
-from pixtrack_b200 import synthetic as syn
+import synthetic as syn
 import cases
 
 pytestmark = pytest.mark.gpu

@@ -125,7 +125,8 @@ def test_geometry_wrappers():
 def test_install_and_adapters_fail_loudly_without_cuda():
     """install() on a reference-shaped localizer must raise instead of leaving the PyTorch path in place."""
     from types import SimpleNamespace
-    from pixtrack_b200 import _lib, synthetic as syn
+    import synthetic as syn
+    from pixtrack_b200 import _lib
     from pixtrack_b200.install import install
     from pixtrack_b200.nerf import NerfTestbed
     from pixtrack_b200.mask import query_mask

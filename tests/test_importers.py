@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 import torch
 
-from pixtrack_b200 import importers, synthetic as syn
+import synthetic as syn
+from pixtrack_b200 import importers
 
 
 def _checkpoint():

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import cases
-from pixtrack_b200 import synthetic as syn
+import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import nerf as onerf
-from pixtrack_b200 import synthetic as syn
+import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 from oracle import nerf
-from pixtrack_b200 import synthetic as syn
+import synthetic as syn
 
 f32 = np.float32
 

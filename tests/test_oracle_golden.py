@@ -6,7 +6,7 @@ import torch
 
 import cases
 from oracle import lm, unet
-from pixtrack_b200 import synthetic as syn
+import synthetic as syn
 
 torch.set_grad_enabled(False)
 

@@ -1,54 +1,66 @@
 """GPU: the whole per-frame hot path (FrameTracker: two extractions, reference sampling, 3-level LM chain, optional
 device-side mask) against the CPU oracle pipeline on the same frame.
 
-The LM alone is held to 1e-4 rad / 1e-3 on identical feature maps (tests/test_lm_parity_gpu.py).  End to end the
-extractor runs on fp16 tensor-core operands while the oracle UNet is fp32, which perturbs the features by ~1e-2
-relative and moves the optimum slightly: the poses of the two pipelines are required to agree within 2e-3 rad and
-2e-3 translation units (about 10x below the distance of either to the ground truth on this noisy scene), the
-iteration counts within +-1, and nothing may fail.
+Tolerance = the bound BASELINE.json's north_star states: 1e-4 rad rotation / 1e-3 translation units between the
+pose of the B200 pipeline and of the fp32 oracle pipeline on identical inputs, END TO END -- i.e. including the
+extractor, which runs on fp16 tensor-core operands with fp32 accumulation while the oracle UNet is fp32.  That
+perturbs the descriptors by ~1e-3 of their norm; the pose moves by 1e-7 .. 1e-6 rad (measured on the CPU by emulating
+the operand rounding inside the oracle, profiles/r2/precision_study.py, and on the GPU by bench.py's `parity`
+block), 100x inside the bound.  Iteration counts must be equal and nothing may fail.  The rotation difference is
+measured with atan2 of the skew part (geometry.rotation_angle): acos of the trace has a 3e-4 rad noise floor on
+float32 matrices, which is what round 1's 2e-3 tolerance had been absorbing.
 """
 import numpy as np
 import pytest
 import torch
 
 from oracle import lm, unet
-from pixtrack_b200 import synthetic as syn
+import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 STOP = dict(num_iters=150, grad_stop=1e-4, dt_stop=5e-3, dR_stop=5e-2)
 N_VIEWS, N = 3, 800
 
 
+ROT_TOL, TRANS_TOL = 1e-4, 1e-3      # north_star: 1e-4 rad / 1e-3 translation units
+
+
 def _rot_angle(Ra, Rb):
-    c = ((Ra @ Rb.transpose(-1, -2)).diagonal(dim1=-2, dim2=-1).sum(-1) - 1) / 2
-    return torch.acos(c.clamp(-1, 1))
+    from pixtrack_b200.geometry import rotation_angle
+    return rotation_angle(Ra, Rb)
 
 
-def _setup(overlap=True):
+def _setup(overlap=True, n=N, n_views=N_VIEWS, query_wh=(640, 360), ref_wh=(448, 336), seed=7):
     from pixtrack_b200.extractor import B200FeatureExtractor
     from pixtrack_b200.pipeline import FrameTracker
     dev = torch.device('cuda:0')
-    seq = syn.tracked_sequence(7, n_frames=1, N=N, n_views=N_VIEWS, query_wh=(640, 360), ref_wh=(448, 336))
+    seq = syn.tracked_sequence(seed, n_frames=1, N=n, n_views=n_views, query_wh=query_wh, ref_wh=ref_wh)
     sd = syn.unet_weights(0)
     ext = B200FeatureExtractor(sd, dev)
     lam = lm.damping_lambda(torch.zeros(6))
     fr = seq['frames'][0]
-    trk = FrameTracker(ext, fr['img_q'].shape[:2], seq['cam_q'], seq['p3d'], [lam.to(dev)] * 3, N_VIEWS,
+    trk = FrameTracker(ext, fr['img_q'].shape[:2], seq['cam_q'], seq['p3d'], [lam.to(dev)] * 3, n_views,
                        overlap_reference=overlap, **STOP)
     return dev, seq, sd, lam, fr, trk
 
 
 def _run(trk, dev, seq, fr, mask_depth=None):
     T_ref = torch.cat([fr['R_r'].reshape(-1), fr['t_r']])
-    for v in range(N_VIEWS):
+    for v in range(trk.B):
         trk.refresh_reference(v, fr['img_r'].to(dev), seq['cam_r'], T_ref)
     T, failed = trk.track(fr['img_q'].to(dev), fr['T_init'].to(dev), mask_depth=mask_depth)
     torch.cuda.synchronize()
     return T.clone(), failed.clone(), [n.clone() for n in trk.plan.n_iters]
 
 
-def test_frame_tracker_matches_the_oracle_pipeline():
-    dev, seq, sd, lam, fr, trk = _setup()
+@pytest.mark.parametrize('size', ['small', 'c2'])
+def test_frame_tracker_matches_the_oracle_pipeline(size):
+    """small: 640x360 query, 448x336 reference view, N=800, 3 views.  c2: the benchmarked configuration -- 1920x1080
+    query (1024x576 network), 1008x756 reference view, N=5000, B=8 views (about 10 s of oracle time)."""
+    if size == 'small':
+        dev, seq, sd, lam, fr, trk = _setup()
+    else:
+        dev, seq, sd, lam, fr, trk = _setup(n=5000, n_views=8, query_wh=(1920, 1080), ref_wh=(1008, 756), seed=100)
     T, failed, n_it = _run(trk, dev, seq, fr)
     assert not bool(failed.any())
     # oracle: the reference's per-frame path restated on the CPU (bench.py's CpuFrame does the same)
@@ -58,20 +70,21 @@ def test_frame_tracker_matches_the_oracle_pipeline():
     fq, sc_q, cf_q = unet.extract(sd, fr['img_q'].numpy().astype(np.float32))
     maps_q = [torch.cat([f, c], 0) for f, c in zip(fq, cf_q)]
     assert int(trk.valid[0].sum()) == int(keep.sum())              # same points kept by the reference sampler
-    for v in range(N_VIEWS):
+    worst = [0.0, 0.0]
+    for v in range(trk.B):
         T0 = fr['T_init'][v]
         out = lm.refine_levels(maps_q, sc_q, seq['cam_q'].float(), T0[:9].reshape(3, 3), T0[9:], [o[keep] for o in obs],
                                seq['p3d'][keep].float(), [lam] * 3, **STOP)
         assert out['success']
         Tg = T[v].cpu()
-        dR = float(_rot_angle(Tg[:9].reshape(3, 3).double(), out['R'].double()))
+        dR = float(_rot_angle(Tg[:9].reshape(3, 3), out['R']))
         dt = float((Tg[9:].double() - out['t'].double()).norm())
-        assert dR < 2e-3 and dt < 2e-3, (v, dR, dt)
-        gt_R = float(_rot_angle(out['R'].double(), fr['R_q']))
-        assert dR < 0.5 * max(gt_R, 1e-3) or dR < 5e-4            # far inside the distance to the ground truth
+        assert dR < ROT_TOL and dt < TRANS_TOL, (v, dR, dt)
+        worst = [max(worst[0], dR), max(worst[1], dt)]
         its = [int(n[v]) for n in n_it]
         ref_its = [r['n_iters'] for r in out['runs']]
-        assert all(abs(a - b) <= 1 for a, b in zip(its, ref_its)), (its, ref_its)
+        assert its == ref_its, (its, ref_its)
+    print(f'[{size}] worst pose difference to the fp32 oracle pipeline: {worst[0]:.2e} rad, {worst[1]:.2e}')
     from pixtrack_b200 import _lib
     _lib.device_status(0)
 

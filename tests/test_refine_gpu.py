@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as tF
 
 import cases
-from pixtrack_b200 import synthetic as syn
+import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
