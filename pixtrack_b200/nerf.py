@@ -197,12 +197,18 @@ class NerfTestbed:
         return v
 
     def render_device(self, width: int, height: int, spp: int = 8, want_rgba: bool = True, want_u8: bool = False,
-                      want_depth: bool = False):
+                      want_depth: bool = False, out_u8: Optional[torch.Tensor] = None):
         """Stream-ordered render; returns (rgba float32 [H,W,4] | None, u8 [H,W,3] | None, depth | None) CUDA
-        tensors.  The uint8 image feeds FrameTracker.refresh_reference without leaving the device."""
+        tensors.  The uint8 image feeds FrameTracker.refresh_reference without leaving the device; `out_u8` is a
+        caller-owned [H,W,3] uint8 buffer to render into (a static address lets the extractor replay its plan graph)."""
         v = self._view(width, height, spp)
         rgba = torch.empty((height, width, 4), dtype=torch.float32, device=self.device) if want_rgba else None
-        u8 = torch.empty((height, width, 3), dtype=torch.uint8, device=self.device) if want_u8 else None
+        if out_u8 is not None:
+            assert out_u8.is_cuda and out_u8.dtype == torch.uint8 and out_u8.is_contiguous()
+            assert tuple(out_u8.shape) == (height, width, 3)
+            u8 = out_u8
+        else:
+            u8 = torch.empty((height, width, 3), dtype=torch.uint8, device=self.device) if want_u8 else None
         dep = torch.empty((height, width), dtype=torch.float32, device=self.device) if want_depth else None
         _lib.check(self._lib.ptk_nerf_render(self._h, C.byref(v), None if rgba is None else rgba.data_ptr(),
                                              None if u8 is None else u8.data_ptr(),

@@ -295,7 +295,8 @@ def render_plane(tex: Tensor, cam: Tensor, R: Tensor, t: Tensor, half_extent: fl
 
 
 def tracked_sequence(seed: int, n_frames: int = 4, N: int = 5000, n_views: int = 8, query_wh=(1920, 1080),
-                     ref_wh=(1008, 756), rot_deg: float = 1.0, trans: float = 0.005) -> Dict:
+                     ref_wh=(1008, 756), rot_deg: float = 1.0, trans: float = 0.005, cam_q: Optional[Tensor] = None,
+                     cam_r: Optional[Tensor] = None) -> Dict:
     """A short tracked sequence with REAL pixels (BASELINE config 2 restated): one textured
     plane carrying N model points, and per frame a query image (1920x1080 camera frame) plus the
     reference-view render r9 makes at the previous pose estimate with the SfM camera x 0.5 (1008x756;
@@ -306,7 +307,8 @@ def tracked_sequence(seed: int, n_frames: int = 4, N: int = 5000, n_views: int =
     g = _gen(seed * 3 + 2)
     p = torch.zeros(N, 3, dtype=torch.float64)
     p[:, :2] = (torch.rand(N, 2, generator=g, dtype=torch.float64) - 0.5) * 0.5       # central 0.5 m square
-    cam_q, cam_r = pixtrack_camera(*query_wh), pixtrack_camera(*ref_wh)
+    cam_q = pixtrack_camera(*query_wh) if cam_q is None else cam_q.clone()      # cam_q / cam_r: explicit intrinsics
+    cam_r = pixtrack_camera(*ref_wh) if cam_r is None else cam_r.clone()        # (e.g. the YCB-Video camera, config C3)
     cam_q[6:] = 0
     cam_r[6:] = 0
     base = torch.rand(6, generator=g, dtype=torch.float64) - 0.5
