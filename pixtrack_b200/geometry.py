@@ -177,3 +177,49 @@ class Camera(_Wrapper):
             scales = (scales, scales)
         s = self._data.new_tensor(scales)
         return Camera(torch.cat([self.size * s, self.f * s, (self.c + 0.5) * s - 0.5, self.dist], -1))
+
+    # ---- host-side projection chain (interface of wrappers.py:299-355; not on the per-iteration path: the LM kernel and
+    #      the reference sampler carry their own copies in registers; this serves code that calls the Camera directly,
+    #      e.g. the reference's interp_sparse_observations, pixloc_pose_refiners.py:347) -------------------------------
+    eps = 1e-3                                                  # wrappers.py:225
+
+    def in_image(self, p2d: Tensor) -> Tensor:
+        """0 <= p <= size - 1 on the (float) camera size."""
+        p2d = _as_tensor(p2d, self._data)
+        hi = (self.size - 1).unsqueeze(-2)
+        return ((p2d >= 0) & (p2d <= hi)).all(-1)
+
+    def project(self, p3d: Tensor) -> Tuple[Tensor, Tensor]:
+        p3d = _as_tensor(p3d, self._data)
+        z = p3d[..., 2]
+        return p3d[..., :2] / z.clamp(min=self.eps).unsqueeze(-1), z > self.eps
+
+    def undistort(self, pts: Tensor) -> Tuple[Tensor, Tensor]:
+        """Applies the radial (+ tangential) model to normalised coordinates and flags points beyond the model's inflection
+        radius (utils.py:36-69; the reference calls this direction `undistort` too)."""
+        pts = _as_tensor(pts, self._data)
+        d = self.dist.unsqueeze(-2)
+        ok = torch.ones(pts.shape[:-1], dtype=torch.bool, device=pts.device)
+        if d.shape[-1] == 0:
+            return pts, ok
+        k1, k2 = d[..., 0:1], d[..., 1:2]
+        r2 = pts.pow(2).sum(-1, keepdim=True)
+        out = pts * (1 + k1 * r2 + k2 * r2 * r2)
+        disc = 9 * k1 * k1 - 20 * k2
+        bounded = ((k2 > 0) & (disc > 0)) | ((k2 <= 0) & (k1 > 0))
+        radius2 = torch.where(k2 > 0, (disc.clamp(min=0).sqrt() - 3 * k1) / (10 * k2), 1 / (3 * k1)).abs()
+        ok = ok & (~bounded | (r2 < radius2)).squeeze(-1)
+        if d.shape[-1] > 2:
+            p = d[..., 2:4]
+            out = out + 2 * p * pts.prod(-1, keepdim=True) + p.flip(-1) * (r2 + 2 * pts * pts)
+        return out, ok
+
+    def denormalize(self, p2d: Tensor) -> Tensor:
+        return _as_tensor(p2d, self._data) * self.f.unsqueeze(-2) + self.c.unsqueeze(-2)
+
+    def world2image(self, p3d: Tensor) -> Tuple[Tensor, Tensor]:
+        """Camera-frame 3-D points -> (pixel coordinates, valid = in front & inside the model's radius & inside the image)."""
+        xy, front = self.project(p3d)
+        xy, ok = self.undistort(xy)
+        uv = self.denormalize(xy)
+        return uv, front & ok & self.in_image(uv)

@@ -86,6 +86,22 @@ def test_context_creation_failure_raises_instead_of_deadlocking(monkeypatch):
     assert 0 not in _lib._contexts
 
 
+def test_camera_world2image_matches_the_reference_fixture():
+    """Camera.world2image of the product (host side) on the points / cameras the unmodified reference was run on
+    (tests/golden/geometry.npz: pinhole, radial +/-, tangential)."""
+    import cases
+    from pixtrack_b200.geometry import Camera
+    g = cases.gold('geometry')
+    pc = torch.from_numpy(g['pc'])
+    for tag, dist in (('d0', []), ('d2', [0.1, 0.01]), ('d2n', [-0.2, 0.05]), ('d4', [0.15, -0.3, 0.002, -0.001])):
+        cam = Camera(torch.tensor([640., 480., 300., 350., 320., 240.] + dist))
+        uv, valid = cam.world2image(pc)
+        assert np.array_equal(valid.numpy(), g[f'{tag}_valid'])
+        np.testing.assert_allclose(uv.numpy()[g[f'{tag}_valid']], g[f'{tag}_uv'][g[f'{tag}_valid']], rtol=2e-6, atol=2e-4)
+        uv64, valid64 = Camera(cam._data.double()).world2image(pc.double().numpy())      # numpy in, float64 chain
+        assert uv64.dtype == torch.float64 and np.array_equal(valid64.numpy(), g[f'{tag}_valid'])
+
+
 def test_product_package_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, 'pixtrack_b200')):
         for f in files:
