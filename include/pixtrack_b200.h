@@ -318,6 +318,9 @@ void ptk_nerf_destroy(PtkNerf* n);
 int64_t ptk_nerf_grid_entries(int32_t aabb_scale);
 int ptk_nerf_render(PtkNerf* n, const PtkNerfView* view, float* out_rgba, uint8_t* out_u8, float* out_depth,
                     void* stream);
+/* SYNCHRONISING statistics of the last render of `n` (benchmarks): out4 = network samples evaluated, warp steps,
+ * rays marched (those that reach an occupied cell), lane slots that sat out a warp step. */
+int ptk_nerf_stats(PtkNerf* n, uint64_t* out4);
 
 /* ------------------------------------------------------------------------
  * Query-frame object mask.

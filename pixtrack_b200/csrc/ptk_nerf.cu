@@ -93,6 +93,7 @@ struct NerfParams {
   float* starts;                 // [spp][H*W] first sample position of every ray, < 0: the ray is dead (nerf_start_kernel)
   float4* frames;                // [spp][H*W] shaded result of every live ray (nerf_render_kernel -> nerf_resolve_kernel)
   float* frame_depth;            // [H*W] depth of the last sample-per-pixel ray
+  unsigned long long* stats;     // [4] network samples, warp steps, rays marched, lanes that sat out a warp step
 };
 
 struct V3 {
@@ -573,6 +574,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_c
   ry.pix = -1;
   ry.alive = false;
   bool exhausted = false;
+  unsigned st_samples = 0, st_steps = 0, st_rays = 0;   // per-warp statistics (identical in every lane; lane 0 reports)
 
   while (true) {
     // ---- take new rays until every lane has a live one or the queue is empty.  The work unit is a (pixel, sample)
@@ -593,6 +595,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_c
           const int pix = (int)(mine / (unsigned)P.spp), sidx = (int)(mine - (unsigned)pix * (unsigned)P.spp);
           const float t = __ldg(P.starts + (size_t)sidx * (size_t)npix + pix);
           if (t >= 0.f) {
+            ++st_rays;
             float tentry;
             setup_ray(P, o, pix, ry.d, ry.id, tentry, ry.tu0, ry.tu1);
             ry.pix = pix;
@@ -620,6 +623,8 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_c
     }
     const unsigned sm = __ballot_sync(full, sample);
     if (sm != 0) {
+      st_samples += (unsigned)__popc(sm);
+      ++st_steps;
       // warp_position -> network input in the unit cube of the training box
       const float wx = (pos.x - P.tmin[0]) / (P.tmax[0] - P.tmin[0]);
       const float wy = (pos.y - P.tmin[1]) / (P.tmax[1] - P.tmin[1]);
@@ -675,6 +680,16 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_c
       ry.pix = -1;
     }
   }
+  {   // statistics of the render (ptk_nerf_stats): one set of atomics per warp at exit
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) st_rays += __shfl_xor_sync(full, st_rays, m);
+    if (lane == 0) {
+      atomicAdd(P.stats + 0, (unsigned long long)st_samples);
+      atomicAdd(P.stats + 1, (unsigned long long)st_steps);
+      atomicAdd(P.stats + 2, (unsigned long long)st_rays);
+      atomicAdd(P.stats + 3, (unsigned long long)st_steps * 32ull - (unsigned long long)st_samples);
+    }
+  }
 }
 
 }  // namespace
@@ -682,7 +697,7 @@ __global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_c
 struct PtkNerf {
   PtkContext* ctx;
   NerfParams base;
-  unsigned* counter;
+  unsigned* counter;             // [2 + 2 * 4]: ray queue counter, pad, statistics (4 x u64)
   float* starts;        // workspace of the largest render so far: per-ray frames, first-sample positions, depth
   size_t starts_cap;    // floats
   int aabb_scale;
@@ -773,7 +788,7 @@ extern "C" int ptk_nerf_create(PtkContext* ctx, const PtkNerfModel* m, PtkNerf**
     }
     free(host);
   }
-  cudaError_t e = cudaMalloc(&n->counter, sizeof(unsigned));
+  cudaError_t e = cudaMalloc(&n->counter, sizeof(unsigned) * 2 + sizeof(unsigned long long) * 4);
   if (e != cudaSuccess) {
     ptk_set_error("cudaMalloc: %s", cudaGetErrorString(e));
     free(n);
@@ -789,6 +804,15 @@ extern "C" void ptk_nerf_destroy(PtkNerf* n) {
   if (n->counter) cudaFree(n->counter);
   if (n->starts) cudaFree(n->starts);
   free(n);
+}
+
+// SYNCHRONISING: statistics of the last render on this object (benchmarks / profiles).
+extern "C" int ptk_nerf_stats(PtkNerf* n, uint64_t* out4) {
+  PTK_REQUIRE(n && out4, "null argument");
+  PtkDeviceGuard guard(n->ctx->device);
+  PTK_CUDA_CHECK(cudaDeviceSynchronize());
+  PTK_CUDA_CHECK(cudaMemcpy(out4, n->counter + 2, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost));
+  return PTK_OK;
 }
 
 extern "C" int64_t ptk_nerf_grid_entries(int32_t aabb_scale) {
@@ -839,6 +863,7 @@ extern "C" int ptk_nerf_render(PtkNerf* n, const PtkNerfView* v, float* out_rgba
   P.out_u8 = out_u8;
   P.out_depth = out_depth;
   P.counter = n->counter;
+  P.stats = reinterpret_cast<unsigned long long*>(n->counter + 2);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t npix = (size_t)v->width * v->height;
   const size_t need = npix * v->spp;
@@ -853,7 +878,7 @@ extern "C" int ptk_nerf_render(PtkNerf* n, const PtkNerfView* v, float* out_rgba
   P.frames = reinterpret_cast<float4*>(n->starts);           // 16-byte aligned start of the workspace
   P.starts = n->starts + 4 * need;
   P.frame_depth = P.starts + need;
-  PTK_CUDA_CHECK(cudaMemsetAsync(n->counter, 0, sizeof(unsigned), s));
+  PTK_CUDA_CHECK(cudaMemsetAsync(n->counter, 0, sizeof(unsigned) * 2 + sizeof(unsigned long long) * 4, s));
   nerf_start_kernel<<<(unsigned)(((size_t)v->width * v->height + 255) / 256), 256, 0, s>>>(P);
   int per_sm = 1;
   PTK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nerf_render_kernel, kThreads, kSmemBytes));

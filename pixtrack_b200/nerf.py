@@ -216,6 +216,12 @@ class NerfTestbed:
                                              _lib.current_stream_ptr(self.device)))
         return rgba, u8, dep
 
+    def last_stats(self) -> dict:
+        """Statistics of the last render (synchronises): network samples, warp steps, rays that reached the object."""
+        out = (C.c_uint64 * 4)()
+        _lib.check(self._lib.ptk_nerf_stats(self._h, out))
+        return dict(samples=int(out[0]), warp_steps=int(out[1]), rays=int(out[2]), idle_lane_steps=int(out[3]))
+
     def render(self, width: int, height: int, spp: int = 8, linear: bool = True) -> np.ndarray:
         """pyngp Testbed.render -> float32 [H,W,4] on the host (python_api.cu:127-173)."""
         if not linear:

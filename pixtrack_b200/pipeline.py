@@ -31,20 +31,45 @@ from .sampling import sample_reference
 Tensor = torch.Tensor
 
 
+def morton_order(xyz) -> torch.Tensor:
+    """Permutation that sorts points [N,3] along a 3-D Morton (Z-order) curve over their bounding box (10 bits per axis).
+    Points that are close in space become close in memory, hence close in the image under any pose: the LM kernel hands
+    contiguous index ranges to its CTAs and walks them in passes of 1024, so the 12-texel footprints of a pass overlap and
+    are served by the SM's L1 instead of L2 (the kernel is bound by L2 -> SM bandwidth at C = 128).  Sums
+    are order-independent up to rounding; the reference keeps COLMAP's dictionary order, which carries no meaning."""
+    x = torch.as_tensor(xyz, dtype=torch.float64).cpu()
+    if x.shape[0] == 0:
+        return torch.zeros(0, dtype=torch.long)
+    lo, hi = x.min(0).values, x.max(0).values
+    q = ((x - lo) / (hi - lo).clamp(min=1e-300) * 1023.0).round().clamp(0, 1023).to(torch.int64)
+
+    def spread(v):                       # 10 bits -> every third bit
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    return torch.argsort(code, stable=True)
+
+
 class FrameTracker:
     def __init__(self, extractor: B200FeatureExtractor, image_hw, camera: Tensor, p3d: Tensor, lams: Sequence[Tensor],
                  n_views: int, scale_image: int = 1, use_graph: bool = True, pad: int = 1,
-                 overlap_reference: bool = True, **lm_conf):
+                 overlap_reference: bool = True, sort_points: bool = True, **lm_conf):
         """camera: [n_cam] query camera at the IMAGE resolution; p3d [N,3] model points (float64 kept for
         the reference-side projection, float32 copy for the LM); lams[l] [6] damping per level;
-        lm_conf -> LmLaunch (num_iters, stop criteria)."""
+        lm_conf -> LmLaunch (num_iters, stop criteria).  sort_points: keep the points in Morton order on the device
+        (`self.order[i]` = caller's index of stored row i; poses do not depend on it beyond rounding)."""
         dev = extractor.device
         self.extractor, self.scale_image, self.B, self.pad = extractor, scale_image, n_views, pad
         ih, iw = image_hw
         H, W, sr = extractor.network_size(ih, iw, scale_image)
         shapes = extractor.plan(H, W).shapes
         N = p3d.shape[0]
-        self.p3d64 = p3d.to(dev, torch.float64).contiguous()
+        self.sort_points = sort_points
+        self.order = morton_order(p3d) if sort_points else torch.arange(N)
+        self.p3d64 = torch.as_tensor(p3d, dtype=torch.float64).cpu()[self.order].to(dev).contiguous()
         self.p3d32 = self.p3d64.float()
         # query pyramid (channels-last, L2-normalised by the fused head) + confidences
         self.feats = [torch.zeros((h, w, c), dtype=torch.float32, device=dev) for c, h, w in shapes]
@@ -75,7 +100,13 @@ class FrameTracker:
         n = int(xyz.shape[0])
         if n > self.p3d64.shape[0]:
             raise ValueError(f'{n} points exceed the capacity {self.p3d64.shape[0]} this tracker was built for')
-        src = torch.as_tensor(xyz, dtype=torch.float64).to(self.p3d64.device, non_blocking=True)
+        src = torch.as_tensor(xyz, dtype=torch.float64)
+        if self.sort_points:
+            self.order = morton_order(src)
+            src = src.cpu()[self.order]
+        else:
+            self.order = torch.arange(n)
+        src = src.to(self.p3d64.device, non_blocking=True)
         self.p3d64[:n].copy_(src)
         self.p3d32[:n].copy_(src)
         self.n_active = n

@@ -102,6 +102,19 @@ def test_camera_world2image_matches_the_reference_fixture():
         assert uv64.dtype == torch.float64 and np.array_equal(valid64.numpy(), g[f'{tag}_valid'])
 
 
+def test_morton_order_is_a_locality_preserving_permutation():
+    from pixtrack_b200.pipeline import morton_order
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(4096, 3, generator=g, dtype=torch.float64)
+    o = morton_order(x)
+    assert sorted(o.tolist()) == list(range(4096))
+    y = x[o]
+    # neighbours along the curve are close in space: mean step far below the mean distance of random pairs (0.66)
+    assert float((y[1:] - y[:-1]).norm(dim=1).mean()) < 0.15
+    assert float((x[1:] - x[:-1]).norm(dim=1).mean()) > 0.5
+    assert morton_order(torch.zeros(0, 3)).numel() == 0 and morton_order(torch.ones(5, 3)).tolist() == [0, 1, 2, 3, 4]
+
+
 def test_product_package_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, 'pixtrack_b200')):
         for f in files:

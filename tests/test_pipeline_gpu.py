@@ -30,7 +30,7 @@ def _rot_angle(Ra, Rb):
     return rotation_angle(Ra, Rb)
 
 
-def _setup(overlap=True, n=N, n_views=N_VIEWS, query_wh=(640, 360), ref_wh=(448, 336), seed=7):
+def _setup(overlap=True, n=N, n_views=N_VIEWS, query_wh=(640, 360), ref_wh=(448, 336), seed=7, **kw):
     from pixtrack_b200.extractor import B200FeatureExtractor
     from pixtrack_b200.pipeline import FrameTracker
     dev = torch.device('cuda:0')
@@ -40,7 +40,7 @@ def _setup(overlap=True, n=N, n_views=N_VIEWS, query_wh=(640, 360), ref_wh=(448,
     lam = lm.damping_lambda(torch.zeros(6))
     fr = seq['frames'][0]
     trk = FrameTracker(ext, fr['img_q'].shape[:2], seq['cam_q'], seq['p3d'], [lam.to(dev)] * 3, n_views,
-                       overlap_reference=overlap, **STOP)
+                       overlap_reference=overlap, **STOP, **kw)
     return dev, seq, sd, lam, fr, trk
 
 
@@ -97,6 +97,22 @@ def test_side_stream_overlap_does_not_change_results():
     c = _run(trk2, dev, seq, fr)
     assert torch.equal(a[0], b[0]) and torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
     assert all(torch.equal(x, y) for x, y in zip(a[2], c[2]))
+
+
+def test_morton_ordered_points_give_the_same_poses():
+    """The tracker stores the model points along a Morton curve (L1 locality of the LM gathers); only the summation order
+    changes: poses agree to float rounding with the caller's order, iteration counts are equal, the same points are kept."""
+    from pixtrack_b200.geometry import pose_distance
+    dev, seq, _, _, fr, trk = _setup(sort_points=True)
+    a = _run(trk, dev, seq, fr)
+    _, _, _, _, _, trk2 = _setup(sort_points=False)
+    b = _run(trk2, dev, seq, fr)
+    assert not torch.equal(trk.p3d64, trk2.p3d64) and torch.equal(trk.p3d64.cpu(), seq['p3d'][trk.order])
+    assert sorted(trk.order.tolist()) == list(range(N))
+    assert torch.equal(trk.valid.cpu(), trk2.valid.cpu()[:, trk.order])
+    dR, dt = pose_distance(a[0].cpu(), b[0].cpu())
+    assert float(dR.max()) < 2e-6 and float(dt.max()) < 2e-6, (float(dR.max()), float(dt.max()))
+    assert all(torch.equal(x, y) for x, y in zip(a[2], b[2]))
 
 
 def test_mask_hook_equals_masking_the_frame_first():
