@@ -35,8 +35,8 @@ def morton_order(xyz) -> torch.Tensor:
     """Permutation that sorts points [N,3] along a 3-D Morton (Z-order) curve over their bounding box (10 bits per axis).
     Points that are close in space become close in memory, hence close in the image under any pose: the LM kernel hands
     contiguous index ranges to its CTAs and walks them in passes of 1024, so the 12-texel footprints of a pass overlap and
-    are served by the SM's L1 instead of L2 (the kernel is bound by L2 -> SM bandwidth at C = 128).  Sums
-    are order-independent up to rounding; the reference keeps COLMAP's dictionary order, which carries no meaning."""
+    are served by the SM's L1 instead of L2 (measured effect: see FrameTracker's `sort_points`).  Sums are
+    order-independent up to rounding; the reference keeps COLMAP's dictionary order, which carries no meaning."""
     x = torch.as_tensor(xyz, dtype=torch.float64).cpu()
     if x.shape[0] == 0:
         return torch.zeros(0, dtype=torch.long)
@@ -56,11 +56,14 @@ def morton_order(xyz) -> torch.Tensor:
 class FrameTracker:
     def __init__(self, extractor: B200FeatureExtractor, image_hw, camera: Tensor, p3d: Tensor, lams: Sequence[Tensor],
                  n_views: int, scale_image: int = 1, use_graph: bool = True, pad: int = 1,
-                 overlap_reference: bool = True, sort_points: bool = True, **lm_conf):
+                 overlap_reference: bool = True, sort_points: bool = False, **lm_conf):
         """camera: [n_cam] query camera at the IMAGE resolution; p3d [N,3] model points (float64 kept for
         the reference-side projection, float32 copy for the LM); lams[l] [6] damping per level;
         lm_conf -> LmLaunch (num_iters, stop criteria).  sort_points: keep the points in Morton order on the device
-        (`self.order[i]` = caller's index of stored row i; poses do not depend on it beyond rounding)."""
+        (`self.order[i]` = caller's index of stored row i; poses do not depend on it beyond rounding).  Off by default:
+        measured on B200 (profiles/r2/lm_order.json + lm_*_ncu.json) it raises the L1 hit rate of the LM gathers from 3 %
+        to 33 % and cuts L2 -> SM traffic by 31 %, but the launch gets 4 % SLOWER (181 -> 188 us per iteration at
+        C = 128, N = 20000, B = 16): the kernel is bound by issue + latency at 16 warps per SM, not by that traffic."""
         dev = extractor.device
         self.extractor, self.scale_image, self.B, self.pad = extractor, scale_image, n_views, pad
         ih, iw = image_hw

@@ -25,6 +25,15 @@ KEEP = [
     'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'launch__waves_per_multiprocessor',
     'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers',
     'smsp__sass_inst_executed_op_local_ld.sum', 'smsp__sass_inst_executed_op_local_st.sum',
+    # memory-hierarchy detail (round 2): L1 hit rate, L1 / L2 sector counts, L2 -> SM bytes, stall reasons per issue
+    'l1tex__t_sector_hit_rate.pct', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
+    'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'lts__t_sectors.sum', 'l1tex__m_xbar2l1tex_read_bytes.sum',
+    'smsp__thread_inst_executed_per_inst_executed.ratio',
+    'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
 ]
 
 
@@ -51,7 +60,12 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    txt = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    """src: an .ncu-rep, or the `ncu -i x.ncu-rep --page raw --csv` text of one made on the GPU box (reports above the
+    64 MiB gpurun_out/ limit are converted there and only the CSV travels back)."""
+    if src.endswith('.csv'):
+        txt = open(src, errors='replace').read()
+    else:
+        txt = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
     out = []
