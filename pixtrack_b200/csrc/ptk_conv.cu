@@ -400,13 +400,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int N>
+// SPLIT = 2: the 64-channel chunks (K) of ONE output tile are shared by a cluster of two CTAs (small maps: too few
+// 16 x 16 tiles to fill the machine, long K).  Each CTA runs the main loop over its half of the chunks; rank 1 then
+// ships its fp32 partial accumulators into rank 0's shared memory -- into the operand staging area, which is idle
+// once rank 0's MMAs have retired (rank 0 tells rank 1 so through `go_bar`) -- column-major, so a warp writes 128
+// contiguous bytes per column, and arrives on rank 0's `peer_bar`; rank 0 adds them in its epilogue.  One tile per
+// cluster (not persistent): grid = 2 x total_tiles.
+template <int N, int SPLIT>
 __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                     const __grid_constant__ CUtensorMap tmA1,
                                                                     const __grid_constant__ CUtensorMap tmW,
                                                                     const HaloParams P) {
   constexpr int kBBytes = N * 128;
   constexpr int kSlots = kBBudget / kBBytes;
+  static_assert(SPLIT == 1 || N * 256 * 4 <= 2 * kHaloBytes + kBBudget, "partial sums must fit the operand staging area");
   constexpr uint32_t kTmemCols = 4 * N < 32 ? 32 : 4 * N;      // 2 buffers x 2 half tiles
   constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
@@ -420,10 +427,19 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
   uint64_t* emptyB = fullB + kSlots;
   uint64_t* tmem_full = emptyB + kSlots;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint64_t* go_bar = tmem_empty + 2;       // SPLIT, on rank 1: rank 0's MMAs have retired, its staging area may be written
+  uint64_t* peer_bar = go_bar + 1;         // SPLIT, on rank 0: rank 1's partial sums have landed
+  uint32_t* tmem_slot = (uint32_t*)(peer_bar + 1);
+  float* xbuf = reinterpret_cast<float*>(smem);   // SPLIT: [N][256] fp32 partial sums of rank 1 (aliases sA / sB)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = P.chunks0 + P.chunks1;
+  const int krank = SPLIT > 1 ? (int)cluster_ctarank() : 0;
+  const int c_begin = SPLIT > 1 ? (krank == 0 ? 0 : (chunks + 1) / 2) : 0;
+  const int c_end = SPLIT > 1 ? (krank == 0 ? (chunks + 1) / 2 : chunks) : chunks;
+  // work distribution: persistent CTAs stride over the tiles; a SPLIT cluster owns exactly one tile
+  const int tile_first = SPLIT > 1 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = SPLIT > 1 ? P.total_tiles : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
@@ -439,6 +455,8 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
       mbar_init(&fullB[s], 1);
       mbar_init(&emptyB[s], 1);
     }
+    mbar_init(go_bar, 1);
+    mbar_init(peer_bar, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -448,7 +466,8 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (SPLIT > 1) cluster_sync_all();   // the peer's barriers must exist before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -460,11 +479,11 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
       const bool timed = P.dbg != nullptr && blockIdx.x == 0;
       long long wA = 0, wB = 0;
       const long long tstart = clock64();
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < P.total_tiles; tile += tile_step) {
         const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
         const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
         const int h0 = th * 16, w0 = tw * 16, n0 = nb * N;
-        for (int c = 0; c < chunks; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           const int sa = a_it & 1;
           mbar_wait_t(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u, wA, timed);
           mbar_expect_tx(&fullA[sa], kHaloBytes);
@@ -478,7 +497,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
             for (int tap = 0; tap < 9; ++tap) {
               int sb;
               if (P.resident) {
-                sb = c * 9 + tap;
+                sb = (c - c_begin) * 9 + tap;
               } else {
                 sb = b_it % kSlots;
                 mbar_wait_t(&emptyB[sb], ((b_it / kSlots) & 1u) ^ 1u, wB, timed);
@@ -503,11 +522,11 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
     const bool timed = P.dbg != nullptr && blockIdx.x == 0;
     long long wT = 0, wA = 0, wB = 0;
     const long long tstart = clock64();
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++t_it) {
+    for (int tile = tile_first; tile < P.total_tiles; tile += tile_step, ++t_it) {
       const uint32_t buf = t_it & 1u;
       mbar_wait_t(&tmem_empty[buf], ((t_it >> 1) & 1u) ^ 1u, wT, timed);
       tc_fence_after();
-      for (int c = 0; c < chunks; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         const int sa = a_it & 1;
         mbar_wait_t(&fullA[sa], (a_it >> 1) & 1u, wA, timed);
         ++a_it;
@@ -525,7 +544,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
           for (int t3 = 0; t3 < 3; ++t3) {
             const int tap = tg * 3 + t3;
             if (P.resident) {
-              sb[t3] = c * 9 + tap;
+              sb[t3] = (c - c_begin) * 9 + tap;
               if (t_it == 0) mbar_wait_t(&fullB[sb[t3]], 0, wB, timed);
             } else {
               sb[t3] = b_it % kSlots;
@@ -547,7 +566,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
                 const uint32_t d = tmem_base + (buf * 2u + (uint32_t)sx) * (uint32_t)N;
 #pragma unroll
                 for (int k = 0; k < kKChunk / 16; ++k)
-                  tc_mma_f16(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (c | tap | k) != 0 ? 1u : 0u);
+                  tc_mma_f16(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, ((c - c_begin) | tap | k) != 0 ? 1u : 0u);
               }
               if (!P.resident) tc_commit(&emptyB[sb[t3]]);
             }
@@ -578,13 +597,38 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
     const bool timed = P.dbg != nullptr && blockIdx.x == 0 && warp == 2;   // warp 2: quadrant 2 of half tile 0
     long long wF = 0;
     const long long tstart = clock64();
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++t_it) {
+    for (int tile = tile_first; tile < P.total_tiles; tile += tile_step, ++t_it) {
       const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
       const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
       const int h = th * 16 + y, n0 = nb * N;
       const uint32_t buf = t_it & 1u;
       mbar_wait_t(&tmem_full[buf], (t_it >> 1) & 1u, wF, timed);
       tc_fence_after();
+      if (SPLIT > 1) {
+        const int mg = sx * 128 + m;                 // row of the 256-pixel tile
+        if (krank != 0) {
+          // rank 0's staging area is free once its MMAs have retired: wait for its word, then ship the partial sums
+          mbar_wait_cluster(go_bar, 0);
+          const uint32_t remote = map_to_rank0(smem_u32(xbuf)) + (uint32_t)mg * 4u;
+#pragma unroll 1
+          for (int c = 0; c < N; c += 32) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sx * (uint32_t)N + (uint32_t)c, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(remote + (uint32_t)(c + j) * 1024u), "r"(v[j]) : "memory");
+          }
+          mbar_arrive_leader(peer_bar);
+          continue;
+        }
+        // rank 0: its own accumulators are complete, i.e. every operand it staged has been consumed
+        if (warp == 2 && lane == 0) {
+          uint32_t remote_go;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, 1;" : "=r"(remote_go) : "r"(smem_u32(go_bar)));
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_go) : "memory");
+        }
+        mbar_wait_cluster(peer_bar, 0);
+      }
       {
         const int w = tw * 16 + 8 * sx + xx;
         const bool inside = (h < P.H) && (w < P.W);
@@ -595,6 +639,10 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
         for (int c = 0; c < N; c += 32) {
           uint32_t v[32];
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2u + (uint32_t)sx) * (uint32_t)N + (uint32_t)c, v);
+          if (SPLIT > 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + xbuf[(c + j) * 256 + sx * 128 + m]);
+          }
           uint32_t pw[16];
           const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);   // 32 consecutive biases, 16-byte loads
 #pragma unroll
@@ -635,7 +683,8 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (SPLIT > 1) cluster_sync_all();   // rank 0's shared memory stays mapped until rank 1 has finished writing to it
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
@@ -950,17 +999,33 @@ int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
 }
 
 
-template <int N>
+template <int N, int SPLIT = 1>
 int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int grid,
                 cudaStream_t stream) {
   constexpr int kSlots = kBBudget / (N * 128);
-  constexpr int smem = 2 * kHaloBytes + kSlots * N * 128 + (4 + 2 * kSlots + 4) * 8 + 16 + 1024;
+  constexpr int smem = 2 * kHaloBytes + kSlots * N * 128 + (4 + 2 * kSlots + 6) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
-    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  conv_halo_kernel<N><<<grid, kHalo1Threads, smem, stream>>>(a0, a1, w, P);
+  if (SPLIT == 1) {
+    conv_halo_kernel<N, SPLIT><<<grid, kHalo1Threads, smem, stream>>>(a0, a1, w, P);
+  } else {   // one cluster of SPLIT CTAs per tile
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(SPLIT * P.total_tiles);
+    cfg.blockDim = dim3(kHalo1Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SPLIT;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PTK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<N, SPLIT>, a0, a1, w, P));
+  }
   PTK_CUDA_CHECK(cudaGetLastError());
   return PTK_OK;
 }
@@ -1060,6 +1125,41 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
     // finer-grained kernel fills the machine better
     const int waves = (total + ctx->num_sms - 1) / ctx->num_sms;
     const bool wanted = mode == 2 || (mode == 1 && total * 10 >= waves * ctx->num_sms * 8);
+    // Small maps with a long K (the 1/16-scale block, the first decoder convolution): too few tiles for one CTA each,
+    // but two CTAs per tile, each running half of the 64-channel chunks, fill half to all of the machine -- and the
+    // halo staging moves 2-3x fewer L2 -> shared-memory bytes than the per-tap kernel, which is what bounds these
+    // layers (PTK_CONV_HALO_SPLIT=0 switches it off).
+    static int hsplit = -1;
+    if (hsplit < 0) hsplit = getenv("PTK_CONV_HALO_SPLIT") ? atoi(getenv("PTK_CONV_HALO_SPLIT")) : 1;
+    const int chunks_all = ctot / kKChunk;
+    const bool split_wanted = hsplit != 0 && mode != 0 && legal && !wanted && chunks_all >= 4 &&
+                              2 * total <= ctx->num_sms && (hsplit == 2 || 4 * total >= ctx->num_sms);
+    if (split_wanted) {
+      rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kHaloW, rows_per_op);
+      if (rc != PTK_OK) return rc;
+      if (cin1 > 0) {
+        rc = make_map_3d(&a1, in1, cin1, W, H, cin1, (uint64_t)in1_W * cin1, kKChunk, kHaloW, rows_per_op);
+        if (rc != PTK_OK) return rc;
+      } else {
+        a1 = a0;
+      }
+      rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, n_halo, 1);
+      if (rc != PTK_OK) return rc;
+      HaloParams Q;
+      Q.H = H; Q.W = W; Q.Cout = Cout; Q.chunks0 = cin0 / kKChunk; Q.chunks1 = cin1 / kKChunk; Q.relu = relu;
+      Q.tiles_w = tiles_w16; Q.tiles_hw = tiles_w16 * tiles_h16; Q.total_tiles = total;
+      Q.resident = 0;
+      Q.rows_per_op = rows_per_op;
+      Q.bias = bias;
+      Q.out = (__half*)out;
+      Q.pool = (__half*)pool_out;
+      Q.dbg = nullptr;
+      switch (n_halo) {
+        case 32: return launch_halo<32, 2>(a0, a1, wm, Q, 2 * total, s);
+        case 64: return launch_halo<64, 2>(a0, a1, wm, Q, 2 * total, s);
+        default: return launch_halo<128, 2>(a0, a1, wm, Q, 2 * total, s);
+      }
+    }
     if (legal && wanted) {
       rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kHaloW, rows_per_op);
       if (rc != PTK_OK) return rc;
