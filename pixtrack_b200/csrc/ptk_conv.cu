@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* peer_bar = tmem_full_bar + 1;                       // SPLIT: rank 1's partial sums have landed
   uint32_t* tmem_slot = (uint32_t*)(peer_bar + 1);
-  float* xbuf = (float*)(smem + STAGES * kStageBytes + 256);    // SPLIT: [BLOCK_N][128] fp32 partial sums of rank 1
+  float* xbuf = (float*)(smem + STAGES * kStageBytes + 256);    // SPLIT: [BLOCK_N / 4][128][4] fp32 partial sums of rank 1
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
@@ -297,14 +297,17 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (SPLIT > 1 && krank != 0) {   // hand the partial sums to rank 0 and leave
-      const uint32_t remote = map_to_rank0(smem_u32(xbuf)) + (uint32_t)m * 4u;
+      // exchange layout [column / 4][128 pixels][4 columns]: a lane ships 16 bytes per store, a warp 512 contiguous bytes
+      const uint32_t remote = map_to_rank0(smem_u32(xbuf)) + (uint32_t)m * 16u;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(remote + (uint32_t)(c + j) * 512u), "r"(v[j]) : "memory");
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)(c / 4 + j) * 2048u),
+                       "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
       }
       mbar_arrive_leader(peer_bar);
     } else {
@@ -318,7 +321,13 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
       if (SPLIT > 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + xbuf[(c + j) * 128 + m]);
+        for (int j = 0; j < 8; ++j) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xbuf + ((c / 4 + j) * 128 + m) * 4);
+          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + x4.x);
+          v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + x4.y);
+          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + x4.z);
+          v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + x4.w);
+        }
       }
       uint32_t pw[16];
       const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);   // 32 consecutive biases, 16-byte loads
@@ -404,7 +413,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // 16 x 16 tiles to fill the machine, long K).  Each CTA runs the main loop over its half of the chunks; rank 1 then
 // ships its fp32 partial accumulators into rank 0's shared memory -- into the operand staging area, which is idle
 // once rank 0's MMAs have retired (rank 0 tells rank 1 so through `go_bar`) -- column-major, so a warp writes 128
-// contiguous bytes per column, and arrives on rank 0's `peer_bar`; rank 0 adds them in its epilogue.  One tile per
+// contiguous bytes per store, and arrives on rank 0's `peer_bar`; rank 0 adds them in its epilogue.  One tile per
 // cluster (not persistent): grid = 2 x total_tiles.
 template <int N, int SPLIT>
 __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
@@ -609,14 +618,17 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
         if (krank != 0) {
           // rank 0's staging area is free once its MMAs have retired: wait for its word, then ship the partial sums
           mbar_wait_cluster(go_bar, 0);
-          const uint32_t remote = map_to_rank0(smem_u32(xbuf)) + (uint32_t)mg * 4u;
+          // exchange layout [column / 4][256 pixels][4 columns]: 16 bytes per lane and store, 512 contiguous bytes per warp
+          const uint32_t remote = map_to_rank0(smem_u32(xbuf)) + (uint32_t)mg * 16u;
 #pragma unroll 1
           for (int c = 0; c < N; c += 32) {
             uint32_t v[32];
             tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sx * (uint32_t)N + (uint32_t)c, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(remote + (uint32_t)(c + j) * 1024u), "r"(v[j]) : "memory");
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)(c / 4 + j) * 4096u),
+                           "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                           : "memory");
           }
           mbar_arrive_leader(peer_bar);
           continue;
@@ -641,7 +653,13 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2u + (uint32_t)sx) * (uint32_t)N + (uint32_t)c, v);
           if (SPLIT > 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + xbuf[(c + j) * 256 + sx * 128 + m]);
+            for (int j = 0; j < 8; ++j) {
+              const float4 x4 = *reinterpret_cast<const float4*>(xbuf + ((c / 4 + j) * 256 + sx * 128 + m) * 4);
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + x4.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + x4.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + x4.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + x4.w);
+            }
           }
           uint32_t pw[16];
           const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);   // 32 consecutive biases, 16-byte loads
@@ -1130,7 +1148,7 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
     // halo staging moves 2-3x fewer L2 -> shared-memory bytes than the per-tap kernel, which is what bounds these
     // layers (PTK_CONV_HALO_SPLIT=0 switches it off).
     static int hsplit = -1;
-    if (hsplit < 0) hsplit = getenv("PTK_CONV_HALO_SPLIT") ? atoi(getenv("PTK_CONV_HALO_SPLIT")) : 1;
+    if (hsplit < 0) hsplit = getenv("PTK_CONV_HALO_SPLIT") ? atoi(getenv("PTK_CONV_HALO_SPLIT")) : 0;
     const int chunks_all = ctot / kKChunk;
     const bool split_wanted = hsplit != 0 && mode != 0 && legal && !wanted && chunks_all >= 4 &&
                               2 * total <= ctx->num_sms && (hsplit == 2 || 4 * total >= ctx->num_sms);

@@ -94,30 +94,49 @@ def test_halo_kernels_two_inputs_with_crop(cin0, cin1, cout, H, W, grow):
     _check(y, _ref(x, w, b, True, x1=x1, hw=(H, W)), (cin0, cin1, cout))
 
 
-@pytest.mark.parametrize('cin0,cin1,cout,H,W,pool', [
+SPLIT_SHAPES = [
     (512, 0, 512, 36, 64, False),       # 1/16-scale block of the 1024x576 plan: halo<128, SPLIT 2>, 48 tiles x 2 CTAs
     (512, 0, 512, 47, 63, False),       # ... of the 1008x756 plan (odd sizes, ragged tiles)
     (512, 512, 64, 72, 128, False),     # first decoder convolution: two inputs, 16 chunks, halo<64, SPLIT 2>
     (512, 512, 64, 94, 126, False),
     (320, 0, 64, 80, 128, True),        # odd number of chunks (5 -> 3 + 2) and a fused pool
-])
-def test_split_k_halo_kernel(cin0, cin1, cout, H, W, pool):
-    """Small maps with a long K run the halo kernel with the 64-channel chunks of each tile shared by a cluster of two
-    CTAs (partial sums through distributed shared memory): against an fp32 convolution of the same operands."""
+]
+
+
+def _split_k_halo_checks():
+    """Body of test_split_k_halo_kernel; runs in a child process with PTK_CONV_HALO_SPLIT=2 (the dispatch reads its
+    switches once per process)."""
     from pixtrack_b200.extractor import conv_f16, pack_conv3x3
-    x, x1, w, b = _case(cin0, cout, H, W, seed=cin0 + cin1 + cout + H, cin1=cin1)
-    for relu in (True, False):
-        out = conv_f16(x, pack_conv3x3(w), b, relu=relu, x1=x1, out_hw=(H, W), pool=pool)
+    for cin0, cin1, cout, H, W, pool in SPLIT_SHAPES:
+        x, x1, w, b = _case(cin0, cout, H, W, seed=cin0 + cin1 + cout + H, cin1=cin1)
+        for relu in (True, False):
+            out = conv_f16(x, pack_conv3x3(w), b, relu=relu, x1=x1, out_hw=(H, W), pool=pool)
+            torch.cuda.synchronize()
+            y = out[0] if pool else out
+            _check(y, _ref(x, w, b, relu, x1=x1, hw=(H, W)), (cin0, cin1, cout, relu))
+            if pool:
+                want = tF.max_pool2d(y.float().permute(2, 0, 1)[None], 2, 2)[0].permute(1, 2, 0)
+                assert torch.equal(out[1].float(), want)
+        # run-to-run bit reproducibility (fixed summation order: rank 0's sum + rank 1's sum)
+        again = conv_f16(x, pack_conv3x3(w), b, relu=False, x1=x1, out_hw=(H, W))
         torch.cuda.synchronize()
-        y = out[0] if pool else out
-        _check(y, _ref(x, w, b, relu, x1=x1, hw=(H, W)), (cin0, cin1, cout, relu))
-        if pool:
-            want = tF.max_pool2d(y.float().permute(2, 0, 1)[None], 2, 2)[0].permute(1, 2, 0)
-            assert torch.equal(out[1].float(), want)
-    # run-to-run bit reproducibility (fixed summation order: rank 0's sum + rank 1's sum)
-    again = conv_f16(x, pack_conv3x3(w), b, relu=False, x1=x1, out_hw=(H, W))
-    torch.cuda.synchronize()
-    assert torch.equal(again, y)
+        assert torch.equal(again if not pool else again, y)
+    print('split-k halo ok')
+
+
+def test_split_k_halo_kernel():
+    """Small maps with a long K can run the halo kernel with the 64-channel chunks of each tile shared by a cluster of two
+    CTAs (partial sums through distributed shared memory; PTK_CONV_HALO_SPLIT, off by default because the per-tap
+    kernel's own K split measured faster on B200): against an fp32 convolution of the same operands."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PTK_CONV_HALO_SPLIT='2')
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, '-c', 'import sys; sys.path[:0] = [%r, %r]; import test_conv_paths_gpu as t; '
+                        't._split_k_halo_checks()' % (here, os.path.dirname(here))], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and 'split-k halo ok' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_benchmark_layer_shapes_at_full_resolution():
