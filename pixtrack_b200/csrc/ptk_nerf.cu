@@ -38,6 +38,7 @@
 //  * The marching / compositing arithmetic is compiled with -fmad=false (see build.py) so that it
 //    is the same sequence of IEEE operations as the numpy oracle.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "ptk_common.cuh"
 
@@ -205,45 +206,42 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// C[32 x N] = A[32 x K] * W[N x K]^T for one warp: A as two m16 tiles of K/16 fragments,
-// W in shared memory with row stride WS halfs.
+// C[16 x N] = A[16 x K] * W[N x K]^T for one m16 tile of a warp: A as K/16 fragments, W in shared memory with row
+// stride WS halfs.  (One tile at a time: the accumulators of both tiles together cost 64 registers more, which is the
+// difference between two and three resident CTAs per SM -- and this kernel lives on occupancy: it is bound by the
+// latency of the hash-grid gathers.)
 template <int K, int N, int WS>
-__device__ __forceinline__ void layer(const uint32_t (&a)[2][K / 16][4], const __half* __restrict__ w, int lane,
-                                      float (&c)[2][N / 8][4]) {
+__device__ __forceinline__ void layer(const uint32_t (&a)[K / 16][4], const __half* __restrict__ w, int lane,
+                                      float (&c)[N / 8][4]) {
   const int n_in = lane >> 2, k_in = (lane & 3) * 2;
 #pragma unroll
   for (int nt = 0; nt < N / 8; ++nt) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
+    for (int i = 0; i < 4; ++i) c[nt][i] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < K / 16; ++kk) {
       const __half* wr = w + (nt * 8 + n_in) * WS + kk * 16 + k_in;
       const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr);
       const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
-      mma16816(c[0][nt], a[0][kk], b0, b1);
-      mma16816(c[1][nt], a[1][kk], b0, b1);
+      mma16816(c[nt], a[kk], b0, b1);
     }
   }
 }
 
 // accumulator fragments of a layer (fp32) -> A fragments of the next one (fp16), optional ReLU
 template <int N, bool kRelu>
-__device__ __forceinline__ void to_a(const float (&c)[2][N / 8][4], uint32_t (&a)[2][N / 16][4]) {
+__device__ __forceinline__ void to_a(const float (&c)[N / 8][4], uint32_t (&a)[N / 16][4]) {
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int kk = 0; kk < N / 16; ++kk)
 #pragma unroll
-    for (int kk = 0; kk < N / 16; ++kk)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v0 = c[mt][2 * kk + h][0], v1 = c[mt][2 * kk + h][1], v2 = c[mt][2 * kk + h][2], v3 = c[mt][2 * kk + h][3];
-        if (kRelu) {
-          v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
-        }
-        a[mt][kk][2 * h] = pack_h2(v0, v1);
-        a[mt][kk][2 * h + 1] = pack_h2(v2, v3);
+    for (int h = 0; h < 2; ++h) {
+      float v0 = c[2 * kk + h][0], v1 = c[2 * kk + h][1], v2 = c[2 * kk + h][2], v3 = c[2 * kk + h][3];
+      if (kRelu) {
+        v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
       }
+      a[kk][2 * h] = pack_h2(v0, v1);
+      a[kk][2 * h + 1] = pack_h2(v2, v3);
+    }
 }
 
 template <int KS, int STRIDE>
@@ -340,63 +338,57 @@ __device__ __forceinline__ void sh_encode(const V3& d, __half* __restrict__ row)
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
 
 // Network for the warp's 32 samples.  feat / sh tiles are filled by the lanes; out[lane] =
-// (raw r, raw g, raw b, raw density), each rounded to fp16 like the reference's network output.
+// (raw r, raw g, raw b, raw density), each rounded to fp16 like the reference's network output.  The two m16 tiles of
+// the warp go through the five layers one after the other (see `layer`).
 __device__ __forceinline__ void run_network(const __half* __restrict__ wts, const __half* __restrict__ feat,
                                             const __half* __restrict__ sh, float4* __restrict__ out, int lane,
                                             bool want_rgb) {
-  uint32_t a32[2][2][4];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) load_a<32, kS32>(feat, lane, kk * 16, a32[mt][kk], mt);
-  uint32_t a64[2][4][4];
-  {
-    float c[2][8][4];
-    layer<32, 64, kS32>(a32, wts + kOffWd1, lane, c);
-    to_a<64, true>(c, a64);
-  }
-  float cd[2][2][4];
-  layer<64, 16, kS64>(a64, wts + kOffWd2, lane, cd);
   const int r = lane >> 2, q = lane & 3;
-  if (q == 0) {
-    out[r].w = round_h(cd[0][0][0]);
-    out[r + 8].w = round_h(cd[0][0][2]);
-    out[r + 16].w = round_h(cd[1][0][0]);
-    out[r + 24].w = round_h(cd[1][0][2]);
-  }
-  if (!want_rgb) return;
-  {
-    uint32_t ad[2][1][4];
-    to_a<16, false>(cd, ad);
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    uint32_t a32[2][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a32[mt][0][i] = ad[mt][0][i];
-      load_a<16, kSsh>(sh, lane, 0, a32[mt][1], mt);
+    for (int kk = 0; kk < 2; ++kk) load_a<32, kS32>(feat, lane, kk * 16, a32[kk], mt);
+    uint32_t a64[4][4];
+    {
+      float c[8][4];
+      layer<32, 64, kS32>(a32, wts + kOffWd1, lane, c);
+      to_a<64, true>(c, a64);
     }
-  }
-  {
-    float c[2][8][4];
-    layer<32, 64, kS32>(a32, wts + kOffWc1, lane, c);
-    to_a<64, true>(c, a64);
-  }
-  {
-    float c[2][8][4];
-    layer<64, 64, kS64>(a64, wts + kOffWc2, lane, c);
-    to_a<64, true>(c, a64);
-  }
-  float c3[2][1][4];
-  layer<64, 8, kS64>(a64, wts + kOffWc3, lane, c3);
-  if (q == 0) {
-    out[r].x = round_h(c3[0][0][0]); out[r].y = round_h(c3[0][0][1]);
-    out[r + 8].x = round_h(c3[0][0][2]); out[r + 8].y = round_h(c3[0][0][3]);
-    out[r + 16].x = round_h(c3[1][0][0]); out[r + 16].y = round_h(c3[1][0][1]);
-    out[r + 24].x = round_h(c3[1][0][2]); out[r + 24].y = round_h(c3[1][0][3]);
-  } else if (q == 1) {
-    out[r].z = round_h(c3[0][0][0]);
-    out[r + 8].z = round_h(c3[0][0][2]);
-    out[r + 16].z = round_h(c3[1][0][0]);
-    out[r + 24].z = round_h(c3[1][0][2]);
+    float cd[2][4];
+    layer<64, 16, kS64>(a64, wts + kOffWd2, lane, cd);
+    float4* o = out + mt * 16;
+    if (q == 0) {
+      o[r].w = round_h(cd[0][0]);
+      o[r + 8].w = round_h(cd[0][2]);
+    }
+    if (!want_rgb) continue;
+    {
+      uint32_t ad[1][4];
+      to_a<16, false>(cd, ad);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a32[0][i] = ad[0][i];
+      load_a<16, kSsh>(sh, lane, 0, a32[1], mt);
+    }
+    {
+      float c[8][4];
+      layer<32, 64, kS32>(a32, wts + kOffWc1, lane, c);
+      to_a<64, true>(c, a64);
+    }
+    {
+      float c[8][4];
+      layer<64, 64, kS64>(a64, wts + kOffWc2, lane, c);
+      to_a<64, true>(c, a64);
+    }
+    float c3[1][4];
+    layer<64, 8, kS64>(a64, wts + kOffWc3, lane, c3);
+    if (q == 0) {
+      o[r].x = round_h(c3[0][0]); o[r].y = round_h(c3[0][1]);
+      o[r + 8].x = round_h(c3[0][2]); o[r + 8].y = round_h(c3[0][3]);
+    } else if (q == 1) {
+      o[r].z = round_h(c3[0][0]);
+      o[r + 8].z = round_h(c3[0][2]);
+    }
   }
 }
 
@@ -546,7 +538,9 @@ __global__ void __launch_bounds__(256) nerf_resolve_kernel(const __grid_constant
   if (P.out_depth) P.out_depth[pix] = last_alive ? P.frame_depth[pix] : 0.f;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) nerf_render_kernel(const __grid_constant__ NerfParams P) {
+// kCtas = resident CTAs per SM the register allocation is bounded for (2: 128 registers, 3: 80).
+template <int kCtas>
+__global__ void __launch_bounds__(kThreads, kCtas) nerf_render_kernel(const __grid_constant__ NerfParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __half* wts = reinterpret_cast<__half*>(smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -794,7 +788,8 @@ extern "C" int ptk_nerf_create(PtkContext* ctx, const PtkNerfModel* m, PtkNerf**
     free(n);
     return PTK_ERR_CUDA;
   }
-  PTK_CUDA_CHECK(cudaFuncSetAttribute(nerf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  PTK_CUDA_CHECK(cudaFuncSetAttribute(nerf_render_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  PTK_CUDA_CHECK(cudaFuncSetAttribute(nerf_render_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   *out = n;
   return PTK_OK;
 }
@@ -880,14 +875,21 @@ extern "C" int ptk_nerf_render(PtkNerf* n, const PtkNerfView* v, float* out_rgba
   P.frame_depth = P.starts + need;
   PTK_CUDA_CHECK(cudaMemsetAsync(n->counter, 0, sizeof(unsigned) * 2 + sizeof(unsigned long long) * 4, s));
   nerf_start_kernel<<<(unsigned)(((size_t)v->width * v->height + 255) / 256), 256, 0, s>>>(P);
+  static int want_ctas = -1;   // PTK_NERF_CTAS = 2 | 3 resident CTAs per SM (register bound of the instantiation used)
+  if (want_ctas < 0) {
+    const char* e = getenv("PTK_NERF_CTAS");
+    want_ctas = (e != nullptr && atoi(e) == 2) ? 2 : 3;
+  }
   int per_sm = 1;
-  PTK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nerf_render_kernel, kThreads, kSmemBytes));
+  if (want_ctas == 2) PTK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nerf_render_kernel<2>, kThreads, kSmemBytes));
+  else PTK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nerf_render_kernel<3>, kThreads, kSmemBytes));
   if (per_sm < 1) per_sm = 1;
   const long long warps_needed = ((long long)v->width * v->height + 31) / 32;
   long long ctas = (warps_needed + kWarpsPerCta - 1) / kWarpsPerCta;
   const long long cap = (long long)n->ctx->num_sms * per_sm;
   if (ctas > cap) ctas = cap;
-  nerf_render_kernel<<<(unsigned)ctas, kThreads, kSmemBytes, s>>>(P);
+  if (want_ctas == 2) nerf_render_kernel<2><<<(unsigned)ctas, kThreads, kSmemBytes, s>>>(P);
+  else nerf_render_kernel<3><<<(unsigned)ctas, kThreads, kSmemBytes, s>>>(P);
   nerf_resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(P);
   PTK_CUDA_CHECK(cudaGetLastError());
   return PTK_OK;
