@@ -318,6 +318,13 @@ void ptk_nerf_destroy(PtkNerf* n);
 int64_t ptk_nerf_grid_entries(int32_t aabb_scale);
 int ptk_nerf_render(PtkNerf* n, const PtkNerfView* view, float* out_rgba, uint8_t* out_u8, float* out_depth,
                     void* stream);
+/* The network alone: replaces NerfNetwork::inference_mixed_precision_impl
+ *   (include/neural-graphics-primitives/nerf_network.h:101-136: hash-grid encoding -> density MLP -> [16 | SH16] -> rgb
+ *   MLP) for `count` inputs.  pos01 [count][3]: positions in the unit cube of the training box (warp_position applied);
+ *   dir [count][3]: unit view directions.  out_rgbd [count][4] fp32: raw r, g, b, raw density (the fp16 values the
+ *   reference's network emits, before the activations); out_features [count][32] fp32 or NULL: the hash-grid encoding. */
+int ptk_nerf_eval(PtkNerf* n, const float* pos01, const float* dir, int32_t count, float* out_rgbd, float* out_features,
+                  void* stream);
 /* SYNCHRONISING statistics of the last render of `n` (benchmarks): out4 = network samples evaluated, warp steps,
  * rays marched (those that reach an occupied cell), lane slots that sat out a warp step. */
 int ptk_nerf_stats(PtkNerf* n, uint64_t* out4);

@@ -54,6 +54,21 @@ def lift_helpers(cu_path: str, names=None) -> str:
     return '\n'.join(out)
 
 
+def lift_member(header_path: str, name: str) -> str:
+    """The definition of member function `name` (first one with a body) out of a class in a header, verbatim."""
+    import re
+    lines = open(header_path).read().split('\n')
+    pat = re.compile(r'^\s*(virtual\s+)?[\w:<>\*& ]+\b' + name + r'\(.*\{\s*$')
+    start = next(i for i, ln in enumerate(lines) if pat.match(ln))
+    depth, i = 0, start
+    while True:
+        depth += lines[i].count('{') - lines[i].count('}')
+        if depth == 0:
+            break
+        i += 1
+    return '\n'.join(lines[start:i + 1]) + '\n'
+
+
 def _one_definition(lines, start):
     out = []
     if lines[start - 1].startswith('template'):
@@ -103,6 +118,9 @@ def build(verbose: bool = True) -> str:
         f.write(lift_helpers(os.path.join(tinc, 'encodings', 'grid.h'), TCNN_HELPERS))
         f.write('\n')
         f.write(lift_helpers(os.path.join(tinc, 'encodings', 'spherical_harmonics.h'), TCNN_SH))
+    lifted3 = os.path.join(tmp_inc, 'nerf_network_set_params.inc')
+    with open(lifted3, 'w') as f:
+        f.write(lift_member(os.path.join(REF, 'include', 'neural-graphics-primitives', 'nerf_network.h'), 'set_params'))
     cmd.insert(-3, f'-I{tmp_inc}')
     if verbose:
         print(' '.join(cmd), file=sys.stderr)
@@ -111,6 +129,7 @@ def build(verbose: bool = True) -> str:
     finally:
         os.remove(lifted)
         os.remove(lifted2)
+        os.remove(lifted3)
         os.rmdir(tmp_inc)
     return out
 

@@ -562,7 +562,7 @@ def tonemap(accum, background=(1.0, 1.0, 1.0, 0.0)):
 
 def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov_deg: float, spp: int = 8,
            depth_mode: bool = False, min_transmittance: float = 1e-7, fov_axis: int = 0,
-           background=(1.0, 1.0, 1.0, 0.0)) -> Dict[str, np.ndarray]:
+           background=(1.0, 1.0, 1.0, 0.0), network_fn=None) -> Dict[str, np.ndarray]:
     """Testbed.render(width, height, spp, linear=True) with the settings of
     pixtrack/utils/ingp_utils.py:22-44 (snap_to_pixel_centers, min transmittance 1e-7, fov_axis 0,
     exposure 0, background alpha 0 by default) -> dict(rgba float32 [H,W,4], depth [H,W]).
@@ -570,7 +570,9 @@ def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov
     python_api.cu:127-173 -> testbed.cu:2591-2749 (render_frame) -> testbed_nerf.cu:2228-2330
     (render_nerf) -> :1781-1890 (ray init), :606-657 (first advance), :2035-2146 (trace),
     :693-752 (samples), :754-955 (composite), :1721-1754 (shade); render_buffer.cu:236-275
-    (accumulate), :542-570 (tonemap, linear, identity curve)."""
+    (accumulate), :542-570 (tonemap, linear, identity curve).
+    network_fn(wpos, wdir) -> fp16 [n,4] replaces the hash grid + MLPs (the orchestration is pinned against the
+    reference's kernels chained in the reference's order with an analytic network, tests/test_nerf_oracle.py)."""
     cam = np.asarray(camera_matrix, f32)
     o, d = pixel_rays(cam, width, height, fov_deg, fov_axis)
     n = o.shape[0]
@@ -592,7 +594,8 @@ def render(m: NerfModel, camera_matrix: np.ndarray, width: int, height: int, fov
             t, alive, k, wpos, wdir, wdt = next_sample(m, o, d, idir, t, alive)
             if k.size == 0:
                 break
-            out = network(m, wpos, wdir, want_rgb=not depth_mode).astype(f32)
+            out = (network(m, wpos, wdir, want_rgb=not depth_mode) if network_fn is None
+                   else network_fn(wpos, wdir)).astype(f32)
             done = composite_sample(rgba, maxw, dep, k, out, wpos, wdt, m.aabb, o[k], cam, depth_scale, depth_mode,
                                     min_transmittance)
             alive[k[done]] = False

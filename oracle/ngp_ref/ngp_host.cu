@@ -24,6 +24,17 @@
 //   generate_next_nerf_network_inputs (the marching kernel)   src/testbed_nerf.cu:693-752
 //   compact_kernel_nerf (atomicAdd -> a host counter)   src/testbed_nerf.cu:1756-1779; tonemap + tonemap_kernel
 //                                  (surf2Dwrite -> a host array)   src/render_buffer.cu:273-345,542-569
+//   THE ORCHESTRATION: `render_chain` strings the lifted kernels together exactly as the reference does --
+//                                  Testbed::render_to_cpu (src/python_api.cu:127-173: one render_frame per sample),
+//                                  render_frame (src/testbed.cu:2591-2749: clear, render_nerf, accumulate, tonemap),
+//                                  render_nerf (src/testbed_nerf.cu:2228-2359), NerfTracer::init_rays_from_camera (:1956-2033)
+//                                  and NerfTracer::trace (:2035-2157: double-buffered compaction, n_steps_between_compaction,
+//                                  generate -> network -> composite rounds, final hit list) -- with an analytic stand-in for
+//                                  the network (simple float arithmetic rounded to network_precision_t, restated in
+//                                  tests/test_nerf_oracle.py), and prints the final image of a Shade and a Depth render.
+//   NerfNetwork::set_params        include/neural-graphics-primitives/nerf_network.h:361-395: the body is lifted into a mock
+//                                  class whose four sub-modules record the parameter offsets they are handed (the order of
+//                                  `params_binary` in a snapshot).
 // The fused MLPs (wmma fragments) cannot run without a GPU; that part of the oracle stays unpinned.
 // Built by oracle/build_ref.py into oracle/_ref/ngp_host (git-ignored).
 #include <neural-graphics-primitives/common.h>
@@ -106,6 +117,25 @@ namespace lifted {
 }
 
 using namespace ngp;
+
+// NerfNetwork::set_params lifted into a mock: the sub-modules record where in the parameter vector they are pointed.
+namespace paramorder {
+struct Recorder {
+  const char* name;
+  size_t n;
+  long long offset = -1;
+  uint16_t* base = nullptr;
+  void set_params(uint16_t* params, uint16_t*, uint16_t*, uint16_t*) { offset = (long long)(params - base); }
+  size_t n_params() const { return n; }
+};
+struct MockNerfNetwork {
+  using T = uint16_t;
+  Recorder *m_density_network, *m_rgb_network, *m_pos_encoding, *m_dir_encoding;
+#define override
+#include "nerf_network_set_params.inc"
+#undef override
+};
+}
 
 static uint32_t lcg_state = 12345u;
 static float rnd() {   // uniform in [0, 1)
@@ -487,7 +517,137 @@ int main() {
     }
     printf("],\n\"unused2\": [");
   }
-  printf("],\n\"march\": [\n");
+  printf("],\n");
+
+  // ---- parameter order of a snapshot (NerfNetwork::set_params) ----
+  {
+    using namespace paramorder;
+    std::vector<uint16_t> buf(8);
+    // base.json network: density MLP 32 -> 64 -> 16 (padded), rgb MLP 32 (16 + SH16) -> 64 -> 64 -> 16 (padded); hash grid of
+    // aabb_scale 1 (tests/synthetic.py::nerf_grid_size); the SH encoding has no parameters
+    Recorder dn{"density_network", 64 * 32 + 16 * 64}, rn{"rgb_network", 64 * 32 + 64 * 64 + 16 * 64}, pe{"pos_encoding", 2 * 6098120},
+        de{"dir_encoding", 0};
+    dn.base = rn.base = pe.base = de.base = buf.data();
+    MockNerfNetwork net{&dn, &rn, &pe, &de};
+    net.set_params(buf.data(), buf.data(), buf.data(), buf.data());
+    printf("\"set_params\": [");
+    const Recorder* all[4] = {&dn, &rn, &pe, &de};
+    for (int i = 0; i < 4; ++i) printf("%s{\"module\": \"%s\", \"n_params\": %zu, \"offset\": %lld}", i ? ", " : "", all[i]->name, all[i]->n, all[i]->offset);
+    printf("],\n");
+  }
+  // ---- the whole render: python_api.cu render_to_cpu -> render_frame -> render_nerf -> NerfTracer, analytic network ----
+  printf("\"render_chain\": [");
+  for (int mode = 0; mode < 2; ++mode) {
+    const Vector2i res(20, 14);
+    const uint32_t n = (uint32_t)(res.x() * res.y());
+    const int SPP = 3;
+    const float fov = 34.f, min_T = 0.01f, depth_scale = 1.f / 0.33f;
+    const float f = fov_to_focal_length(1, fov) * (float)res.x();
+    Matrix<float, 3, 4> cam;
+    cam << 0.948683f, -0.094916f, 0.301511f, -0.25f,
+           0.f,        0.953463f, 0.301511f, -0.2f,
+          -0.316228f, -0.284747f, 0.904534f, -1.9f;
+    const BoundingBox box(Vector3f::Constant(0.f), Vector3f::Constant(1.f));     // render box = training box, aabb_scale 1
+    const float cone = 0.f;                                                       // testbed_nerf.cu:2596 for aabb_scale 1
+    const ERenderMode rmode = mode ? ERenderMode::Depth : ERenderMode::Shade;
+    const Array4f background(255.f, 255.f, 255.f, 0.f);                           // ingp_utils.py:31
+    std::vector<Array4f> acc(n, Array4f::Zero());
+    std::vector<float> db(n, 0.f);
+    std::vector<uint32_t> hits, rounds;
+    for (int spp = 0; spp < SPP; ++spp) {
+      std::vector<Array4f> fb(n, Array4f::Zero());                                // render_buffer.clear_frame
+      std::fill(db.begin(), db.end(), 0.f);
+      // NerfTracer::init_rays_from_camera
+      struct Soa { std::vector<Array4f> rgba; std::vector<float> depth; std::vector<NerfPayload> payload; };
+      Soa rays[2], hit;
+      for (Soa* r : {&rays[0], &rays[1], &hit}) { r->rgba.assign(n, Array4f::Zero()); r->depth.assign(n, 0.f); r->payload.resize(n); }
+      for (int y = 0; y < res.y(); ++y)
+        for (int x = 0; x < res.x(); ++x) {
+          lifted::h_tid.x = (uint32_t)x; lifted::h_tid.y = (uint32_t)y;
+          init_rays_with_payload_kernel_nerf((uint32_t)spp, rays[0].payload.data(), res, Vector2f(f, f), cam, cam, Vector4f::Zero(),
+                                             Vector2f(0.5f, 0.5f), Vector3f(0.f, 0.f, 1.f), true, box, Matrix3f::Identity(), 1.0f, 0.0f,
+                                             CameraDistortion{}, nullptr, Vector2i::Zero(), fb.data(), db.data(), nullptr, Vector2i::Zero(), rmode);
+        }
+      lifted::h_tid.y = 0;
+      for (uint32_t i = 0; i < n; ++i) {
+        lifted::h_tid.x = i;
+        advance_pos_nerf(n, box, Matrix3f::Identity(), cam.col(2), Vector2f(f, f), (uint32_t)spp, rays[0].payload.data(), bits.data(), 0, cone);
+      }
+      // NerfTracer::trace
+      uint32_t hit_counter = 0, n_alive = n, step = 1, dbi = 0, n_rounds = 0;
+      std::vector<NerfCoordinate> coords((size_t)n * 8, NerfCoordinate(Vector3f::Zero(), Vector3f::Zero(), 0.f));
+      std::vector<network_precision_t> out;
+      while (step < 10000u) {                                                       // MARCH_ITER
+        Soa& cur = rays[(dbi + 1) % 2];
+        Soa& tmp = rays[dbi % 2];
+        ++dbi;
+        uint32_t alive_counter = 0;
+        for (uint32_t i = 0; i < n_alive; ++i) {
+          lifted::h_tid.x = i;
+          compact_kernel_nerf(n_alive, tmp.rgba.data(), tmp.depth.data(), tmp.payload.data(), cur.rgba.data(), cur.depth.data(),
+                              cur.payload.data(), hit.rgba.data(), hit.depth.data(), hit.payload.data(), &alive_counter, &hit_counter);
+        }
+        n_alive = alive_counter;
+        if (n_alive == 0) break;
+        ++n_rounds;
+        const uint32_t n_steps = std::min(std::max(n / n_alive, 1u), 8u);         // MIN / MAX_STEPS_INBETWEEN_COMPACTION
+        std::fill(coords.begin(), coords.end(), NerfCoordinate(Vector3f::Zero(), Vector3f::Zero(), 0.f));
+        for (uint32_t i = 0; i < n_alive; ++i) {
+          lifted::h_tid.x = i;
+          generate_next_nerf_network_inputs(n_alive, box, Matrix3f::Identity(), box, Vector2f(f, f), cam.col(2), cur.payload.data(),
+                                            PitchedPtr<NerfCoordinate>(coords.data(), 1), n_steps, bits.data(), 0, cone, nullptr);
+        }
+        const uint32_t n_elements = ((n_alive * n_steps + 127u) / 128u) * 128u;   // next_multiple(.., batch_size_granularity)
+        out.assign((size_t)16 * n_elements, (network_precision_t)0.f);
+        for (uint32_t e = 0; e < n_alive * n_steps; ++e) {                          // the analytic stand-in network
+          const NerfCoordinate& c = coords[e];
+          const float x = c.pos.p.x(), y = c.pos.p.y(), z = c.pos.p.z();
+          const float m = fmaxf(fmaxf(fabsf(x - 0.5f), fabsf(y - 0.5f)), fabsf(z - 0.5f));
+          const float raw[4] = {8.f * x - 4.f, 8.f * y - 4.f, 6.f * c.dir.d.z() - 3.f, 6.f - 14.f * m};
+          for (int k = 0; k < 4; ++k) out[(size_t)k * n_elements + e] = (network_precision_t)raw[k];
+        }
+        for (uint32_t i = 0; i < n_alive; ++i) {
+          lifted::h_tid.x = i;
+          composite_kernel_nerf(n_alive, n_elements, step, box, 0.f, 0, 0, nullptr, cam, Vector2f(f, f), depth_scale, cur.rgba.data(),
+                                cur.depth.data(), cur.payload.data(), PitchedPtr<NerfCoordinate>(coords.data(), 1), out.data(), 16, n_steps,
+                                rmode, bits.data(), ENerfActivation::Logistic, ENerfActivation::Exponential, -1, min_T);
+        }
+        step += n_steps;
+      }
+      hits.push_back(hit_counter);
+      rounds.push_back(n_rounds);
+      // render_nerf: shade the rays that hit; render_frame: accumulate, tonemap
+      for (uint32_t i = 0; i < hit_counter; ++i) {
+        lifted::h_tid.x = i;
+        shade_kernel_nerf(hit_counter, hit.rgba.data(), hit.depth.data(), hit.payload.data(), rmode, false, fb.data(), db.data());
+      }
+      for (int y = 0; y < res.y(); ++y)
+        for (int x = 0; x < res.x(); ++x) {
+          lifted::h_tid.x = (uint32_t)x; lifted::h_tid.y = (uint32_t)y;
+          accumulate_kernel(res, fb.data(), acc.data(), (float)spp, EColorSpace::Linear);
+        }
+      lifted::h_tid.y = 0;
+    }
+    lifted::host_surface.assign(n, float4{0, 0, 0, 0});
+    lifted::host_surface_w = res.x();
+    for (int y = 0; y < res.y(); ++y)
+      for (int x = 0; x < res.x(); ++x) {
+        lifted::h_tid.x = (uint32_t)x; lifted::h_tid.y = (uint32_t)y;
+        tonemap_kernel(res, 0.0f, background, acc.data(), EColorSpace::Linear, EColorSpace::Linear, ETonemapCurve::Identity, false, 0);
+      }
+    lifted::h_tid.y = 0;
+    printf("%s{\"depth_mode\": %d, \"width\": %d, \"height\": %d, \"spp\": %d, \"fov\": %.9g, \"min_transmittance\": %.9g, \"depth_scale\": %.9g, \"camera\": [",
+           mode ? ",\n" : "", mode, res.x(), res.y(), SPP, fov, min_T, depth_scale);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) printf("%s%.9g", (r || c) ? ", " : "", cam(r, c));
+    printf("], \"n_hit\": [%u, %u, %u], \"rounds\": [%u, %u, %u], \"rgba\": [", hits[0], hits[1], hits[2], rounds[0], rounds[1], rounds[2]);
+    for (uint32_t i = 0; i < n; ++i)
+      printf("%s[%.9g, %.9g, %.9g, %.9g]", i ? ", " : "", lifted::host_surface[i].x, lifted::host_surface[i].y, lifted::host_surface[i].z, lifted::host_surface[i].w);
+    printf("], \"depth\": [");
+    for (uint32_t i = 0; i < n; ++i) printf("%s%.9g", i ? ", " : "", db[i]);
+    printf("]}");
+  }
+  printf("],\n");
+  printf("\"march\": [\n");
   for (int i = 0; i < 160; ++i) {
     // positions across the cascades (cascade c covers [0.5 - 2^(c-1), 0.5 + 2^(c-1)])
     const float half = 0.5f * (float)(1 << (i % 4));

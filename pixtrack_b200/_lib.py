@@ -106,6 +106,7 @@ SYMBOLS = {
     'ptk_nerf_destroy': (None, [C.c_void_p]),
     'ptk_nerf_grid_entries': (C.c_int64, [C.c_int32]),
     'ptk_nerf_render': (C.c_int, [C.c_void_p, C.POINTER(NerfView), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ptk_nerf_eval': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ptk_nerf_stats': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     'ptk_query_mask': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),

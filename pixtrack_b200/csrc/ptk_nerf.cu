@@ -686,6 +686,49 @@ __global__ void __launch_bounds__(kThreads, kCtas) nerf_render_kernel(const __gr
   }
 }
 
+// Network alone (NerfNetwork::inference_mixed_precision_impl, nerf_network.h:101-136): one warp per 32 inputs, the same
+// hash_encode / sh_encode / run_network the render kernel uses.  pos01 [n][3] = positions in the unit cube of the training
+// box (warp_position applied), dir [n][3] = unit view directions; out [n][4] = raw r, g, b and raw density (fp16 values).
+__global__ void __launch_bounds__(kThreads) nerf_eval_kernel(const __grid_constant__ NerfParams P, const float* __restrict__ pos01,
+                                                             const float* __restrict__ dir, int n, float4* __restrict__ out,
+                                                             float* __restrict__ feat_out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __half* wts = reinterpret_cast<__half*>(smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* wbase = smem + kWeightHalfs * 2 + warp * (kWarpHalfs * 2 + 32 * 16);
+  __half* feat = reinterpret_cast<__half*>(wbase);
+  __half* sh = feat + 32 * kS32;
+  float4* outv = reinterpret_cast<float4*>(wbase + kWarpHalfs * 2);
+  for (int i = threadIdx.x; i < 64 * 32; i += kThreads) {
+    wts[kOffWd1 + (i >> 5) * kS32 + (i & 31)] = P.w[0][i];
+    wts[kOffWc1 + (i >> 5) * kS32 + (i & 31)] = P.w[2][i];
+  }
+  for (int i = threadIdx.x; i < 16 * 64; i += kThreads) wts[kOffWd2 + (i >> 6) * kS64 + (i & 63)] = P.w[1][i];
+  for (int i = threadIdx.x; i < 64 * 64; i += kThreads) wts[kOffWc2 + (i >> 6) * kS64 + (i & 63)] = P.w[3][i];
+  for (int i = threadIdx.x; i < 8 * 64; i += kThreads) wts[kOffWc3 + (i >> 6) * kS64 + (i & 63)] = P.w[4][i];
+  __syncthreads();
+  for (int base = (blockIdx.x * kWarpsPerCta + warp) * 32; base < n; base += gridDim.x * kWarpsPerCta * 32) {
+    const int i = base + lane;
+    if (i < n) {
+      hash_encode(P, pos01[3 * i], pos01[3 * i + 1], pos01[3 * i + 2], feat + lane * kS32);
+      const V3 d = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
+      sh_encode(d, sh + lane * kSsh);
+    } else {
+      uint4* z = reinterpret_cast<uint4*>(feat + lane * kS32);
+      z[0] = z[1] = z[2] = z[3] = make_uint4(0, 0, 0, 0);
+      uint4* zs = reinterpret_cast<uint4*>(sh + lane * kSsh);
+      zs[0] = zs[1] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    if (feat_out != nullptr && i < n)
+      for (int k = 0; k < 32; ++k) feat_out[(size_t)i * 32 + k] = __half2float(feat[lane * kS32 + k]);
+    run_network(wts, feat, sh, outv, lane, true);
+    __syncwarp();
+    if (i < n) out[i] = outv[lane];
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 struct PtkNerf {
@@ -799,6 +842,25 @@ extern "C" void ptk_nerf_destroy(PtkNerf* n) {
   if (n->counter) cudaFree(n->counter);
   if (n->starts) cudaFree(n->starts);
   free(n);
+}
+
+extern "C" int ptk_nerf_eval(PtkNerf* n, const float* pos01, const float* dir, int32_t count, float* out_rgbd,
+                             float* out_features, void* stream) {
+  PTK_REQUIRE(n && out_rgbd && (count == 0 || (pos01 && dir)) && count >= 0, "bad argument");
+  if (count == 0) return PTK_OK;
+  PtkDeviceGuard guard(n->ctx->device);
+  static bool configured = false;
+  if (!configured) {
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(nerf_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  long long ctas = ((long long)count + kThreads - 1) / kThreads;
+  const long long cap = 2LL * n->ctx->num_sms;
+  if (ctas > cap) ctas = cap;
+  nerf_eval_kernel<<<(unsigned)ctas, kThreads, kSmemBytes, (cudaStream_t)stream>>>(n->base, pos01, dir, count,
+                                                                                 reinterpret_cast<float4*>(out_rgbd), out_features);
+  PTK_CUDA_CHECK(cudaGetLastError());
+  return PTK_OK;
 }
 
 // SYNCHRONISING: statistics of the last render on this object (benchmarks / profiles).

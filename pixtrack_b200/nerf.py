@@ -216,6 +216,19 @@ class NerfTestbed:
                                              _lib.current_stream_ptr(self.device)))
         return rgba, u8, dep
 
+    def network(self, pos01: torch.Tensor, dirs: torch.Tensor, want_features: bool = False):
+        """The network alone (NerfNetwork::inference, nerf_network.h:101-136) for [n,3] unit-cube positions and [n,3] unit
+        directions (CUDA fp32): -> raw (r, g, b, density) [n,4] fp32 holding the fp16 network outputs, and optionally the
+        [n,32] hash-grid encoding.  Stream-ordered."""
+        pos01 = pos01.to(self.device, torch.float32).contiguous()
+        dirs = dirs.to(self.device, torch.float32).contiguous()
+        n = pos01.shape[0]
+        out = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+        feats = torch.empty((n, 32), dtype=torch.float32, device=self.device) if want_features else None
+        _lib.check(self._lib.ptk_nerf_eval(self._h, pos01.data_ptr(), dirs.data_ptr(), n, out.data_ptr(),
+                                           None if feats is None else feats.data_ptr(), _lib.current_stream_ptr(self.device)))
+        return (out, feats) if want_features else out
+
     def last_stats(self) -> dict:
         """Statistics of the last render (synchronises): network samples, warp steps, rays that reached the object."""
         out = (C.c_uint64 * 4)()

@@ -492,3 +492,75 @@ def test_product_host_side_camera_code_matches_the_reference_too():
         srgb = {round(r[0], 6): r[1] for r in HOST['srgb']}
         lin = nerf.srgb_to_linear(np.array([0.2, 0.5, 0.8], f32))
         assert np.allclose([v.background[i] for i in range(3)], lin, rtol=1e-6) and v.background[3] == 1.0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The orchestration: the reference's kernels chained in the reference's order (render_to_cpu -> render_frame ->
+# render_nerf -> NerfTracer::init_rays_from_camera / trace with its compaction rounds -> shade -> accumulate -> tonemap,
+# oracle/ngp_ref/ngp_host.cu `render_chain`) with an analytic network, against oracle/nerf.py::render with the same one.
+# ------------------------------------------------------------------------------------------------------------
+def _analytic_network(wpos, wdir):
+    """The stand-in network of the harness: plain float32 arithmetic (no transcendental functions, so C and numpy agree
+    bit for bit), rounded to fp16 like the reference's network output."""
+    x, y, z = wpos[:, 0].astype(f32), wpos[:, 1].astype(f32), wpos[:, 2].astype(f32)
+    m = np.maximum(np.maximum(np.abs(x - f32(0.5)), np.abs(y - f32(0.5))), np.abs(z - f32(0.5))).astype(f32)
+    raw = np.stack([f32(8) * x - f32(4), f32(8) * y - f32(4), f32(6) * wdir[:, 2].astype(f32) - f32(3),
+                    f32(6) - f32(14) * m], 1).astype(f32)
+    return raw.astype(np.float16)
+
+
+def _pattern_model():
+    """aabb_scale 1 model whose occupancy bitfield is the harness's reproducible pattern (byte i = (i * 2654435761) >> 13)."""
+    i = np.arange(nerf.CASCADES * nerf.GRID ** 3 // 8, dtype=np.uint64)
+    bits = (((i * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)) >> np.uint64(13)).astype(np.uint8)
+    sc = syn.nerf_scene(0, 1, zero_network=True)
+    return nerf.NerfModel(1, sc['grid'], sc['w_density'], sc['w_rgb'], bits)
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_render_orchestration_matches_the_reference_kernels_chained_in_the_reference_order(mode):
+    R = HOST['render_chain'][mode]
+    assert R['depth_mode'] == mode
+    m = _pattern_model()
+    cam = np.array(R['camera'], f32).reshape(3, 4)
+    out = nerf.render(m, cam, R['width'], R['height'], R['fov'], spp=R['spp'], depth_mode=bool(mode),
+                      min_transmittance=R['min_transmittance'], background=(255.0, 255.0, 255.0, 0.0),
+                      network_fn=_analytic_network)
+    want = np.array(R['rgba'], np.float64).reshape(R['height'], R['width'], 4)
+    got = out['rgba'].astype(np.float64)
+    assert (want[..., 3] > 0.5).sum() > 50 and (want[..., 3] == 0).sum() > 10        # object and background both present
+    # expf / powf of the two math libraries differ by an ulp or two per sample, hundreds of samples per ray: 2e-5.  A ray
+    # grazing the box can gain or lose ONE border sample when a position lands an ulp on the other side of a cell
+    # boundary (weight ~ 7e-4 there): allowed on at most 2 pixels, and never more than 1e-3.
+    close = np.isclose(got, want, rtol=2e-5, atol=2e-6)
+    assert (~close).any(-1).sum() <= 2, np.argwhere(~close)
+    np.testing.assert_allclose(got, want, rtol=3e-3, atol=1e-3)
+    # the depth buffer of the last sample pass: the reference leaves MAX_DEPTH (1e10) where no ray was shaded
+    wd = np.array(R['depth'], np.float64).reshape(R['height'], R['width'])
+    shaded = wd < 1e9
+    np.testing.assert_allclose(out['depth'].astype(np.float64)[shaded], wd[shaded], rtol=2e-5, atol=2e-6)
+    assert not out['depth'][~shaded].any()
+
+
+def test_snapshot_parameter_order_matches_nerf_network_set_params():
+    """`params_binary` of a snapshot is the concatenation NerfNetwork::set_params walks (nerf_network.h:361-395, its body
+    run in the harness over recording sub-modules): density MLP, rgb MLP, hash grid, (parameter-free) SH encoding."""
+    rec = {r['module']: r for r in HOST['set_params']}
+    assert [r['module'] for r in sorted(HOST['set_params'], key=lambda r: (r['offset'], r['n_params'] == 0))] == \
+        ['density_network', 'rgb_network', 'pos_encoding', 'dir_encoding']
+    n_grid = syn.nerf_grid_size(1)
+    assert rec['pos_encoding']['n_params'] == 2 * n_grid
+    total = rec['dir_encoding']['offset']
+    params = (np.arange(total) % 2039).astype(np.float16)                  # every position identifiable (< 2048: exact in fp16)
+    wd, wc, grid = nerf.split_params(params, 1)
+    o = rec['density_network']['offset']
+    assert np.array_equal(np.concatenate([w.ravel() for w in wd]), params[o:o + rec['density_network']['n_params']])
+    o = rec['rgb_network']['offset']
+    assert np.array_equal(np.concatenate([w.ravel() for w in wc]), params[o:o + rec['rgb_network']['n_params']])
+    o = rec['pos_encoding']['offset']
+    assert np.array_equal(grid.ravel(), params[o:o + 2 * n_grid])
+    # the product's importer splits the same way (pixtrack_b200/nerf.py::split_params needs the built library for the
+    # grid size only)
+    from pixtrack_b200.nerf import split_params as product_split
+    pd, pc, pg = product_split(params, 1)
+    assert all(np.array_equal(a, b) for a, b in zip((*pd, *pc, pg), (*wd, *wc, grid)))
