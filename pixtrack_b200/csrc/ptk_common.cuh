@@ -7,7 +7,7 @@
 
 #include "pixtrack_b200.h"
 
-#define PTK_MAX_SMS 256
+#define PTK_MAX_SMS 320     // CTA slots of a cooperative LM launch (2 per SM on 148 SMs = 296)
 
 struct PtkContext {
   int device;

@@ -27,6 +27,8 @@
 //    copy of the pose -- identical arithmetic, so no broadcast is needed.
 //  * Grid <= number of SMs (one 512-thread CTA per SM), launched cooperatively
 //    so the spin barrier is safe.
+#include <stdlib.h>
+
 #include "ptk_common.cuh"
 
 namespace {
@@ -337,8 +339,10 @@ struct GroupReduce {
 // phases in registers, so its issue slots go to loads and the interpolation FMAs.
 // kFast: C == 4*LPP (one float4 per lane per texel, compile-time texel stride) and pad >= 1 (all
 // 12 texels in bounds except the two that carry an exactly-zero weight, which are clamped).
-template <int LPP, bool kFast>
-__global__ void __launch_bounds__(kThreads, 1) lm_kernel(const LmParams P) {
+// kCtas: resident CTAs per SM the register allocation is bounded for (1: ~116 registers, 2: 64 -- twice the warps to
+// hide the L2 latency of the gathers behind).
+template <int LPP, bool kFast, int kCtas>
+__global__ void __launch_bounds__(kThreads, kCtas) lm_kernel(const LmParams P) {
   constexpr int PPW = 32 / LPP;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -692,11 +696,20 @@ int pick_lpp(int C) {
   return 32;
 }
 
+int ctas_per_sm() {   // PTK_LM_CTAS = 1 | 2 (default 2)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PTK_LM_CTAS");
+    v = (e != nullptr && atoi(e) == 1) ? 1 : 2;
+  }
+  return v;
+}
+
 void plan(const PtkContext* ctx, const PtkLmProblem* p, int* G, int* n_groups) {
-  const int sms = ctx->num_sms;
+  const int sms = ctx->num_sms * ctas_per_sm();   // co-resident CTA slots of the cooperative launch
   const int lpp = pick_lpp(p->C);
   const int pts_per_pass = kWarps * (32 / lpp);
-  int ng = p->B < sms ? p->B : sms;
+  int ng = p->B < ctx->num_sms ? p->B : ctx->num_sms;
   if (ng < 1) ng = 1;
   int g = sms / ng;
   // do not spread a problem so thin that a CTA has under two passes of work
@@ -769,11 +782,20 @@ extern "C" int ptk_lm_run(PtkContext* ctx, const PtkLmProblem* prob, const PtkLm
   const void* fn = nullptr;
   const int lpp = pick_lpp(p.C);
   const bool fast = (p.C == 4 * lpp) && (p.pad >= 1);
-  switch (lpp) {
-    case 4: fn = fast ? (const void*)lm_kernel<4, true> : (const void*)lm_kernel<4, false>; break;
-    case 8: fn = fast ? (const void*)lm_kernel<8, true> : (const void*)lm_kernel<8, false>; break;
-    case 16: fn = fast ? (const void*)lm_kernel<16, true> : (const void*)lm_kernel<16, false>; break;
-    default: fn = fast ? (const void*)lm_kernel<32, true> : (const void*)lm_kernel<32, false>; break;
+  if (ctas_per_sm() == 2) {
+    switch (lpp) {
+      case 4: fn = fast ? (const void*)lm_kernel<4, true, 2> : (const void*)lm_kernel<4, false, 2>; break;
+      case 8: fn = fast ? (const void*)lm_kernel<8, true, 2> : (const void*)lm_kernel<8, false, 2>; break;
+      case 16: fn = fast ? (const void*)lm_kernel<16, true, 2> : (const void*)lm_kernel<16, false, 2>; break;
+      default: fn = fast ? (const void*)lm_kernel<32, true, 2> : (const void*)lm_kernel<32, false, 2>; break;
+    }
+  } else {
+    switch (lpp) {
+      case 4: fn = fast ? (const void*)lm_kernel<4, true, 1> : (const void*)lm_kernel<4, false, 1>; break;
+      case 8: fn = fast ? (const void*)lm_kernel<8, true, 1> : (const void*)lm_kernel<8, false, 1>; break;
+      case 16: fn = fast ? (const void*)lm_kernel<16, true, 1> : (const void*)lm_kernel<16, false, 1>; break;
+      default: fn = fast ? (const void*)lm_kernel<32, true, 1> : (const void*)lm_kernel<32, false, 1>; break;
+    }
   }
   if (P.G > 1) {
     PTK_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, args, 0, (cudaStream_t)stream));
