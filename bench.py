@@ -354,6 +354,15 @@ def run_ours(args, rank, world, local_rank, wl):
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
+        # every rank launches ~60 kernels per frame from its own host thread: give each rank its own slice of the host
+        # cores, so that the ranks' launch threads (and the pinned-memory copies they enqueue) do not migrate over each other
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per] or cores)
+        except (AttributeError, OSError):
+            pass
+    if world > 1:
         # keep stdout to the one JSON line: NCCL prints its version banner with printf while the communicator is
         # created, so file descriptor 1 points at stderr during the (eager) initialisation and a first collective
         sys.stdout.flush()

@@ -344,6 +344,19 @@ int ptk_nerf_stats(PtkNerf* n, uint64_t* out4);
 int ptk_query_mask(PtkContext* ctx, const uint8_t* depth_u8, int32_t H, int32_t W, const void* image,
                    int32_t img_dtype, void* out_image, uint8_t* out_mask, uint8_t* workspace, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Result overlay (visualisation of a tracked frame).
+ *
+ * Replaces, per frame of pixtrack/visualization/run_vis_on_poses.py:289-371:
+ *   blend_images (:215-219): out = uint8(query * alpha + swap_rb(nerf) * (1 - alpha)) in float64;
+ *   draw_axes (:74-79): three thick lines between the end points add_pose_axes (:82-112) projects on the host.
+ * query / out: [H][W][3] uint8 in the camera frame's channel order (BGR from cv2.imread); nerf: [H][W][3] uint8 RGB
+ * render (ptk_nerf_render out_u8) or NULL = white; host_axes_px: HOST int16 [6][2] end points (x0 y0 x1 y1 per axis)
+ * or NULL = no axes; thickness in pixels.
+ * ---------------------------------------------------------------------- */
+int ptk_overlay(PtkContext* ctx, const uint8_t* query, const uint8_t* nerf, int32_t H, int32_t W, double alpha,
+                const int16_t* host_axes_px, int32_t thickness, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,8 @@ SYMBOLS = {
     'ptk_nerf_stats': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     'ptk_query_mask': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    'ptk_overlay': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_int16),
+                              C.c_int32, C.c_void_p, C.c_void_p]),
     'ptk_copy_d2d': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'ptk_chw_to_hwc': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p]),

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(HERE, '_build')
 LIB = os.path.join(HERE, 'libpixtrack_b200.so')
-SOURCES = ('ptk_api.cu', 'ptk_lm.cu', 'ptk_sample.cu', 'ptk_sample_ref.cu', 'ptk_conv.cu', 'ptk_unet.cu', 'ptk_nerf.cu', 'ptk_mask.cu')
+SOURCES = ('ptk_api.cu', 'ptk_lm.cu', 'ptk_sample.cu', 'ptk_sample_ref.cu', 'ptk_conv.cu', 'ptk_unet.cu', 'ptk_nerf.cu', 'ptk_mask.cu', 'ptk_overlay.cu')
 # per-file extra flags: the NeRF marcher is compiled without FMA contraction so that its geometric decisions
 # (voxel stepping, occupancy tests) are the same IEEE operation sequence as the numpy oracle
 EXTRA_FLAGS = {'ptk_nerf.cu': ['-fmad=false']}
