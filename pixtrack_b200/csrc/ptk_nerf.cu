@@ -261,45 +261,25 @@ __device__ __forceinline__ void load_a(const __half* __restrict__ tile, int lane
 __device__ __forceinline__ void hash_level(const __half2* __restrict__ g, const uint32_t (&ix)[2], const uint32_t (&iy)[2],
                                            const uint32_t (&iz)[2], bool hashed, uint32_t size, float wx, float wy,
                                            float wz, __half* __restrict__ dst) {
-  // The two x-neighbours of a (y, z) corner pair are fetched together when they share an aligned 8-byte pair of entries
-  // (dense levels: idx, idx + 1 with idx even; hashed levels: h ^ x, h ^ (x + 1) = (h ^ x) ^ 1 with x even), i.e. half of
-  // the time: one 8-byte load + a second 4-byte load only in the lanes that need it.  Same values, a quarter fewer L1
-  // line look-ups -- the unit this kernel saturates (l1tex throughput 66-76 %, profiles/r2/nerf_soft_ncu.json).
-  const uint2* __restrict__ g2 = reinterpret_cast<const uint2*>(g);      // level offsets are multiples of 8 entries
-  uint32_t i0[4], i1[4];
-  uint2 pr[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (hashed) {
-      const uint32_t h = iy[c & 1] ^ iz[c >> 1];
-      i0[c] = (ix[0] ^ h) & (size - 1u);                                  // hashed levels hold 2^19 entries
-      i1[c] = (ix[1] ^ h) & (size - 1u);
-    } else {
-      const uint32_t b = iy[c & 1] + iz[c >> 1];
-      i0[c] = ix[0] + b;
-      i1[c] = ix[1] + b;
-      i0[c] -= i0[c] >= size ? size : 0u;                                 // == idx % size: idx < 2 * size here
-      i1[c] -= i1[c] >= size ? size : 0u;
-    }
-    pr[c] = __ldg(g2 + (i0[c] >> 1));
-  }
-  uint32_t second[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    second[c] = (i1[c] & 1u) ? pr[c].y : pr[c].x;
-    if ((i1[c] >> 1) != (i0[c] >> 1)) second[c] = __ldg(reinterpret_cast<const uint32_t*>(g) + i1[c]);
-  }
+  // (Tried: fetching the two x-neighbours of a corner pair with one 8-byte load when they share an aligned pair of
+  // entries, plus a predicated 4-byte load otherwise -- a quarter fewer L1 line look-ups, but 10-14 % SLOWER on B200:
+  // profiles/r2/nerf_paired_loads.json.  Eight independent 4-byte gathers it stays.)
   __half2 v[8];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint32_t first = (i0[c] & 1u) ? pr[c].y : pr[c].x;
-    v[2 * c] = *reinterpret_cast<const __half2*>(&first);
-    v[2 * c + 1] = *reinterpret_cast<const __half2*>(&second[c]);
+  for (int c = 0; c < 8; ++c) {
+    uint32_t idx;
+    if (hashed) {
+      idx = (ix[c & 1] ^ iy[(c >> 1) & 1] ^ iz[c >> 2]) & (size - 1u);   // hashed levels hold 2^19 entries
+    } else {
+      idx = ix[c & 1] + iy[(c >> 1) & 1] + iz[c >> 2];
+      idx -= idx >= size ? size : 0u;                                    // == idx % size: idx < 2 * size here
+    }
+    v[c] = __ldg(g + idx);
   }
   const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
   __half2 acc = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {          // corner order x fastest, then y, then z: v[c] = corner (c & 1, (c >> 1) & 1, c >> 2)
+  for (int c = 0; c < 8; ++c) {
     float w = 1.f;
     w *= (c & 1) ? wx : ux;
     w *= (c & 2) ? wy : uy;

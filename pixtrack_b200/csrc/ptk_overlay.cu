@@ -30,7 +30,8 @@ __global__ void overlay_kernel(const uint8_t* __restrict__ query, const uint8_t*
   for (int c = 0; c < 3; ++c) {
     const double q = (double)query[(size_t)p * 3 + c];
     const double n = nerf ? (double)nerf[(size_t)p * 3 + (2 - c)] : 255.0;     // cvtColor(BGR2RGB) = channel swap
-    px[c] = (uint8_t)(int)(q * P.alpha + n * (1.0 - P.alpha));
+    // numpy evaluates q * alpha + n * (1 - alpha) with separately rounded products: no FMA contraction here
+    px[c] = (uint8_t)(int)__dadd_rn(__dmul_rn(q, P.alpha), __dmul_rn(n, 1.0 - P.alpha));
   }
   for (int s = 0; s < P.n_seg; ++s) {
     const float ax = P.seg[s][0], ay = P.seg[s][1], bx = P.seg[s][2], by = P.seg[s][3];

@@ -59,8 +59,9 @@ def test_network_alone_matches_the_oracle(aabb_scale):
     kernel_grid's arithmetic exactly (fp16 products and sums in corner order) like the oracle, which is itself
     bit-pinned on the reference's kernel_grid (tests/test_nerf_oracle.py).  The MLPs multiply fp16 operands and
     accumulate in fp32 on both sides; they differ in summation order only, which flips an fp16 output by at most one
-    ulp here and there (a flipped hidden activation can move an output a little further): outputs within 4 fp16 ulps,
-    97 % identical or 1 ulp off.  (The reference's wmma path
+    ulp here and there (a flipped hidden activation can move an output a little further): on IDENTICAL encodings the
+    outputs are within 4 fp16 ulps, 97 % identical or 1 ulp off; with each side's own encoding within 12 ulps, 88 %
+    within one (measured: 8 ulps, 92 %).  (The reference's wmma path
     accumulates in fp16 fragments: emulating that in the oracle moves the outputs by <= 3 fp16 ulps -- the stated bound
     of DESIGN.md 6 -- and no uint8 level of a render by more than one.)"""
     tb, m = _testbed(syn.nerf_scene(3, aabb_scale))
@@ -80,16 +81,27 @@ def test_network_alone_matches_the_oracle(aabb_scale):
     # Hence an absolute bound, and ~4 % (2/16 x 30 %) of the values allowed to differ at all.
     de = np.abs(fe - enc)
     assert de.max() <= 1.5e-3 and (de == 0).mean() > 0.94, (de.max(), (de == 0).mean())
-    ref = onerf.network(m, pos, ((d + np.float32(1)) * np.float32(0.5)).astype(np.float32)).astype(np.float32)
     got = out.cpu().numpy()
     assert np.array_equal(got, got.astype(np.float16).astype(np.float32))          # fp16 values, like the reference's output
-    # error in fp16 ulps of the output's magnitude (at least that of 1.0: sums of terms of that size cancel)
-    ulp = np.spacing(np.maximum(np.abs(ref), np.float32(1)).astype(np.float16)).astype(np.float32)
-    err = np.abs(got - ref) / ulp
-    print(f'network alone: max {err.max():.1f} fp16 ulp, {100 * (err == 0).mean():.1f}% identical, '
-          f'{100 * (err <= 1).mean():.2f}% within 1 ulp; encoding: max abs {de.max():.1e}, {100 * (de == 0).mean():.1f}% identical')
-    assert err.max() <= 4.0, err.max()
-    assert (err <= 1.0).mean() > 0.97 and (err == 0).mean() > 0.5, ((err <= 1).mean(), (err == 0).mean())
+    d01 = ((d + np.float32(1)) * np.float32(0.5)).astype(np.float32)
+
+    def ulps(ref):   # error in fp16 ulps of the output's magnitude (at least that of 1.0: terms of that size cancel)
+        return np.abs(got - ref) / np.spacing(np.maximum(np.abs(ref), np.float32(1)).astype(np.float16)).astype(np.float32)
+
+    # (a) the MLPs alone: the oracle's layers on the encoding the KERNEL produced -- only the fp32 summation order differs
+    h = onerf._layer(fe.astype(np.float16), m.w_density[0], True)
+    dens = onerf._layer(h, m.w_density[1], False)
+    x = onerf._layer(np.concatenate([dens, onerf.sh_encode(d01)], 1), m.w_rgb[0], True)
+    x = onerf._layer(x, m.w_rgb[1], True)
+    mlp = np.concatenate([onerf._layer(x, m.w_rgb[2], False)[:, :3], dens[:, :1]], 1).astype(np.float32)
+    ea = ulps(mlp)
+    # (b) end to end: the 4 % of encoding values that differ (above) propagate through five layers
+    eb = ulps(onerf.network(m, pos, d01).astype(np.float32))
+    print(f'MLPs alone: max {ea.max():.1f} fp16 ulp, {100 * (ea == 0).mean():.1f}% identical, {100 * (ea <= 1).mean():.2f}% within 1; '
+          f'with the encoding: max {eb.max():.1f}, {100 * (eb == 0).mean():.1f}% identical, {100 * (eb <= 1).mean():.2f}% within 1; '
+          f'encoding: max abs {de.max():.1e}, {100 * (de == 0).mean():.1f}% identical')
+    assert ea.max() <= 4.0 and (ea <= 1.0).mean() > 0.97 and (ea == 0).mean() > 0.7, (ea.max(), (ea <= 1).mean(), (ea == 0).mean())
+    assert eb.max() <= 12.0 and (eb <= 1.0).mean() > 0.88 and (eb == 0).mean() > 0.6, (eb.max(), (eb <= 1).mean(), (eb == 0).mean())
 
 
 def test_medium_size_shade_render_matches_oracle():
