@@ -230,16 +230,28 @@ def lm_stress(dev, lam, peaks):
     ncu = ncu_summary('r2_lm_ncu.json') or ncu_summary('r1_lm_v3_ncu.json')
     dram = dram_bytes(ncu['launches'][:1]) if ncu else None
     ach = byts / (ms * 1e-3) / 1e9
+    l2 = {}
+    try:      # L2 -> SM traffic and L2 utilisation of the same launch from the committed ncu capture (profiles/r2_lm_ncu.json)
+        r0 = ncu['launches'][0]
+        v, u = r0['l1tex__m_xbar2l1tex_read_bytes.sum'].split()
+        t, tu = r0['gpu__time_duration.sum'].split()
+        l2 = {'l2_to_sm_bytes_ncu': float(v) * {'Gbyte': 1e9, 'Mbyte': 1e6}[u],
+              'l2_to_sm_gbs_ncu': float(v) * {'Gbyte': 1e9, 'Mbyte': 1e6}[u] / (float(t) * {'ms': 1e-3, 'us': 1e-6}[tu]) / 1e9,
+              'lts_throughput_pct_of_peak_ncu': float(r0['lts__throughput.avg.pct_of_peak_sustained_elapsed'].split()[0]),
+              'l1_hit_rate_pct_ncu': float(r0['l1tex__t_sector_hit_rate.pct'].split()[0])}
+    except (KeyError, ValueError, TypeError, IndexError):
+        pass
     return {'kernel': 'lm_kernel', 'bound': 'l2 (latency)',
             'workload': 'C4 level 1: C=128 144x256, N=20000, B=16, 30 fixed iterations', 'ms_per_launch': ms,
             'us_per_iteration': 1e3 * ms / 30, 'algorithmic_gbs': ach, 'algorithmic_bytes': byts,
             'algorithmic_over_hbm_peak': ach / hbm, 'hbm_peak_gbs': hbm,
             'dram_bytes_per_launch_ncu': dram,
             'dram_frac_of_hbm_peak': (dram / (ms * 1e-3) / 1e9 / hbm) if dram else None,
-            'ctas_per_problem': g, 'problems_in_flight': ng,
+            'ctas_per_problem': g, 'problems_in_flight': ng, **l2,
             'note': 'the 19 MB query map is L2-resident: the 52C+32 algorithmic bytes per valid point per iteration are '
-                    'served by L2, DRAM only re-reads the reference descriptors (dram_frac_of_hbm_peak); the kernel is '
-                    'bound by L2 latency / occupancy, see profiles/README.md'}
+                    'served by L2 (L1 hit rate ~4 %), DRAM only re-reads the reference descriptors (dram_frac_of_hbm_peak); '
+                    'the bound is L2 -> SM bandwidth / latency at 32 warps per SM (2 CTAs of 512 threads, 64 registers), see '
+                    'DESIGN.md 3.1'}
 
 
 def ncu_summary(name):
@@ -459,7 +471,7 @@ def run_ours(args, rank, world, local_rank, wl):
     n_launch_plan = 28
     if rank == 0:
         rows = None
-        for _ in range(3):
+        for _ in range(8):       # best of 8: an event-bracketed launch carries ~2 us of launch jitter
             r = ext.profile(devi[0][0]['q'])
             rows = r if rows is None else [(a[0], min(a[1], b[1]), a[2]) for a, b in zip(rows, r)]
         n_launch_plan = len(rows)
