@@ -68,6 +68,16 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination (src must still be a mapped address)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
 constexpr int kC1Stride = 18 * 3 + 2;   // halfs per tile row (56: keeps rows 4-byte aligned)
 
 __global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict__ img, int H, int W,
@@ -107,18 +117,35 @@ __global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict_
     }
   const __half hz = __float2half_rn(0.f);
 
+  // The image tile of the NEXT tile is fetched into registers (4 floats per thread) before the MMAs of the current one,
+  // so its DRAM latency hides behind them instead of sitting between two barriers.
+  float nxt[4];
+  auto fetch = [&](int t) {
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + j * 256;
+      const int yy = i / 54, rr = i - yy * 54;
+      const int xx = rr / 3, c = rr - xx * 3;
+      const int gy = ty * 16 + yy - 1, gx = tx * 16 + xx - 1;
+      nxt[j] = (i < 18 * 54 && gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(img + ((size_t)gy * W + gx) * 3 + c) : 0.f;
+    }
+  };
+  if ((int)blockIdx.x < tiles) fetch(blockIdx.x);
   for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const int x0 = tx * 16, y0 = ty * 16;
     __syncthreads();   // previous tile fully consumed
-    for (int i = threadIdx.x; i < 18 * 54; i += 256) {
-      const int yy = i / 54, rr = i - yy * 54;
-      const int xx = rr / 3, c = rr - xx * 3;
-      const int gy = y0 + yy - 1, gx = x0 + xx - 1;
-      const float v = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[((size_t)gy * W + gx) * 3 + c] : 0.f;
-      tile[yy * kC1Stride + rr] = __float2half_rn(v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + j * 256;
+      if (i < 18 * 54) {
+        const int yy = i / 54, rr = i - yy * 54;
+        tile[yy * kC1Stride + rr] = __float2half_rn(nxt[j]);
+      }
     }
     __syncthreads();
+    if (t + (int)gridDim.x < tiles) fetch(t + gridDim.x);
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       const int ly = warp * 2 + mt;                 // tile row of this m16 tile
@@ -235,35 +262,49 @@ __global__ void __launch_bounds__(256) head_mma_kernel(const __half* __restrict_
                                                        const __half* __restrict__ w, const float* __restrict__ b,
                                                        float* __restrict__ feat, float* __restrict__ conf,
                                                        int normalize, int wpb) {
-  extern __shared__ __align__(16) __half sw[];   // [NT*8][Cin + 8]
+  extern __shared__ __align__(16) __half sw[];   // [NT*8][Cin + 8] weights, then 2 x [wpb * 32 pixels][Cin + 8] activations
   const int ws = Cin + 8;
   const int nout = Cout + 1;
-  const int c8 = Cin >> 3;                        // 16-byte pieces per weight row
+  const int c8 = Cin >> 3;                        // 16-byte pieces per row
+  const int c8_log2 = 31 - __clz(c8);             // Cin is 32, 64 or 512: a power of two
+  // Staging goes through cp.async: every thread has all of its 16-byte pieces in flight at once.  (The plain
+  // load -> store loop this replaces kept ONE load in flight per thread -- 34 dependent L2 round trips for the 132 KB
+  // weight matrix of the coarsest head, 29 us for 0.3 GFLOP.)
   for (int idx = threadIdx.x; idx < NT * 8 * c8; idx += 256) {
-    const int n = idx / c8, q = idx - n * c8;
-    const uint4 v = n < nout ? __ldg(reinterpret_cast<const uint4*>(w + (size_t)n * Cin) + q) : make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(sw + n * ws + q * 8) = v;
+    const int n = idx >> c8_log2, q = idx & (c8 - 1);
+    cp_async16(sw + n * ws + q * 8, reinterpret_cast<const uint4*>(w + (size_t)(n < nout ? n : 0) * Cin) + q, n < nout);
   }
-  __syncthreads();
+  cp_async_commit();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, q2 = (lane & 3) * 2;
   const int groups = (npix + 31) / 32;
-  __half* sa = sw + NT * 8 * ws;                  // [wpb * 32 pixels][Cin + 8] activations of this round
-  // wpb warps of the block take a group of 32 pixels each per round; all 8 warps stage the round's activations
-  // (coalesced 16-byte loads, one round trip) -- per-lane fragment loads from global memory left the single
-  // compute warp of a small map waiting on L2 once per K step
-  for (int base = blockIdx.x * wpb; base < groups; base += gridDim.x * wpb) {
-    __syncthreads();
+  __half* sa0 = sw + NT * 8 * ws;                 // two activation buffers: round i + 1 is staged while round i is computed
+  const int sa_halfs = wpb * 32 * ws;
+  const int stride = gridDim.x * wpb;
+  auto stage = [&](int base, int buf) {
+    __half* sa = sa0 + buf * sa_halfs;
     const int pbase = base * 32;
     for (int idx = threadIdx.x; idx < wpb * 32 * c8; idx += 256) {
-      const int pl = idx / c8, q = idx - pl * c8;
+      const int pl = idx >> c8_log2, q = idx & (c8 - 1);
       const int p = pbase + pl;
-      const uint4 v = p < npix ? __ldg(reinterpret_cast<const uint4*>(x + (size_t)p * Cin) + q) : make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sa + pl * ws + q * 8) = v;
+      cp_async16(sa + pl * ws + q * 8, reinterpret_cast<const uint4*>(x + (size_t)(p < npix ? p : 0) * Cin) + q, p < npix);
+    }
+    cp_async_commit();
+  };
+  int buf = 0;
+  if ((int)blockIdx.x * wpb < groups) stage(blockIdx.x * wpb, 0);
+  // wpb warps of the block take a group of 32 pixels each per round; all 8 warps stage the activations
+  for (int base = blockIdx.x * wpb; base < groups; base += stride, buf ^= 1) {
+    if (base + stride < groups) {
+      stage(base + stride, buf ^ 1);
+      cp_async_wait<1>();                          // everything but the round just issued has landed (weights included)
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const __half* sa = sa0 + buf * sa_halfs;
     const int grp = base + warp;
-    if (warp >= wpb || grp >= groups) continue;
+    if (warp < wpb && grp < groups) {
     const int p0 = grp * 32;
     const __half* ta = sa + warp * 32 * ws;
     float acc[2][NT][4];
@@ -322,6 +363,8 @@ __global__ void __launch_bounds__(256) head_mma_kernel(const __half* __restrict_
         }
       }
     }
+    }   // compute warps
+    __syncthreads();   // this round's buffer is free before the round after next is staged into it
   }
 }
 
@@ -331,7 +374,7 @@ int launch_head(const PtkContext* ctx, const __half* x, long long npix, int Cin,
   const long long groups = (npix + 31) / 32;
   long long wpb = (groups + ctx->num_sms - 1) / ctx->num_sms;
   wpb = wpb < 1 ? 1 : (wpb > 8 ? 8 : wpb);
-  const int smem = (NT * 8 + (int)wpb * 32) * (Cin + 8) * 2;
+  const int smem = (NT * 8 + 2 * (int)wpb * 32) * (Cin + 8) * 2;   // weights + two activation buffers
   static int configured = 0;
   if (configured < smem) {
     PTK_CUDA_CHECK(cudaFuncSetAttribute(head_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
