@@ -567,15 +567,18 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
             for (int t3 = 0; t3 < 3; ++t3) {
               const int tap = tg * 3 + t3;
               const uint64_t bdesc = make_sw128_desc(smem_u32(sB + sb[t3] * kBBytes));
+              // k outer, half tile inner: consecutive MMAs write DIFFERENT accumulators, so an MMA never has to wait for
+              // the accumulate of the one issued just before it
 #pragma unroll
-              for (int sx = 0; sx < 2; ++sx) {
-                // start row of this tap's view: ((1+dy)*24 + 8*sx + 1+dx), 128 B per row, >> 4 in the descriptor
-                const int row0 = (tap / 3) * kHaloW + 8 * sx + (tap % 3);
-                const uint64_t adesc = adesc0 + (uint64_t)(row0 * 8);
-                const uint32_t d = tmem_base + (buf * 2u + (uint32_t)sx) * (uint32_t)N;
+              for (int k = 0; k < kKChunk / 16; ++k) {
 #pragma unroll
-                for (int k = 0; k < kKChunk / 16; ++k)
+                for (int sx = 0; sx < 2; ++sx) {
+                  // start row of this tap's view: ((1+dy)*24 + 8*sx + 1+dx), 128 B per row, >> 4 in the descriptor
+                  const int row0 = (tap / 3) * kHaloW + 8 * sx + (tap % 3);
+                  const uint64_t adesc = adesc0 + (uint64_t)(row0 * 8);
+                  const uint32_t d = tmem_base + (buf * 2u + (uint32_t)sx) * (uint32_t)N;
                   tc_mma_f16(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, ((c - c_begin) | tap | k) != 0 ? 1u : 0u);
+                }
               }
               if (!P.resident) tc_commit(&emptyB[sb[t3]]);
             }
