@@ -724,9 +724,8 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
 // stages / publishes accumulators with multicast commits, and both CTAs run the epilogue on their own
 // TMEM lanes (2 half tiles x 256 columns = all 512 columns, so the epilogue is not overlapped).
 // ---------------------------------------------------------------------------------------------
-constexpr int kPairN = 256;
-constexpr int kPairBBytes = (kPairN / 2) * 128;      // this CTA's half of a weight tile: 16 KB
-constexpr int kPairSlots = 7;
+constexpr int kPairN = 256;                          // widest pair tile (C_out = k * 256); N = 128 is the double-buffered form
+constexpr int kPairBudget = 7 * 128 * 128;           // weight ring per CTA: 112 KB
 
 // TMA load whose completion bytes are credited to the mbarrier at the same offset in the pair's leader CTA
 __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
@@ -753,10 +752,16 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc,
       : "memory");
 }
 
+// N = 256: one accumulator set (2 half tiles x 256 columns = all of TMEM), the epilogue is not overlapped.
+// N = 128: two accumulator sets, so the epilogue of a tile runs under the MMAs of the next one -- the pair then keeps what
+//          it gains on weight traffic (each CTA stages only half of every weight tile).
+template <int N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
     conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmW, const HaloParams P) {
-  constexpr int N = kPairN;
+  constexpr int kPairBBytes = (N / 2) * 128;           // this CTA's half of a weight tile
+  constexpr int kPairSlots = kPairBudget / kPairBBytes;
+  constexpr int kBufs = (4 * N <= 512) ? 2 : 1;        // accumulator sets in TMEM
   constexpr uint32_t kTmemCols = 512;
   // D=F32, A=B=F16 K-major, N >> 3 at bit 17, M (= 256 for the pair) >> 4 at bit 24
   constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -770,8 +775,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
   uint64_t* fullB = emptyA + 2;
   uint64_t* emptyB = fullB + kPairSlots;
   uint64_t* tmem_full = emptyB + kPairSlots;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 1);
+  uint64_t* tmem_empty = tmem_full + kBufs;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + kBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -791,8 +796,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       mbar_init(&fullB[s], 1);
       mbar_init(&emptyB[s], 1);
     }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 8);        // 4 epilogue warps of each CTA arrive on the leader's copy
+    for (int s = 0; s < kBufs; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps of each CTA arrive on the leader's copy
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -839,7 +846,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       // ---------------- MMA issuer of the pair (warp-uniform loop, one elected lane issues) ----------------
       uint32_t a_it = 0, b_it = 0, t_it = 0;
       for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs, ++t_it) {
-        mbar_wait(tmem_empty, (t_it & 1u) ^ 1u);
+        const uint32_t buf = t_it % kBufs;
+        mbar_wait(&tmem_empty[buf], ((t_it / kBufs) & 1u) ^ 1u);
         tc_fence_after();
         for (int c = 0; c < chunks; ++c) {
           const int sa = a_it & 1;
@@ -860,7 +868,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
               for (int sx = 0; sx < 2; ++sx) {
                 const int row0 = (tap / 3) * kHaloW + 8 * sx + (tap % 3);
                 const uint64_t adesc = adesc0 + (uint64_t)(row0 * 8);
-                const uint32_t d = tmem_base + (uint32_t)sx * (uint32_t)N;
+                const uint32_t d = tmem_base + (buf * 2u + (uint32_t)sx) * (uint32_t)N;
 #pragma unroll
                 for (int k = 0; k < kKChunk / 16; ++k)
                   tc_mma_f16_pair(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (c | tap | k) != 0 ? 1u : 0u);
@@ -872,7 +880,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
           if (elect_one()) tc_commit_pair(&emptyA[sa]);
           __syncwarp();
         }
-        if (elect_one()) tc_commit_pair(tmem_full);
+        if (elect_one()) tc_commit_pair(&tmem_full[buf]);
         __syncwarp();
       }
     }
@@ -886,7 +894,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
       const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
       const int h = th * 16 + y, n0 = nb * N;
-      mbar_wait(tmem_full, t_it & 1u);
+      const uint32_t buf = t_it % kBufs;
+      mbar_wait(&tmem_full[buf], (t_it / kBufs) & 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int sx = 0; sx < 2; ++sx) {
@@ -898,7 +907,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
 #pragma unroll 1
         for (int c = 0; c < N; c += 32) {
           uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sx * (uint32_t)N + (uint32_t)c, v);
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2u + (uint32_t)sx) * (uint32_t)N + (uint32_t)c, v);
           uint32_t pw[16];
           const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);
 #pragma unroll
@@ -930,7 +939,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(tmem_empty);
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
     }
   }
 
@@ -1051,15 +1060,17 @@ int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   return PTK_OK;
 }
 
+template <int N>
 int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int n_pairs,
                  cudaStream_t stream) {
-  constexpr int smem = 2 * kHaloBytes + kPairSlots * kPairBBytes + (4 + 2 * kPairSlots + 2) * 8 + 16 + 1024;
+  constexpr int kSlots = kPairBudget / ((N / 2) * 128);
+  constexpr int smem = 2 * kHaloBytes + kPairBudget + (4 + 2 * kSlots + 4) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
-    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo2_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  conv_halo2_kernel<<<2 * n_pairs, kHaloThreads, smem, stream>>>(a0, a1, w, P);   // __cluster_dims__(2, 1, 1)
+  conv_halo2_kernel<N><<<2 * n_pairs, kHaloThreads, smem, stream>>>(a0, a1, w, P);   // __cluster_dims__(2, 1, 1)
   PTK_CUDA_CHECK(cudaGetLastError());
   return PTK_OK;
 }
@@ -1107,16 +1118,19 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
       // 256-channel block (144x256, 43.5 GFLOP): 40.9 us as pairs vs 40.8 us single-CTA -- the layer is bound by MMA
       // execution + issue, not by the operand bytes a pair saves, and the pair's epilogue is not overlapped -- so the
       // single-CTA kernel stays the default; the pair kernel is kept (and tested) for the shapes where B traffic binds.
-      static int pair_mode = -1;
+      static int pair_mode = -1, pair_n_env = 128;   // PTK_CONV_PAIR_N = 128 (double-buffered accumulators, default) | 256
       if (pair_mode < 0) {
         const char* e = getenv("PTK_CONV_PAIR");
         pair_mode = e ? atoi(e) : 0;
+        const char* n = getenv("PTK_CONV_PAIR_N");
+        if (n && atoi(n) == 256) pair_n_env = 256;
       }
+      const int pair_n = (pair_n_env == 256 && Cout % 256 == 0) ? 256 : 128;
       const int pairs_w = (tiles_w16 + 1) / 2;
-      const int total_pairs = pairs_w * tiles_h16 * (Cout / kPairN);
+      const int total_pairs = pairs_w * tiles_h16 * (Cout / pair_n);
       const int pair_slots = ctx->num_sms / 2;
       const int pwaves = (total_pairs + pair_slots - 1) / pair_slots;
-      const bool pair_legal = taps == 9 && Cout % kPairN == 0 && mode != 0;
+      const bool pair_legal = taps == 9 && Cout % pair_n == 0 && mode != 0;
       const bool pair_wanted = pair_mode == 2 || (pair_mode == 1 && total_pairs * 10 >= pwaves * pair_slots * 8);
       if (pair_legal && pair_wanted) {
         rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kHaloW, rows_per_op);
@@ -1127,7 +1141,7 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
         } else {
           a1 = a0;
         }
-        rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, kPairN / 2, 1);
+        rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, pair_n / 2, 1);
         if (rc != PTK_OK) return rc;
         HaloParams Q;
         Q.H = H; Q.W = W; Q.Cout = Cout; Q.chunks0 = cin0 / kKChunk; Q.chunks1 = cin1 / kKChunk; Q.relu = relu;
@@ -1138,7 +1152,8 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
         Q.bias = bias;
         Q.out = (__half*)out;
         Q.pool = (__half*)pool_out;
-        return launch_halo2(a0, a1, wm, Q, total_pairs < pair_slots ? total_pairs : pair_slots, s);
+        const int n_launch = total_pairs < pair_slots ? total_pairs : pair_slots;
+        return pair_n == 256 ? launch_halo2<256>(a0, a1, wm, Q, n_launch, s) : launch_halo2<128>(a0, a1, wm, Q, n_launch, s);
       }
     }
     const bool legal = taps == 9 && (Cout == 32 || Cout == 64 || Cout % 128 == 0);

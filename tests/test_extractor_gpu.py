@@ -234,7 +234,7 @@ import sys, torch, torch.nn.functional as tF
 sys.path.insert(0, %r)
 from pixtrack_b200.extractor import conv_f16, pack_conv3x3
 g = torch.Generator().manual_seed(5)
-for cin, cout, H, W in [(128, 256, 40, 70), (64, 512, 33, 17)]:
+for cin, cout, H, W in [(128, 256, 40, 70), (64, 512, 33, 17), (128, 128, 100, 90), (256, 256, 144, 256)]:
     x = torch.randn(H, W, cin, generator=g).half().cuda()
     w = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).half().cuda()
     b = torch.randn(cout, generator=g).cuda()
@@ -244,6 +244,7 @@ for cin, cout, H, W in [(128, 256, 40, 70), (64, 512, 33, 17)]:
     assert err < 4e-3 * max(1.0, ref.abs().max().item()), err
 print("pair ok")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PTK_CONV_PAIR='2')
-    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and 'pair ok' in r.stdout, r.stdout + r.stderr
+    for pair_n in ('128', '256'):      # N = 128: two accumulator sets in TMEM (epilogue overlapped); N = 256: one
+        env = dict(os.environ, PTK_CONV_PAIR='2', PTK_CONV_PAIR_N=pair_n)
+        r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and 'pair ok' in r.stdout, (pair_n, r.stdout + r.stderr)
