@@ -7,7 +7,8 @@
 // Three kernels, chosen per layer by ptk_conv_f16_pool (bottom of the file):
 //   conv_halo_kernel   persistent, one halo load per 64-channel chunk, taps = shifted descriptors (default for the
 //                      large maps; see its header comment)
-//   conv_halo2_kernel  the same on CTA pairs (tcgen05 cta_group::2); off by default (PTK_CONV_PAIR)
+//   conv_halo2_kernel  the same on CTA pairs (tcgen05 cta_group::2, M = 256 x N = 128 with two accumulator sets in TMEM):
+//                      the many-channel layers on large maps (PTK_CONV_PAIR)
 //   conv_tc_kernel     one tap-shifted TMA box per k-step; small maps and 1x1 (described next); SPLIT = 2 shares the
 //                      K loop of a tile between the two CTAs of a cluster (partial sums through DSMEM)
 // All epilogues add the bias (conv bias or folded BatchNorm), apply ReLU, write fp16 and can also write the
@@ -1114,14 +1115,16 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
     const int total = tiles_w16 * tiles_h16 * (Cout / n_halo);
     // CTA pairs (cta_group::2): C_out = k * 256 and enough pairs of 16x16 tiles for most of a wave of SM pairs
     {
-      // PTK_CONV_PAIR: 0 = never (default), 1 = when the pairs fill a wave, 2 = whenever legal.  Measured on the
-      // 256-channel block (144x256, 43.5 GFLOP): 40.9 us as pairs vs 40.8 us single-CTA -- the layer is bound by MMA
-      // execution + issue, not by the operand bytes a pair saves, and the pair's epilogue is not overlapped -- so the
-      // single-CTA kernel stays the default; the pair kernel is kept (and tested) for the shapes where B traffic binds.
+      // PTK_CONV_PAIR: 0 = never, 1 = when the pairs fill a wave and K is long enough (default), 2 = whenever legal.
+      // Measured on the 256-channel block (144x256, 43.5 GFLOP per layer), 10 launches back to back: single-CTA halo
+      // kernel 44.7 us (972 TF/s: 17 % of the MMA warp's time waits for weight tiles, 84 cycles per MMA); pair with
+      // N = 256 (one accumulator set, epilogue not overlapped) 38.9 us; pair with N = 128 (two accumulator sets)
+      // **34.5-35.8 us = 1 210-1 260 TF/s**.  With only one or two 64-channel chunks per tile (C_in <= 128) the pair
+      // gains nothing (the layers are bound by the halo fetch and the per-tile fixed costs), hence the K condition.
       static int pair_mode = -1, pair_n_env = 128;   // PTK_CONV_PAIR_N = 128 (double-buffered accumulators, default) | 256
       if (pair_mode < 0) {
         const char* e = getenv("PTK_CONV_PAIR");
-        pair_mode = e ? atoi(e) : 0;
+        pair_mode = e ? atoi(e) : 1;
         const char* n = getenv("PTK_CONV_PAIR_N");
         if (n && atoi(n) == 256) pair_n_env = 256;
       }
@@ -1131,7 +1134,8 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
       const int pair_slots = ctx->num_sms / 2;
       const int pwaves = (total_pairs + pair_slots - 1) / pair_slots;
       const bool pair_legal = taps == 9 && Cout % pair_n == 0 && mode != 0;
-      const bool pair_wanted = pair_mode == 2 || (pair_mode == 1 && total_pairs * 10 >= pwaves * pair_slots * 8);
+      const bool pair_wanted = pair_mode == 2 ||
+                               (pair_mode == 1 && ctot >= 4 * kKChunk && total_pairs * 10 >= pwaves * pair_slots * 8);
       if (pair_legal && pair_wanted) {
         rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kHaloW, rows_per_op);
         if (rc != PTK_OK) return rc;

@@ -94,6 +94,29 @@ def test_halo_kernels_two_inputs_with_crop(cin0, cin1, cout, H, W, grow):
     _check(y, _ref(x, w, b, True, x1=x1, hw=(H, W)), (cin0, cin1, cout))
 
 
+@pytest.mark.parametrize('cin0,cin1,cout,H,W,pool', [
+    (256, 0, 256, 144, 256, False),      # the 256-channel block of the 1024x576 plan: 72 pairs x 2 C_out groups
+    (256, 0, 256, 144, 256, True),       # its last layer writes the fused pool
+    (256, 0, 256, 189, 252, True),       # the same block of the 1008x756 plan: odd height, pooled to 94 x 126
+    (128, 128, 128, 150, 250, False),    # two inputs, ragged pair columns (16 tile columns -> 8 pairs, last one half empty)
+])
+def test_cta_pair_kernel_default_dispatch(cin0, cin1, cout, H, W, pool):
+    """Many-channel 3x3 layers on large maps (C_in >= 256, pairs filling >= 80 % of their last wave of 74 SM pairs) run
+    on conv_halo2_kernel<128>: tcgen05 cta_group::2, M = 256 x N = 128, two accumulator sets in TMEM."""
+    from pixtrack_b200.extractor import conv_f16, pack_conv3x3
+    x, x1, w, b = _case(cin0, cout, H, W, seed=cin0 + cout + H + pool, cin1=cin1)
+    out = conv_f16(x, pack_conv3x3(w), b, relu=True, x1=x1, out_hw=(H, W), pool=pool)
+    torch.cuda.synchronize()
+    y = out[0] if pool else out
+    _check(y, _ref(x, w, b, True, x1=x1, hw=(H, W)), (cin0, cin1, cout, H, W))
+    if pool:
+        want = tF.max_pool2d(y.float().permute(2, 0, 1)[None], 2, 2)[0].permute(1, 2, 0)
+        assert torch.equal(out[1].float(), want)
+    again = conv_f16(x, pack_conv3x3(w), b, relu=True, x1=x1, out_hw=(H, W))
+    torch.cuda.synchronize()
+    assert torch.equal(again, y)
+
+
 SPLIT_SHAPES = [
     (512, 0, 512, 36, 64, False),       # 1/16-scale block of the 1024x576 plan: halo<128, SPLIT 2>, 48 tiles x 2 CTAs
     (512, 0, 512, 47, 63, False),       # ... of the 1008x756 plan (odd sizes, ragged tiles)
