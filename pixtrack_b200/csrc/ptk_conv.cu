@@ -1115,12 +1115,13 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
     const int total = tiles_w16 * tiles_h16 * (Cout / n_halo);
     // CTA pairs (cta_group::2): C_out = k * 256 and enough pairs of 16x16 tiles for most of a wave of SM pairs
     {
-      // PTK_CONV_PAIR: 0 = never, 1 = when the pairs fill a wave and K is long enough (default), 2 = whenever legal.
+      // PTK_CONV_PAIR: 0 = never, 1 = when the pairs fill a wave and the weights are streamed (default), 2 = whenever legal.
       // Measured on the 256-channel block (144x256, 43.5 GFLOP per layer), 10 launches back to back: single-CTA halo
       // kernel 44.7 us (972 TF/s: 17 % of the MMA warp's time waits for weight tiles, 84 cycles per MMA); pair with
       // N = 256 (one accumulator set, epilogue not overlapped) 38.9 us; pair with N = 128 (two accumulator sets)
-      // **34.5-35.8 us = 1 210-1 260 TF/s**.  With only one or two 64-channel chunks per tile (C_in <= 128) the pair
-      // gains nothing (the layers are bound by the halo fetch and the per-tile fixed costs), hence the K condition.
+      // **34.5-35.8 us = 1 210-1 260 TF/s**.  Also N = 64 (decoder blocks 64+128->64 at 288x512: 51.2 -> 38.5 us,
+      // 64+256->64 at 144x256: 28.6 -> 22.0 us; their weights do not fit the single-CTA kernel's resident slots, and 20 %
+      // of its MMA warp's time waits for weight tiles).  `profiles/r2/conv_layers_pair_forced.txt` has every layer as pairs.
       static int pair_mode = -1, pair_n_env = 128;   // PTK_CONV_PAIR_N = 128 (double-buffered accumulators, default) | 256
       if (pair_mode < 0) {
         const char* e = getenv("PTK_CONV_PAIR");
@@ -1128,14 +1129,18 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
         const char* n = getenv("PTK_CONV_PAIR_N");
         if (n && atoi(n) == 256) pair_n_env = 256;
       }
-      const int pair_n = (pair_n_env == 256 && Cout % 256 == 0) ? 256 : 128;
+      const int pair_n = Cout == 64 ? 64 : ((pair_n_env == 256 && Cout % 256 == 0) ? 256 : 128);
       const int pairs_w = (tiles_w16 + 1) / 2;
       const int total_pairs = pairs_w * tiles_h16 * (Cout / pair_n);
       const int pair_slots = ctx->num_sms / 2;
       const int pwaves = (total_pairs + pair_slots - 1) / pair_slots;
       const bool pair_legal = taps == 9 && Cout % pair_n == 0 && mode != 0;
+      // not for layers whose weights the single-CTA kernel keeps resident in shared memory (C_out <= 64 with few
+      // chunks): there is no weight traffic to halve, and the pair's ring re-streams them per tile (64->64 at full
+      // resolution: 62 us single, 84 us as pairs)
+      const bool single_resident = Cout == n_halo && 9 * (ctot / kKChunk) <= kBBudget / (n_halo * 128);
       const bool pair_wanted = pair_mode == 2 ||
-                               (pair_mode == 1 && ctot >= 4 * kKChunk && total_pairs * 10 >= pwaves * pair_slots * 8);
+                               (pair_mode == 1 && !single_resident && total_pairs * 10 >= pwaves * pair_slots * 8);
       if (pair_legal && pair_wanted) {
         rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kHaloW, rows_per_op);
         if (rc != PTK_OK) return rc;
@@ -1157,6 +1162,7 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
         Q.out = (__half*)out;
         Q.pool = (__half*)pool_out;
         const int n_launch = total_pairs < pair_slots ? total_pairs : pair_slots;
+        if (pair_n == 64) return launch_halo2<64>(a0, a1, wm, Q, n_launch, s);
         return pair_n == 256 ? launch_halo2<256>(a0, a1, wm, Q, n_launch, s) : launch_halo2<128>(a0, a1, wm, Q, n_launch, s);
       }
     }

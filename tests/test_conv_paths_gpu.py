@@ -99,10 +99,13 @@ def test_halo_kernels_two_inputs_with_crop(cin0, cin1, cout, H, W, grow):
     (256, 0, 256, 144, 256, True),       # its last layer writes the fused pool
     (256, 0, 256, 189, 252, True),       # the same block of the 1008x756 plan: odd height, pooled to 94 x 126
     (128, 128, 128, 150, 250, False),    # two inputs, ragged pair columns (16 tile columns -> 8 pairs, last one half empty)
+    (64, 128, 64, 288, 512, False),      # decoder block 2 of the 1024x576 plan: conv_halo2_kernel<64>, 3 chunks over two inputs
+    (64, 256, 64, 144, 256, False),      # decoder block 1: 5 chunks
 ])
 def test_cta_pair_kernel_default_dispatch(cin0, cin1, cout, H, W, pool):
-    """Many-channel 3x3 layers on large maps (C_in >= 256, pairs filling >= 80 % of their last wave of 74 SM pairs) run
-    on conv_halo2_kernel<128>: tcgen05 cta_group::2, M = 256 x N = 128, two accumulator sets in TMEM."""
+    """3x3 layers whose weights are streamed (not resident in shared memory) and whose tile pairs fill >= 80 % of their last
+    wave of 74 SM pairs run on conv_halo2_kernel<N>: tcgen05 cta_group::2, M = 256 x N = 128 or 64, two (or more)
+    accumulator sets in TMEM."""
     from pixtrack_b200.extractor import conv_f16, pack_conv3x3
     x, x1, w, b = _case(cin0, cout, H, W, seed=cin0 + cout + H + pool, cin1=cin1)
     out = conv_f16(x, pack_conv3x3(w), b, relu=True, x1=x1, out_hw=(H, W), pool=pool)
