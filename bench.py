@@ -67,6 +67,12 @@ WORKLOADS = {
 }
 
 
+def log(msg):
+    """Progress on stderr with PTK_BENCH_VERBOSE=1 (stdout carries only the JSON line)."""
+    if os.environ.get('PTK_BENCH_VERBOSE'):
+        print(f'[bench {time.strftime("%H:%M:%S")}] {msg}', file=sys.stderr, flush=True)
+
+
 def lam0():
     return 10.0 ** (-6.0 + torch.sigmoid(torch.zeros(6)) * 11.0)
 
@@ -426,6 +432,7 @@ def run_ours(args, rank, world, local_rank, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    log('objects built; set-up steps')
     # ---- set-up: every (plan, binding) is seen three times (launch, capture, replay) and the LM chain captured, whatever
     #      --warmup says; then the W warm-up steps the caller asked for -------------------------------------------------
     for i in range(3 * RING * n_obj):
@@ -434,6 +441,7 @@ def run_ours(args, rank, world, local_rank, wl):
         step(i)
     barrier()
 
+    log('warm; timing device-resident passes')
     # ---- device-resident timing: K frames, images already in HBM ---------------------------------
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -447,6 +455,7 @@ def run_ours(args, rank, world, local_rank, wl):
     _lib.device_status(local_rank)
     clk = clocks.stop() if rank == 0 else None
 
+    log('device-resident passes done')
     # ---- results of the last ring pass: LM iteration counts, failures, pose error vs ground truth ------
     iters, errs, ok = [], [], True
     if tbs is None:
@@ -461,6 +470,7 @@ def run_ours(args, rank, world, local_rank, wl):
             dR, dt = pose_distance(T.cpu(), Tgt)
             errs.append([float(torch.rad2deg(dR).median()), float(dt.median())])
 
+    log('results read back; rooflines')
     # ---- rooflines (rank 0): per-launch CUDA-event timing of the extractor plan; LM stress ---------------
     peaks = {}
     try:
@@ -499,6 +509,7 @@ def run_ours(args, rank, world, local_rank, wl):
                     'flop_per_launch': tc_fl / n_tc}
         stress = lm_stress(dev, lam, peaks)
 
+    log('rooflines done; e2e')
     # ---- end to end: host images in (pinned -> device staging), poses out --------------------------------
     # Camera frames do not depend on the pose, so the upload of frame i+1 runs on a copy stream while frame i is
     # tracked (two staging sets); every step still uploads its own inputs inside the timed region and ends with a
@@ -537,6 +548,7 @@ def run_ours(args, rank, world, local_rank, wl):
     h2d = host[0][0]['q'].numel() + (host[0][0]['r'].numel() if tbs is None else 0)
     d2h = N_VIEWS * 13 * 4           # [B,12] fp32 poses + B failure flags, read back as one pinned fp32 buffer
 
+    log('e2e done; nerf legs')
     # ---- NeRF legs (rank 0): the renders alone, and (for the NeRF-less workloads) the frame with the reference-view
     #      render in front ------------------------------------------------------------------------------------------
     nerf = None
@@ -581,6 +593,7 @@ def run_ours(args, rank, world, local_rank, wl):
             torch.cuda.synchronize()
             nerf['frames_per_s_with_reference_render'] = 1e3 * args.steps / ev[0].elapsed_time(ev[1])
 
+    log('nerf legs done; gather')
     # ---- final gather of per-unit results (the only collective on this path): unit = this rank's sequence,
     #      its result = the pose of the best view --------------------------------------------------------
     best = 0
@@ -591,8 +604,11 @@ def run_ours(args, rank, world, local_rank, wl):
     if rank == 0:
         cpu = parity = library = None
         if world == 1 and tbs is None:
+            log('cpu leg')
             cpu, parity = cpu_leg(trk, step, seq, wl, dev)
+            log('library leg')
             library = library_leg(trk, step, seq, wl, dev, args.steps)
+            log('legs done')
         fps = args.steps * world / (ms_total * 1e-3)
         launches_per_frame = 2 * n_launch_plan + 1 + 3 + (4 + 6 if tbs else 0)
         line = {
