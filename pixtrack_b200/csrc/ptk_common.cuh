@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "pixtrack_b200.h"
@@ -35,6 +36,56 @@ struct PtkDeviceGuard {
     if (switched) cudaSetDevice(prev);
   }
 };
+
+// ---- programmatic dependent launch (PDL) ----
+// Kernels of a chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may
+// start (barrier / TMEM set-up, tensor-map and weight prefetch) while the previous kernel drains, and block in
+// ptk_pdl_wait() until the previous grid has COMPLETED and its writes are visible -- before their first access to anything
+// a predecessor wrote, and before their first write.  Rule: every kernel launched through ptk_launch_pdl calls
+// ptk_pdl_wait() on at least one thread of every CTA before it exits (completion of a kernel then implies completion of
+// everything before it in the stream), and ptk_pdl_trigger() only after the wait (at most two kernels of a chain are
+// in flight).  PTK_PDL=0 launches without the attribute (the device calls are then no-ops).
+#ifdef __CUDACC__
+__device__ __forceinline__ void ptk_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ptk_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool ptk_pdl_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("PTK_PDL");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode != 0;
+}
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute (and an optional runtime cluster shape)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ptk_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         dim3 cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster.x * cluster.y * cluster.z > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster.x;
+    attr[n].val.clusterDim.y = cluster.y;
+    attr[n].val.clusterDim.z = cluster.z;
+    ++n;
+  }
+  if (ptk_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 #define PTK_CUDA_CHECK(expr)                                                            \
   do {                                                                                  \

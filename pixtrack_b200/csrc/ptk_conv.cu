@@ -160,6 +160,58 @@ __device__ __forceinline__ void pool_quad(uint32_t (&pw)[16]) {
   }
 }
 
+// Biases of a tile's N output channels, one private copy per epilogue warp in shared memory.  (Read straight from global
+// memory in the epilogue loop they miss L1 every time -- the output stores stream through it -- and each 32-channel step
+// then waits an L2 round trip: measured ~700 of the 860 cycles a step took.)  Loaded before the warp waits for the
+// accumulators, so the latency is hidden.
+template <int N>
+__device__ __forceinline__ void stage_bias(float* s_bias, const float* bias, int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int i = lane * 4; i < N; i += 128) *reinterpret_cast<float4*>(s_bias + i) = __ldg(reinterpret_cast<const float4*>(bias + i));
+  __syncwarp();
+}
+
+// Output rows are written by lane PAIRS: a lane holds 32 output channels (64 B) of its own pixel, but a warp-wide 16-byte
+// store of those scatters over 32 different lines -- 128 requests of 16 B per 32 channels, and the SM's store path, not
+// the tensor pipe, then bounds every layer with a large output map (measured: 9.4 K cycles of epilogue per 256 x 128 tile
+// against 4.7 K cycles of MMAs).  Lanes 2i and 2i + 1 swap halves instead: each store instruction writes 32 B per lane
+// and the pair covers one pixel's 64 contiguous bytes -- two full sectors per request, 32 requests per 32 channels.
+struct PairStore {
+  __half* row[2];     // output rows of the even / odd pixel of this lane's pair (already offset to this lane's half)
+  bool ok[2];
+};
+__device__ __forceinline__ PairStore pair_store_setup(__half* orow, bool inside, int lane) {
+  PairStore s;
+  const unsigned long long p = reinterpret_cast<unsigned long long>(orow);
+  const int half_off = (lane & 1) * 16;
+  s.row[0] = reinterpret_cast<__half*>(__shfl_sync(0xffffffffu, p, lane & ~1)) + half_off;
+  s.row[1] = reinterpret_cast<__half*>(__shfl_sync(0xffffffffu, p, lane | 1)) + half_off;
+  const unsigned m = __ballot_sync(0xffffffffu, inside);
+  s.ok[0] = (m >> (lane & ~1)) & 1u;
+  s.ok[1] = (m >> (lane | 1)) & 1u;
+  return s;
+}
+__device__ __forceinline__ void st_global_256(__half* dst, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// pw: this lane's 32 packed fp16 outputs for channels [c, c + 32) of its own pixel.  Called by the whole warp.
+__device__ __forceinline__ void pair_store(const PairStore& s, int c, const uint32_t (&pw)[16], int lane) {
+  const bool odd = lane & 1;
+  uint32_t a[8], b[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const uint32_t send = odd ? pw[r] : pw[8 + r];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    a[r] = odd ? recv : pw[r];         // even pixel: low half from the even lane, high half from the even lane via the odd one
+    b[r] = odd ? pw[8 + r] : recv;     // odd pixel
+  }
+  if (s.ok[0]) st_global_256(s.row[0] + c, a);
+  if (s.ok[1]) st_global_256(s.row[1] + c, b);
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -215,6 +267,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   uint64_t* peer_bar = tmem_full_bar + 1;                       // SPLIT: rank 1's partial sums have landed
   uint32_t* tmem_slot = (uint32_t*)(peer_bar + 1);
   float* xbuf = (float*)(smem + STAGES * kStageBytes + 256);    // SPLIT: [BLOCK_N / 4][128][4] fp32 partial sums of rank 1
+  float* s_bias = (float*)(smem + STAGES * kStageBytes + 256 + (SPLIT > 1 ? BLOCK_N * 128 * 4 : 0));   // [BLOCK_N], shared by the 4 epilogue warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
@@ -254,18 +307,32 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      for (int ks = 0; ks < num_steps; ++ks) {
-        const int stage = ks % STAGES;
-        const uint32_t phase = (uint32_t)(ks / STAGES) & 1u;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        const int kg = ks_begin + ks;
+      // The weight tiles of the first ring of stages do not depend on the previous kernel: they are requested BEFORE the
+      // programmatic-dependent-launch wait, the activation tiles after it.
+      const int pre = num_steps < STAGES ? num_steps : STAGES;
+      for (int ks = 0; ks < num_steps + pre; ++ks) {
+        // passes 0 .. pre-1: weights of step ks; pass pre .. 2 pre - 1: activations of step ks - pre; then both per step
+        const bool w_only = ks < pre, a_only = ks >= pre && ks < 2 * pre;
+        const int step = w_only ? ks : ks - pre;
+        if (ks == pre) {
+          ptk_pdl_wait();
+          ptk_pdl_trigger();
+        }
+        const int stage = step % STAGES;
+        const uint32_t phase = (uint32_t)(step / STAGES) & 1u;
+        const int kg = ks_begin + step;
         const int tap = kg / steps_per_tap, cc = kg - tap * steps_per_tap;
         const int dy = (P.taps == 9) ? tap / 3 - 1 : 0, dx = (P.taps == 9) ? tap % 3 - 1 : 0;
         uint8_t* sa = smem + stage * kStageBytes;
-        mbar_expect_tx(&full_bar[stage], kStageBytes);
-        if (cc < chunks0) tma_load_3d(sa, &tmA0, &full_bar[stage], cc * kKChunk, w0 + dx, h0 + dy);
-        else tma_load_3d(sa, &tmA1, &full_bar[stage], (cc - chunks0) * kKChunk, w0 + dx, h0 + dy);
-        tma_load_3d(sa + kABytes, &tmW, &full_bar[stage], cc * kKChunk, n0, tap);
+        if (!a_only) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_3d(sa + kABytes, &tmW, &full_bar[stage], cc * kKChunk, n0, tap);
+        }
+        if (!w_only) {
+          if (cc < chunks0) tma_load_3d(sa, &tmA0, &full_bar[stage], cc * kKChunk, w0 + dx, h0 + dy);
+          else tma_load_3d(sa, &tmA1, &full_bar[stage], (cc - chunks0) * kKChunk, w0 + dx, h0 + dy);
+        }
       }
     }
   } else if (warp == 1) {
@@ -295,6 +362,9 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     const int m = q * 32 + lane;                  // row of the tile = pixel
     const int h = h0 + (m >> P.tw_log2), w = w0 + (m & ((1 << P.tw_log2) - 1));
     const bool inside = (h < P.H) && (w < P.W);
+    // biases of this tile's channels -> shared memory (see stage_bias), before waiting for the accumulators
+    for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) s_bias[i] = __ldg(P.bias + n0 + i);
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (SPLIT > 1 && krank != 0) {   // hand the partial sums to rank 0 and leave
@@ -314,6 +384,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     } else {
     if (SPLIT > 1) mbar_wait_cluster(peer_bar, 0);
     __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
+    const PairStore ps = pair_store_setup(orow, inside, lane);
     const bool pool_writer = P.pool != nullptr && ((lane & 17) == 0) && (h >> 1) < (P.H >> 1) && (w >> 1) < (P.W >> 1);
     __half* prow = P.pool != nullptr ? P.pool + ((size_t)(h >> 1) * (P.W >> 1) + (w >> 1)) * P.Cout + n0 : nullptr;
 #pragma unroll 1
@@ -331,10 +402,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         }
       }
       uint32_t pw[16];
-      const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);   // 32 consecutive biases, 16-byte loads
+      const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);   // 32 consecutive biases, broadcast 16-byte loads
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float4 bq = __ldg(b4 + (j >> 1));
+        const float4 bq = b4[j >> 1];
         float a = __uint_as_float(v[2 * j]) + ((j & 1) ? bq.z : bq.x);
         float b = __uint_as_float(v[2 * j + 1]) + ((j & 1) ? bq.w : bq.y);
         if (P.relu) {
@@ -344,11 +415,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         const __half2 hv = __floats2half2_rn(a, b);
         pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
       }
-      if (inside) {
-        uint4* dst = reinterpret_cast<uint4*>(orow + c);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
-      }
+      pair_store(ps, c, pw, lane);
       if (P.pool != nullptr) {   // x neighbour = lane ^ 1, y neighbour = lane ^ 16
         pool_quad<16>(pw);
         if (pool_writer) {
@@ -440,6 +507,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
   uint64_t* go_bar = tmem_empty + 2;       // SPLIT, on rank 1: rank 0's MMAs have retired, its staging area may be written
   uint64_t* peer_bar = go_bar + 1;         // SPLIT, on rank 0: rank 1's partial sums have landed
   uint32_t* tmem_slot = (uint32_t*)(peer_bar + 1);
+  float* s_bias_all = reinterpret_cast<float*>(tmem_slot + 4);   // [8 epilogue warps][N]
   float* xbuf = reinterpret_cast<float*>(smem);   // SPLIT: [N][256] fp32 partial sums of rank 1 (aliases sA / sB)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -485,7 +553,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       uint32_t a_it = 0, b_it = 0;
-      bool first = true;
+      bool first = true, waited = false;
       const bool timed = P.dbg != nullptr && blockIdx.x == 0;
       long long wA = 0, wB = 0;
       const long long tstart = clock64();
@@ -494,17 +562,9 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
         const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
         const int h0 = th * 16, w0 = tw * 16, n0 = nb * N;
         for (int c = c_begin; c < c_end; ++c) {
-          const int sa = a_it & 1;
-          mbar_wait_t(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u, wA, timed);
-          mbar_expect_tx(&fullA[sa], kHaloBytes);
-          for (int r = 0; r < kHaloH; r += P.rows_per_op) {
-            uint8_t* dst = sA + sa * kHaloBytes + r * (kHaloW * 128);
-            if (c < P.chunks0) tma_load_3d(dst, &tmA0, &fullA[sa], c * kKChunk, w0 - 1, h0 - 1 + r);
-            else tma_load_3d(dst, &tmA1, &fullA[sa], (c - P.chunks0) * kKChunk, w0 - 1, h0 - 1 + r);
-          }
-          ++a_it;
-          if (!P.resident || first) {
-            for (int tap = 0; tap < 9; ++tap) {
+          auto load_weights = [&](int tap_begin, int tap_end) {
+            if (P.resident && !first) return;
+            for (int tap = tap_begin; tap < tap_end; ++tap) {
               int sb;
               if (P.resident) {
                 sb = (c - c_begin) * 9 + tap;
@@ -516,9 +576,33 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
               tma_load_3d(sB + sb * kBBytes, &tmW, &fullB[sb], c * kKChunk, n0, tap);
               ++b_it;
             }
+          };
+          // The first weight tiles do not depend on the previous kernel: they are requested BEFORE the
+          // programmatic-dependent-launch wait (as many as have a free slot without any MMA having run).
+          int taps_done = 0;
+          if (!waited) {
+            taps_done = kSlots < 9 ? kSlots : 9;
+            load_weights(0, taps_done);
+            ptk_pdl_wait();
+            ptk_pdl_trigger();
+            waited = true;
           }
+          const int sa = a_it & 1;
+          mbar_wait_t(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u, wA, timed);
+          mbar_expect_tx(&fullA[sa], kHaloBytes);
+          for (int r = 0; r < kHaloH; r += P.rows_per_op) {
+            uint8_t* dst = sA + sa * kHaloBytes + r * (kHaloW * 128);
+            if (c < P.chunks0) tma_load_3d(dst, &tmA0, &fullA[sa], c * kKChunk, w0 - 1, h0 - 1 + r);
+            else tma_load_3d(dst, &tmA1, &fullA[sa], (c - P.chunks0) * kKChunk, w0 - 1, h0 - 1 + r);
+          }
+          ++a_it;
+          load_weights(taps_done, 9);
         }
         first = false;
+      }
+      if (!waited) {   // no work for this CTA: still part of the chain
+        ptk_pdl_wait();
+        ptk_pdl_trigger();
       }
       if (timed) {
         P.dbg[0] = clock64() - tstart;
@@ -615,6 +699,9 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
       const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
       const int h = th * 16 + y, n0 = nb * N;
       const uint32_t buf = t_it & 1u;
+      float* s_bias = s_bias_all + (warp - 2) * N;
+      if (N >= 128) stage_bias<N>(s_bias, P.bias + n0, lane);
+      else stage_bias<128>(s_bias, P.bias + n0, lane < N / 4 ? lane : 0);
       mbar_wait_t(&tmem_full[buf], (t_it >> 1) & 1u, wF, timed);
       tc_fence_after();
       if (SPLIT > 1) {
@@ -649,6 +736,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
         const int w = tw * 16 + 8 * sx + xx;
         const bool inside = (h < P.H) && (w < P.W);
         __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
+        const PairStore ps = pair_store_setup(orow, inside, lane);
         const bool pool_writer = P.pool != nullptr && ((lane & 9) == 0) && (h >> 1) < (P.H >> 1) && (w >> 1) < (P.W >> 1);
         __half* prow = P.pool != nullptr ? P.pool + ((size_t)(h >> 1) * (P.W >> 1) + (w >> 1)) * P.Cout + n0 : nullptr;
 #pragma unroll 1
@@ -666,10 +754,10 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
             }
           }
           uint32_t pw[16];
-          const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);   // 32 consecutive biases, 16-byte loads
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);   // 32 consecutive biases, broadcast 16-byte loads
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float4 bq = __ldg(b4 + (j >> 1));
+            const float4 bq = b4[j >> 1];
             float a = __uint_as_float(v[2 * j]) + ((j & 1) ? bq.z : bq.x);
             float b = __uint_as_float(v[2 * j + 1]) + ((j & 1) ? bq.w : bq.y);
             if (P.relu) {
@@ -679,11 +767,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
             const __half2 hv = __floats2half2_rn(a, b);
             pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
           }
-          if (inside) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
-          }
+          pair_store(ps, c, pw, lane);
           if (P.pool != nullptr) {   // x neighbour = lane ^ 1, y neighbour = lane ^ 8
             pool_quad<8>(pw);
             if (pool_writer) {
@@ -778,6 +862,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
   uint64_t* tmem_full = emptyB + kPairSlots;
   uint64_t* tmem_empty = tmem_full + kBufs;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + kBufs);
+  float* s_bias_all = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -825,13 +910,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
     if (lane == 0) {
       // ---------------- TMA producer (both CTAs: own halo, own half of the weight rows) ----------------
       uint32_t a_it = 0, b_it = 0;
+      bool waited = false;
+      const bool timed = P.dbg != nullptr && blockIdx.x == 0;
+      long long wA = 0, wB = 0;
+      const long long tstart = clock64();
       for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs) {
         const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
         const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;     // tiles_w counts PAIRS of 16-pixel columns
         const int h0 = th * 16, w0 = (tw * 2 + (int)rank) * 16, n0 = nb * N + (int)rank * (N / 2);
         for (int c = 0; c < chunks; ++c) {
+          auto load_weights = [&](int tap_begin, int tap_end) {
+            for (int tap = tap_begin; tap < tap_end; ++tap) {
+              const int sb = b_it % kPairSlots;
+              mbar_wait_t(&emptyB[sb], ((b_it / kPairSlots) & 1u) ^ 1u, wB, timed);
+              if (leader) mbar_expect_tx(&fullB[sb], 2 * kPairBBytes);
+              tma_load_3d_pair(sB + sb * kPairBBytes, &tmW, &fullB[sb], c * kKChunk, n0, tap);
+              ++b_it;
+            }
+          };
+          int taps_done = 0;
+          if (!waited) {   // weights first, then the programmatic-dependent-launch wait, then activations
+            taps_done = kPairSlots < 9 ? kPairSlots : 9;
+            load_weights(0, taps_done);
+            ptk_pdl_wait();
+            ptk_pdl_trigger();
+            waited = true;
+          }
           const int sa = a_it & 1;
-          mbar_wait(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u);
+          mbar_wait_t(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u, wA, timed);
           if (leader) mbar_expect_tx(&fullA[sa], 2 * kHaloBytes);    // both CTAs' halos are credited here
           for (int r = 0; r < kHaloH; r += P.rows_per_op) {
             uint8_t* dst = sA + sa * kHaloBytes + r * (kHaloW * 128);
@@ -839,27 +945,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
             else tma_load_3d_pair(dst, &tmA1, &fullA[sa], (c - P.chunks0) * kKChunk, w0 - 1, h0 - 1 + r);
           }
           ++a_it;
-          for (int tap = 0; tap < 9; ++tap) {
-            const int sb = b_it % kPairSlots;
-            mbar_wait(&emptyB[sb], ((b_it / kPairSlots) & 1u) ^ 1u);
-            if (leader) mbar_expect_tx(&fullB[sb], 2 * kPairBBytes);
-            tma_load_3d_pair(sB + sb * kPairBBytes, &tmW, &fullB[sb], c * kKChunk, n0, tap);
-            ++b_it;
-          }
+          load_weights(taps_done, 9);
         }
+      }
+      if (!waited) {
+        ptk_pdl_wait();
+        ptk_pdl_trigger();
+      }
+      if (timed) {
+        P.dbg[0] = clock64() - tstart;
+        P.dbg[1] = wA;
+        P.dbg[2] = wB;
       }
     }
   } else if (warp == 1) {
     if (leader) {
       // ---------------- MMA issuer of the pair (warp-uniform loop, one elected lane issues) ----------------
       uint32_t a_it = 0, b_it = 0, t_it = 0;
+      const bool timed = P.dbg != nullptr && blockIdx.x == 0;
+      long long wT = 0, wA = 0, wB = 0;
+      const long long tstart = clock64();
       for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs, ++t_it) {
         const uint32_t buf = t_it % kBufs;
-        mbar_wait(&tmem_empty[buf], ((t_it / kBufs) & 1u) ^ 1u);
+        mbar_wait_t(&tmem_empty[buf], ((t_it / kBufs) & 1u) ^ 1u, wT, timed);
         tc_fence_after();
         for (int c = 0; c < chunks; ++c) {
           const int sa = a_it & 1;
-          mbar_wait(&fullA[sa], (a_it >> 1) & 1u);
+          mbar_wait_t(&fullA[sa], (a_it >> 1) & 1u, wA, timed);
           ++a_it;
           const uint32_t abase = smem_u32(sA + sa * kHaloBytes);
           const uint64_t adesc0 = (uint64_t)((abase & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) |
@@ -867,7 +979,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int sb = b_it % kPairSlots;
-            mbar_wait(&fullB[sb], (b_it / kPairSlots) & 1u);
+            mbar_wait_t(&fullB[sb], (b_it / kPairSlots) & 1u, wB, timed);
             ++b_it;
             tc_fence_after();
             const uint64_t bdesc = make_sw128_desc(smem_u32(sB + sb * kPairBBytes));
@@ -891,6 +1003,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
         if (elect_one()) tc_commit_pair(&tmem_full[buf]);
         __syncwarp();
       }
+      if (timed && lane == 0) {
+        P.dbg[3] = clock64() - tstart;
+        P.dbg[4] = wT;
+        P.dbg[5] = wA;
+        P.dbg[6] = wB;
+        P.dbg[7] = t_it;
+      }
     }
   } else {
     // ---------------- epilogue (both CTAs, own TMEM lanes) ----------------
@@ -898,29 +1017,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
     const int m = q * 32 + lane;
     const int y = m >> 3, xx = m & 7;
     uint32_t t_it = 0;
+    const bool timed = P.dbg != nullptr && blockIdx.x == 0 && warp == 2;
+    long long wF = 0, t_ld = 0, t_st = 0;
+    const long long tstart = clock64();
     for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs, ++t_it) {
       const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
       const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
       const int h = th * 16 + y, n0 = nb * N;
       const uint32_t buf = t_it % kBufs;
-      mbar_wait(&tmem_full[buf], (t_it / kBufs) & 1u);
+      float* s_bias = s_bias_all + (warp - 2) * N;
+      if (N >= 128) stage_bias<N>(s_bias, P.bias + n0, lane);
+      else stage_bias<128>(s_bias, P.bias + n0, lane < N / 4 ? lane : 0);
+      mbar_wait_t(&tmem_full[buf], (t_it / kBufs) & 1u, wF, timed);
       tc_fence_after();
 #pragma unroll 1
       for (int sx = 0; sx < 2; ++sx) {
         const int w = (tw * 2 + (int)rank) * 16 + 8 * sx + xx;
         const bool inside = (h < P.H) && (w < P.W);
         __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
+        const PairStore ps = pair_store_setup(orow, inside, lane);
         const bool pool_writer = P.pool != nullptr && ((lane & 9) == 0) && (h >> 1) < (P.H >> 1) && (w >> 1) < (P.W >> 1);
         __half* prow = P.pool != nullptr ? P.pool + ((size_t)(h >> 1) * (P.W >> 1) + (w >> 1)) * P.Cout + n0 : nullptr;
 #pragma unroll 1
         for (int c = 0; c < N; c += 32) {
           uint32_t v[32];
+          const long long tl0 = timed ? clock64() : 0;
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2u + (uint32_t)sx) * (uint32_t)N + (uint32_t)c, v);
+          if (timed) t_ld += clock64() - tl0;
           uint32_t pw[16];
-          const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0 + c);
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float4 bq = __ldg(b4 + (j >> 1));
+            const float4 bq = b4[j >> 1];
             float a = __uint_as_float(v[2 * j]) + ((j & 1) ? bq.z : bq.x);
             float b = __uint_as_float(v[2 * j + 1]) + ((j & 1) ? bq.w : bq.y);
             if (P.relu) {
@@ -930,11 +1058,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
             const __half2 hv = __floats2half2_rn(a, b);
             pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
           }
-          if (inside) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
-          }
+          const long long ts0 = timed ? clock64() : 0;
+          pair_store(ps, c, pw, lane);
+          if (timed) t_st += clock64() - ts0;
           if (P.pool != nullptr) {
             pool_quad<8>(pw);
             if (pool_writer) {
@@ -949,9 +1075,293 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
     }
+    if (timed && lane == 0) {
+      P.dbg[8] = clock64() - tstart;
+      P.dbg[9] = wF;
+      P.dbg[10] = t_ld;
+      P.dbg[11] = t_st;
+    }
   }
 
   tc_fence_before();
+  cluster_sync_all();                // the peer may still read this CTA's shared memory / TMEM until here
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_row2_kernel: CTA pairs on ROW tiles, for the 1/8-scale maps (72 x 128, 94 x 126) with 512 channels.
+//
+// 16 x 16 tiles quantise badly on a 72-row map (80 pair tiles on 74 SM pairs) and the per-tap kernel that served these
+// layers re-reads every activation nine times (663 MB of L2 -> shared traffic per layer: it ran at 1 040 TF/s).  Here an
+// MMA's 128 rows are 128 CONSECUTIVE PIXELS OF ONE IMAGE ROW (core matrices 1 024 B apart in a densely staged row), a
+// CTA owns R rows x 128 columns and stages their (R + 2) x 130-pixel halo once per 64-channel chunk, and a pair
+// (rank r: rows [2R th + R r, + R)) issues M = 256 x N = 128 MMAs with each CTA staging half of every weight tile:
+// 72 x 128 with R = 2 is 72 pair tiles = ONE wave on 74 SM pairs, 94 x 126 with R = 3 is 64; staged bytes per layer
+// drop 4x (159 MB).  The halo rows are denser in bytes than the 16 x 16 form (2.0x the tile at R = 2 against 1.27x), which
+// is why the larger maps stay on conv_halo2_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRowW = 130;                           // staged pixels per halo row: 128 + 2
+
+template <int R>
+struct RowGeom {
+  static constexpr int kN = 128;
+  static constexpr int kHaloRows = R + 2;
+  static constexpr int kHaloBytesExact = kHaloRows * kRowW * 128;
+  static constexpr int kStageA = (kHaloBytesExact + 1023) / 1024 * 1024;
+  static constexpr int kBBytes = (kN / 2) * 128;                       // this CTA's half of a weight tile: 8 KB
+  static constexpr int kSlots = (232448 - 1024 - 2 * kStageA - 512 - 4 * kN * 4) / kBBytes;
+  static constexpr int kBufs = (2 * R * kN <= 512) ? 2 : 1;            // accumulator sets in TMEM
+  static constexpr int kSmem = 2 * kStageA + kSlots * kBBytes + (4 + 2 * kSlots + 2 * kBufs) * 8 + 16 + 4 * kN * 4 + 1024;
+  static_assert(R * kN <= 512, "accumulators of one tile must fit TMEM");
+  static_assert(kSlots >= 6, "weight ring too short");
+  static_assert(kSmem <= 232448, "shared memory budget");
+};
+
+template <int R>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+    conv_row2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                     const __grid_constant__ CUtensorMap tmW, const HaloParams P) {
+  using G = RowGeom<R>;
+  constexpr int N = G::kN;
+  constexpr int kSlots = G::kSlots;
+  constexpr int kBufs = G::kBufs;
+  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2 * G::kStageA;
+  uint64_t* fullA = (uint64_t*)(sB + kSlots * G::kBBytes);
+  uint64_t* emptyA = fullA + 2;
+  uint64_t* fullB = emptyA + 2;
+  uint64_t* emptyB = fullB + kSlots;
+  uint64_t* tmem_full = emptyB + kSlots;
+  uint64_t* tmem_empty = tmem_full + kBufs;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + kBufs);
+  float* s_bias_all = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][N]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int chunks = P.chunks0 + P.chunks1;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    if (P.chunks1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&emptyA[s], 1);
+    }
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&fullB[s], 1);
+      mbar_init(&emptyB[s], 1);
+    }
+    for (int s = 0; s < kBufs; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps of each CTA arrive on the leader's copy
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  cluster_sync_all();                // the peer is running before the pair allocation touches its shared memory (see conv_halo2_kernel)
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs: own halo, own half of the weight rows) ----------------
+      uint32_t a_it = 0, b_it = 0;
+      bool waited = false;
+      const bool timed = P.dbg != nullptr && blockIdx.x == 0;
+      long long wA = 0, wB = 0;
+      const long long tstart = clock64();
+      for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs) {
+        const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
+        const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
+        const int h0 = (th * 2 + (int)rank) * R, w0 = tw * 128, n0 = nb * N + (int)rank * (N / 2);
+        for (int c = 0; c < chunks; ++c) {
+          auto load_weights = [&](int tap_begin, int tap_end) {
+            for (int tap = tap_begin; tap < tap_end; ++tap) {
+              const int sb = b_it % kSlots;
+              mbar_wait_t(&emptyB[sb], ((b_it / kSlots) & 1u) ^ 1u, wB, timed);
+              if (leader) mbar_expect_tx(&fullB[sb], 2 * G::kBBytes);
+              tma_load_3d_pair(sB + sb * G::kBBytes, &tmW, &fullB[sb], c * kKChunk, n0, tap);
+              ++b_it;
+            }
+          };
+          int taps_done = 0;
+          if (!waited) {   // weights first, then the programmatic-dependent-launch wait, then activations
+            taps_done = kSlots < 9 ? kSlots : 9;
+            load_weights(0, taps_done);
+            ptk_pdl_wait();
+            ptk_pdl_trigger();
+            waited = true;
+          }
+          const int sa = a_it & 1;
+          mbar_wait_t(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u, wA, timed);
+          if (leader) mbar_expect_tx(&fullA[sa], 2 * G::kHaloBytesExact);    // both CTAs' halos are credited here
+          uint8_t* dst = sA + sa * G::kStageA;
+          if (c < P.chunks0) tma_load_3d_pair(dst, &tmA0, &fullA[sa], c * kKChunk, w0 - 1, h0 - 1);
+          else tma_load_3d_pair(dst, &tmA1, &fullA[sa], (c - P.chunks0) * kKChunk, w0 - 1, h0 - 1);
+          ++a_it;
+          load_weights(taps_done, 9);
+        }
+      }
+      if (!waited) {
+        ptk_pdl_wait();
+        ptk_pdl_trigger();
+      }
+      if (timed) {
+        P.dbg[0] = clock64() - tstart;
+        P.dbg[1] = wA;
+        P.dbg[2] = wB;
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---------------- MMA issuer of the pair (warp-uniform loop, one elected lane issues) ----------------
+      uint32_t a_it = 0, b_it = 0, t_it = 0;
+      const bool timed = P.dbg != nullptr && blockIdx.x == 0;
+      long long wT = 0, wA = 0, wB = 0;
+      const long long tstart = clock64();
+      for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs, ++t_it) {
+        const uint32_t buf = t_it % kBufs;
+        mbar_wait_t(&tmem_empty[buf], ((t_it / kBufs) & 1u) ^ 1u, wT, timed);
+        tc_fence_after();
+        for (int c = 0; c < chunks; ++c) {
+          const int sa = a_it & 1;
+          mbar_wait_t(&fullA[sa], (a_it >> 1) & 1u, wA, timed);
+          ++a_it;
+          // 128 consecutive pixels of a staged row: core matrices (8 pixels x 128 B) 1 024 B apart
+          const uint64_t adesc0 = make_sw128_desc(smem_u32(sA + sa * G::kStageA));
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int sb = b_it % kSlots;
+            mbar_wait_t(&fullB[sb], (b_it / kSlots) & 1u, wB, timed);
+            ++b_it;
+            tc_fence_after();
+            const uint64_t bdesc = make_sw128_desc(smem_u32(sB + sb * G::kBBytes));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < kKChunk / 16; ++k) {
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {       // consecutive MMAs write different accumulators
+                  const int px0 = (rr + tap / 3) * kRowW + (tap % 3);
+                  const uint64_t adesc = adesc0 + (uint64_t)(px0 * 8);
+                  const uint32_t d = tmem_base + (buf * (uint32_t)R + (uint32_t)rr) * (uint32_t)N;
+                  tc_mma_f16_pair(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (c | tap | k) != 0 ? 1u : 0u);
+                }
+              }
+              tc_commit_pair(&emptyB[sb]);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) tc_commit_pair(&emptyA[sa]);
+          __syncwarp();
+        }
+        if (elect_one()) tc_commit_pair(&tmem_full[buf]);
+        __syncwarp();
+      }
+      if (timed && lane == 0) {
+        P.dbg[3] = clock64() - tstart;
+        P.dbg[4] = wT;
+        P.dbg[5] = wA;
+        P.dbg[6] = wB;
+        P.dbg[7] = t_it;
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs, own TMEM lanes): lane m of an accumulator = column w0 + m of one row -------
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    uint32_t t_it = 0;
+    const bool timed = P.dbg != nullptr && blockIdx.x == 0 && warp == 2;
+    long long wF = 0;
+    const long long tstart = clock64();
+    for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs, ++t_it) {
+      const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
+      const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
+      const int h0 = (th * 2 + (int)rank) * R, w = tw * 128 + m, n0 = nb * N;
+      const uint32_t buf = t_it % kBufs;
+      float* s_bias = s_bias_all + (warp - 2) * N;
+      stage_bias<N>(s_bias, P.bias + n0, lane);
+      mbar_wait_t(&tmem_full[buf], (t_it / kBufs) & 1u, wF, timed);
+      tc_fence_after();
+      PairStore ps[R];
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr)
+        ps[rr] = pair_store_setup(P.out + ((size_t)(h0 + rr) * P.W + w) * P.Cout + n0, (h0 + rr) < P.H && w < P.W, lane);
+#pragma unroll 1
+      for (int c = 0; c < N; c += 32) {
+        uint32_t pooled[16];
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+          const int h = h0 + rr;
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * (uint32_t)R + (uint32_t)rr) * (uint32_t)N + (uint32_t)c, v);
+          uint32_t pw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 bq = b4[j >> 1];
+            float a = __uint_as_float(v[2 * j]) + ((j & 1) ? bq.z : bq.x);
+            float b = __uint_as_float(v[2 * j + 1]) + ((j & 1) ? bq.w : bq.y);
+            if (P.relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            const __half2 hv = __floats2half2_rn(a, b);
+            pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+          }
+          pair_store(ps[rr], c, pw, lane);
+          if ((R & 1) == 0 && P.pool != nullptr) {      // rows pair up inside a CTA only for even R (the host checks)
+            if ((rr & 1) == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pooled[j] = pw[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __half2 x = __hmax2(*reinterpret_cast<__half2*>(&pooled[j]), *reinterpret_cast<__half2*>(&pw[j]));
+                uint32_t cur = *reinterpret_cast<uint32_t*>(&x);
+                const uint32_t o = __shfl_xor_sync(0xffffffffu, cur, 1);
+                x = __hmax2(x, *reinterpret_cast<const __half2*>(&o));
+                pooled[j] = *reinterpret_cast<uint32_t*>(&x);
+              }
+              if ((lane & 1) == 0 && (h >> 1) < (P.H >> 1) && (w >> 1) < (P.W >> 1)) {
+                uint4* dst = reinterpret_cast<uint4*>(P.pool + ((size_t)(h >> 1) * (P.W >> 1) + (w >> 1)) * P.Cout + n0 + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  dst[j] = make_uint4(pooled[4 * j], pooled[4 * j + 1], pooled[4 * j + 2], pooled[4 * j + 3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
+    }
+    if (timed && lane == 0) {
+      P.dbg[8] = clock64() - tstart;
+      P.dbg[9] = wF;
+    }
+  }
+
+  tc_fence_before();
+  __syncwarp();
   cluster_sync_all();                // the peer may still read this CTA's shared memory / TMEM until here
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -1004,7 +1414,7 @@ template <int BLOCK_N, int STAGES, int SPLIT = 1>
 int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& P,
                 cudaStream_t stream) {
   // stage ring | barriers + TMEM slot (256 B) | SPLIT: fp32 exchange buffer | alignment slack
-  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + 256 + (SPLIT > 1 ? BLOCK_N * 128 * 4 : 0) + 1024;
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + 256 + (SPLIT > 1 ? BLOCK_N * 128 * 4 : 0) + BLOCK_N * 4 + 1024;
   static_assert(smem <= 232448, "shared memory budget");
   static_assert(2 * STAGES + 2 <= 31, "barriers + TMEM slot must fit the 256-byte block");
   static bool configured = false;
@@ -1016,22 +1426,9 @@ int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   const int tiles_h = (P.H + tile_h - 1) / tile_h;
   dim3 grid(P.tiles_w * tiles_h, P.Cout / BLOCK_N, SPLIT);
   if (SPLIT == 1) {
-    conv_tc_kernel<BLOCK_N, STAGES, SPLIT><<<grid, kConvThreads, smem, stream>>>(a0, a1, w, P);
-    PTK_CUDA_CHECK(cudaGetLastError());
+    PTK_CUDA_CHECK(ptk_launch_pdl(conv_tc_kernel<BLOCK_N, STAGES, SPLIT>, grid, dim3(kConvThreads), smem, stream, dim3(1, 1, 1), a0, a1, w, P));
   } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = SPLIT;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PTK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, STAGES, SPLIT>, a0, a1, w, P));
+    PTK_CUDA_CHECK(ptk_launch_pdl(conv_tc_kernel<BLOCK_N, STAGES, SPLIT>, grid, dim3(kConvThreads), smem, stream, dim3(1, 1, SPLIT), a0, a1, w, P));
   }
   return PTK_OK;
 }
@@ -1041,28 +1438,18 @@ template <int N, int SPLIT = 1>
 int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int grid,
                 cudaStream_t stream) {
   constexpr int kSlots = kBBudget / (N * 128);
-  constexpr int smem = 2 * kHaloBytes + kSlots * N * 128 + (4 + 2 * kSlots + 6) * 8 + 16 + 1024;
+  constexpr int smem = 2 * kHaloBytes + kSlots * N * 128 + (4 + 2 * kSlots + 6) * 8 + 16 + 8 * N * 4 + 1024;
+  static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   if (SPLIT == 1) {
-    conv_halo_kernel<N, SPLIT><<<grid, kHalo1Threads, smem, stream>>>(a0, a1, w, P);
+    PTK_CUDA_CHECK(ptk_launch_pdl(conv_halo_kernel<N, SPLIT>, dim3(grid), dim3(kHalo1Threads), smem, stream, dim3(1, 1, 1), a0, a1, w, P));
   } else {   // one cluster of SPLIT CTAs per tile
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(SPLIT * P.total_tiles);
-    cfg.blockDim = dim3(kHalo1Threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = SPLIT;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PTK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<N, SPLIT>, a0, a1, w, P));
+    PTK_CUDA_CHECK(ptk_launch_pdl(conv_halo_kernel<N, SPLIT>, dim3(SPLIT * P.total_tiles), dim3(kHalo1Threads), smem, stream,
+                                  dim3(SPLIT, 1, 1), a0, a1, w, P));
   }
   PTK_CUDA_CHECK(cudaGetLastError());
   return PTK_OK;
@@ -1072,14 +1459,28 @@ template <int N>
 int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int n_pairs,
                  cudaStream_t stream) {
   constexpr int kSlots = kPairBudget / ((N / 2) * 128);
-  constexpr int smem = 2 * kHaloBytes + kPairBudget + (4 + 2 * kSlots + 4) * 8 + 16 + 1024;
+  constexpr int smem = 2 * kHaloBytes + kPairBudget + (4 + 2 * kSlots + 4) * 8 + 16 + 4 * N * 4 + 1024;
+  static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo2_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  conv_halo2_kernel<N><<<2 * n_pairs, kHaloThreads, smem, stream>>>(a0, a1, w, P);   // __cluster_dims__(2, 1, 1)
-  PTK_CUDA_CHECK(cudaGetLastError());
+  // the cluster shape is the kernel's compile-time __cluster_dims__(2, 1, 1)
+  PTK_CUDA_CHECK(ptk_launch_pdl(conv_halo2_kernel<N>, dim3(2 * n_pairs), dim3(kHaloThreads), smem, stream, dim3(1, 1, 1), a0, a1, w, P));
+  return PTK_OK;
+}
+
+template <int R>
+int launch_row2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int n_pairs,
+                cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_row2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, RowGeom<R>::kSmem));
+    configured = true;
+  }
+  // the cluster shape is the kernel's compile-time __cluster_dims__(2, 1, 1)
+  PTK_CUDA_CHECK(ptk_launch_pdl(conv_row2_kernel<R>, dim3(2 * n_pairs), dim3(kHaloThreads), RowGeom<R>::kSmem, stream, dim3(1, 1, 1), a0, a1, w, P));
   return PTK_OK;
 }
 
@@ -1169,8 +1570,84 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
         Q.out = (__half*)out;
         Q.pool = (__half*)pool_out;
         const int n_launch = total_pairs < pair_slots ? total_pairs : pair_slots;
+        static int pair_dbg = -1;
+        if (pair_dbg < 0) pair_dbg = getenv("PTK_CONV_DBG") ? atoi(getenv("PTK_CONV_DBG")) : 0;
+        if (pair_dbg) {   // stall attribution (debug only: synchronises and prints)
+          static long long* dbuf = nullptr;
+          if (!dbuf) cudaMalloc(&dbuf, 16 * sizeof(long long));
+          cudaMemsetAsync(dbuf, 0, 16 * sizeof(long long), s);
+          Q.dbg = dbuf;
+          const int lrc = pair_n == 64 ? launch_halo2<64>(a0, a1, wm, Q, n_launch, s)
+                                       : (pair_n == 256 ? launch_halo2<256>(a0, a1, wm, Q, n_launch, s) : launch_halo2<128>(a0, a1, wm, Q, n_launch, s));
+          long long h[16];
+          cudaMemcpy(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost);
+          fprintf(stderr, "[halo2 N=%d %dx%d cin=%d cout=%d tiles/pair=%lld] producer: total %lld waitEmptyA %lld waitEmptyB %lld | "
+                  "mma: total %lld waitTmemEmpty %lld waitFullA %lld waitFullB %lld | epilogue: total %lld waitTmemFull %lld tmemLoad %lld store %lld\n",
+                  pair_n, H, W, cin0 + cin1, Cout, h[7], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[8], h[9], h[10], h[11]);
+          return lrc;
+        }
         if (pair_n == 64) return launch_halo2<64>(a0, a1, wm, Q, n_launch, s);
         return pair_n == 256 ? launch_halo2<256>(a0, a1, wm, Q, n_launch, s) : launch_halo2<128>(a0, a1, wm, Q, n_launch, s);
+      }
+      // Row tiles on CTA pairs (conv_row2_kernel): maps about 128 pixels wide with a long K, where 16x16 tiles quantise badly
+      // and the per-tap kernel is bound by its L2 -> shared traffic.  PTK_CONV_ROW: 0 = never, 1 = when one of R = 2 / 3
+      // fills >= 60 % of its waves of SM pairs (default; the pooled 94 x 126 layer needs R = 2 = 96 tiles on 74 pairs and
+      // still beats the per-tap kernel, 61 us), 2 = whenever legal.
+      static int row_mode = -1;
+      if (row_mode < 0) row_mode = getenv("PTK_CONV_ROW") ? atoi(getenv("PTK_CONV_ROW")) : 1;
+      if (row_mode != 0 && mode != 0 && taps == 9 && Cout % 128 == 0 && ctot >= 256) {
+        const int col_tiles = (W + 127) / 128;
+        int best_r = 0;
+        double best_eff = 0.0;
+        for (int r = 2; r <= 3; ++r) {
+          if (pool_out != nullptr && (r & 1)) continue;       // pooled rows must pair up inside one CTA
+          const long tiles = (long)col_tiles * ((H + 2 * r - 1) / (2 * r)) * (Cout / 128);
+          const long wv = (tiles + pair_slots - 1) / pair_slots;
+          const double eff = (double)H * W * (Cout / 128) / ((double)wv * pair_slots * 2 * r * 128);
+          if (eff > best_eff) {
+            best_eff = eff;
+            best_r = r;
+          }
+        }
+        if (best_r != 0 && (row_mode == 2 || best_eff >= 0.6)) {
+          rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kRowW, best_r + 2);
+          if (rc != PTK_OK) return rc;
+          if (cin1 > 0) {
+            rc = make_map_3d(&a1, in1, cin1, W, H, cin1, (uint64_t)in1_W * cin1, kKChunk, kRowW, best_r + 2);
+            if (rc != PTK_OK) return rc;
+          } else {
+            a1 = a0;
+          }
+          rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, 64, 1);
+          if (rc != PTK_OK) return rc;
+          HaloParams Q;
+          Q.H = H; Q.W = W; Q.Cout = Cout; Q.chunks0 = cin0 / kKChunk; Q.chunks1 = cin1 / kKChunk; Q.relu = relu;
+          Q.tiles_w = col_tiles; Q.tiles_hw = col_tiles * ((H + 2 * best_r - 1) / (2 * best_r));
+          Q.total_tiles = Q.tiles_hw * (Cout / 128);
+          Q.resident = 0;
+          Q.dbg = nullptr;
+          Q.rows_per_op = best_r + 2;
+          Q.bias = bias;
+          Q.out = (__half*)out;
+          Q.pool = (__half*)pool_out;
+          const int n_launch = Q.total_tiles < pair_slots ? Q.total_tiles : pair_slots;
+          static int row_dbg = -1;
+          if (row_dbg < 0) row_dbg = getenv("PTK_CONV_DBG") ? atoi(getenv("PTK_CONV_DBG")) : 0;
+          if (row_dbg) {   // stall attribution (debug only: synchronises and prints)
+            static long long* dbuf = nullptr;
+            if (!dbuf) cudaMalloc(&dbuf, 16 * sizeof(long long));
+            cudaMemsetAsync(dbuf, 0, 16 * sizeof(long long), s);
+            Q.dbg = dbuf;
+            const int lrc = best_r == 2 ? launch_row2<2>(a0, a1, wm, Q, n_launch, s) : launch_row2<3>(a0, a1, wm, Q, n_launch, s);
+            long long h[16];
+            cudaMemcpy(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[row2 R=%d %dx%d cin=%d cout=%d tiles/pair=%lld] producer: total %lld waitEmptyA %lld waitEmptyB %lld | "
+                    "mma: total %lld waitTmemEmpty %lld waitFullA %lld waitFullB %lld | epilogue: total %lld waitTmemFull %lld\n",
+                    best_r, H, W, cin0 + cin1, Cout, h[7], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[8], h[9]);
+            return lrc;
+          }
+          return best_r == 2 ? launch_row2<2>(a0, a1, wm, Q, n_launch, s) : launch_row2<3>(a0, a1, wm, Q, n_launch, s);
+        }
       }
     }
     const bool legal = taps == 9 && (Cout == 32 || Cout == 64 || Cout % 128 == 0);

@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict_
     const int n = i >> 5, k = i & 31;
     sw[n * 40 + k] = __float2half_rn(k < 27 ? w[n * 28 + k] : 0.f);
   }
+  ptk_pdl_wait();                          // the weights are constants; the image comes from the previous kernel
+  ptk_pdl_trigger();
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, q2 = (lane & 3) * 2;
@@ -193,6 +195,8 @@ __global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict_
 // 2x2 output block of input pixel (y, x) for 8 channels from the 3x3 input neighbourhood (9 loads for 4 outputs,
 // separable blend) instead of 4 loads and a general bilinear evaluation per output.
 __global__ void upsample2_kernel(const __half* __restrict__ in, int H, int W, int C, __half* __restrict__ out) {
+  ptk_pdl_wait();
+  ptk_pdl_trigger();
   const int C8 = C >> 3;                           // power of two (C = 64 .. 512)
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (unsigned)(H * W * C8)) return;
@@ -275,6 +279,8 @@ __global__ void __launch_bounds__(256) head_mma_kernel(const __half* __restrict_
     cp_async16(sw + n * ws + q * 8, reinterpret_cast<const uint4*>(w + (size_t)(n < nout ? n : 0) * Cin) + q, n < nout);
   }
   cp_async_commit();
+  ptk_pdl_wait();                                 // the weights above are constants; the activations come from the previous kernel
+  ptk_pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, q2 = (lane & 3) * 2;
   const int groups = (npix + 31) / 32;
@@ -383,7 +389,8 @@ int launch_head(const PtkContext* ctx, const __half* x, long long npix, int Cin,
   long long blocks = (groups + wpb - 1) / wpb;
   const long long cap = 2LL * ctx->num_sms;
   if (blocks > cap) blocks = cap;
-  head_mma_kernel<NT><<<(unsigned)blocks, 256, smem, s>>>(x, (int)npix, Cin, Cout, w, b, feat, conf, normalize, (int)wpb);
+  PTK_CUDA_CHECK(ptk_launch_pdl(head_mma_kernel<NT>, dim3((unsigned)blocks), dim3(256), (size_t)smem, s, dim3(1, 1, 1), x, (int)npix, Cin, Cout,
+                                w, b, feat, conf, normalize, (int)wpb));
   return PTK_OK;
 }
 
@@ -532,8 +539,8 @@ static int run_plan(PtkExtractor* e, const void* image, int32_t img_dtype, int32
   {
     const int tiles_x = (W + 15) / 16, tiles = tiles_x * ((H + 15) / 16);
     const int grid = tiles < 4 * e->ctx->num_sms ? tiles : 4 * e->ctx->num_sms;
-    conv1_mma_kernel<<<grid, 256, 0, s>>>(e->img, H, W, (const float*)e->wts.conv_w[0], e->wts.conv_b[0], e->enc[0][0],
-                                          tiles_x, tiles);
+    PTK_CUDA_CHECK(ptk_launch_pdl(conv1_mma_kernel, dim3(grid), dim3(256), 0, s, dim3(1, 1, 1), (const float*)e->img, H, W,
+                                  (const float*)e->wts.conv_w[0], (const float*)e->wts.conv_b[0], e->enc[0][0], tiles_x, tiles));
   }
   PTK_CUDA_CHECK(cudaGetLastError());
   mark();
@@ -588,7 +595,8 @@ static int run_plan(PtkExtractor* e, const void* image, int32_t img_dtype, int32
     const int sb = 3 - i;   // skip feature comes from encoder block 3, 2, 1, 0
     const int cskip = kEncBlocks[sb][kEncCount[sb] - 1];
     const long long n = (long long)ph * pw * (cprev / 8);      // one thread per input pixel and 8 channels
-    upsample2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(prev, ph, pw, cprev, e->up[i]);
+    PTK_CUDA_CHECK(ptk_launch_pdl(upsample2_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, dim3(1, 1, 1), prev, ph, pw, cprev,
+                                  e->up[i]));
     mark();
     const int rc = ptk_conv_f16(e->ctx, e->up[i], cprev, e->enc[sb][kEncCount[sb] - 1], cskip, e->dh[i], e->dw[i],
                                 e->dh[i], e->dw[i], e->eh[sb], e->ew[sb], e->wts.conv_w[li], e->wts.conv_b[li], kDec[i], 9,

@@ -13,7 +13,12 @@ from pixtrack_b200.extractor import conv_f16, pack_conv3x3  # noqa: E402
 D = 'cuda:0'
 LAYERS = [('enc0.1', 64, 0, 64, 576, 1024, True), ('enc1.0', 64, 0, 128, 288, 512, False), ('enc1.1', 128, 0, 128, 288, 512, True),
           ('enc2.0', 128, 0, 256, 144, 256, False), ('enc2.1', 256, 0, 256, 144, 256, False), ('dec1', 64, 256, 64, 144, 256, False),
-          ('dec2', 64, 128, 64, 288, 512, False), ('dec3', 64, 64, 32, 576, 1024, False)]
+          ('dec2', 64, 128, 64, 288, 512, False), ('dec3', 64, 64, 32, 576, 1024, False),
+          # the 1/8-scale block on conv_row2_kernel (row tiles, CTA pairs)
+          ('enc3.0', 256, 0, 512, 72, 128, False), ('enc3.1', 512, 0, 512, 72, 128, False), ('enc3.3', 512, 0, 512, 72, 128, True),
+          ('enc3.1r', 512, 0, 512, 94, 126, False)]
+if len(sys.argv) > 1:
+    LAYERS = [l for l in LAYERS if l[0] in sys.argv[1:]]
 for name, c0, c1, cout, h, w, pool in LAYERS:
     g = torch.Generator().manual_seed(1)
     x = torch.randn(h, w, c0, generator=g).half().to(D)

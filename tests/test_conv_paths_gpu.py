@@ -120,6 +120,58 @@ def test_cta_pair_kernel_default_dispatch(cin0, cin1, cout, H, W, pool):
     assert torch.equal(again, y)
 
 
+def _row_pair_checks(shapes):
+    from pixtrack_b200.extractor import conv_f16, pack_conv3x3
+    for cin0, cin1, cout, H, W, pool in shapes:
+        x, x1, w, b = _case(cin0, cout, H, W, seed=cin0 + cin1 + cout + H + W, cin1=cin1)
+        for relu in (True, False):
+            out = conv_f16(x, pack_conv3x3(w), b, relu=relu, x1=x1, out_hw=(H, W), pool=pool)
+            torch.cuda.synchronize()
+            y = out[0] if pool else out
+            _check(y, _ref(x, w, b, relu, x1=x1, hw=(H, W)), (cin0, cin1, cout, H, W, relu))
+            if pool:
+                want = tF.max_pool2d(y.float().permute(2, 0, 1)[None], 2, 2)[0].permute(1, 2, 0)
+                assert tuple(out[1].shape) == (H // 2, W // 2, cout)
+                assert torch.equal(out[1].float(), want)
+        again = conv_f16(x, pack_conv3x3(w), b, relu=False, x1=x1, out_hw=(H, W))
+        torch.cuda.synchronize()
+        assert torch.equal(again, y)
+    print('row pair ok')
+
+
+ROW_DEFAULT_SHAPES = [
+    (256, 0, 512, 72, 128, False),      # 1/8-scale block of the 1024x576 plan: conv_row2_kernel<2>, 72 pair tiles = one wave
+    (512, 0, 512, 72, 128, True),       # its last layer, fused pool (rows pair up inside a CTA)
+    (512, 0, 512, 94, 126, False),      # the 1008x756 plan: conv_row2_kernel<3>, 64 pair tiles, ragged right and bottom edges
+    (256, 256, 512, 94, 126, False),    # two inputs
+]
+ROW_FORCED_SHAPES = [
+    (256, 0, 128, 37, 200, True),       # two column tiles (the second 72 pixels wide), odd height, pooled
+    (256, 0, 128, 300, 256, False),     # 150 pair tiles on 74 SM pairs: the persistent loop and both accumulator sets
+    (192, 64, 256, 41, 130, False),     # a 2-pixel-wide second column tile, two inputs, two C_out groups
+]
+
+
+def test_row_tile_pair_kernel_default_dispatch():
+    """Long-K layers on maps about 128 pixels wide (the 512-channel 1/8-scale block) run on conv_row2_kernel<R>: an MMA's
+    128 rows are 128 consecutive pixels of an image row, a CTA pair owns 2R rows, tcgen05 cta_group::2."""
+    _row_pair_checks(ROW_DEFAULT_SHAPES)
+
+
+def test_row_tile_pair_kernel_forced_shapes():
+    """The same kernel on shapes it is not chosen for by default (PTK_CONV_ROW=2: whenever legal): several column tiles,
+    more tiles than SM pairs, ragged edges."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PTK_CONV_ROW='2', PTK_CONV_PAIR='0')
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, '-c', 'import sys; sys.path[:0] = [%r, %r]; import test_conv_paths_gpu as t; '
+                        't._row_pair_checks(t.ROW_FORCED_SHAPES)' % (here, os.path.dirname(here))], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'row pair ok' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 SPLIT_SHAPES = [
     (512, 0, 512, 36, 64, False),       # 1/16-scale block of the 1024x576 plan: halo<128, SPLIT 2>, 48 tiles x 2 CTAs
     (512, 0, 512, 47, 63, False),       # ... of the 1008x756 plan (odd sizes, ragged tiles)
