@@ -80,15 +80,51 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int kC1Stride = 18 * 3 + 2;   // halfs per tile row (56: keeps rows 4-byte aligned)
 
-__global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict__ img, int H, int W,
+// ---------------------------------------------------------------------------------------------
+// Quad transpose of mma.sync accumulator fragments.  In an m16n8 C fragment lane (r, q) holds columns n*8 + 2q, 2q+1
+// of n-tile n: written as they are, a pixel's channels go out as 4- or 8-byte pieces from 4 lanes per n-tile, i.e. many
+// small store requests (the store path, not DRAM, bounded conv1 and the level-0 head).  Two xor-shuffle rounds inside
+// the quad regroup four n-tile items v[h][m] (n = 2h + m, P registers each) so that lane q ends up with the item of
+// n-tile q from all four lanes: o[q'] = what lane q' held for n-tile q -- 32 contiguous bytes per lane, a full line per quad.
+// ---------------------------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ void quad_transpose(const uint32_t (&v)[2][2][P], int q, uint32_t (&o)[4][P]) {
+  const bool b0 = (q & 1) != 0, b1 = (q & 2) != 0;
+  uint32_t x0[2][P], x1[2][P];            // items with m == b0: own / from lane q ^ 1
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      x0[h][p] = b0 ? v[h][1][p] : v[h][0][p];
+      x1[h][p] = __shfl_xor_sync(0xffffffffu, b0 ? v[h][0][p] : v[h][1][p], 1);
+    }
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const uint32_t k0 = b1 ? x0[1][p] : x0[0][p], k1 = b1 ? x1[1][p] : x1[0][p];                    // h == b1: from q, q ^ 1
+    const uint32_t y0 = __shfl_xor_sync(0xffffffffu, b1 ? x0[0][p] : x0[1][p], 2);                // from q ^ 2
+    const uint32_t y1 = __shfl_xor_sync(0xffffffffu, b1 ? x1[0][p] : x1[1][p], 2);                // from q ^ 3
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) o[sl][p] = sl == q ? k0 : (sl == (q ^ 1) ? k1 : (sl == (q ^ 2) ? y0 : y1));
+  }
+}
+__device__ __forceinline__ void st_global_256(void* dst, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                              uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) conv1_mma_kernel(const float* __restrict__ img, int H, int W,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         __half* __restrict__ out, int tiles_x, int tiles) {
   __shared__ __half tile[18 * kC1Stride];
   __shared__ __half sw[64 * 40];           // [n][k] fp16, k padded 27 -> 32 (+8 to spread the banks)
+  __shared__ float sbias[64];
   for (int i = threadIdx.x; i < 64 * 32; i += 256) {
     const int n = i >> 5, k = i & 31;
     sw[n * 40 + k] = __float2half_rn(k < 27 ? w[n * 28 + k] : 0.f);
   }
+  if (threadIdx.x < 64) sbias[threadIdx.x] = bias[threadIdx.x];
   ptk_pdl_wait();                          // the weights are constants; the image comes from the previous kernel
   ptk_pdl_trigger();
   __syncthreads();
@@ -96,7 +132,6 @@ __global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict_
   const int r = lane >> 2, q2 = (lane & 3) * 2;
   // B fragments of the whole weight matrix: 8 n-tiles x 2 k-steps
   uint32_t bf[8][2][2];
-  float bia[8][2];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -105,8 +140,6 @@ __global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict_
       bf[nt][kk][0] = *reinterpret_cast<const uint32_t*>(wr);
       bf[nt][kk][1] = *reinterpret_cast<const uint32_t*>(wr + 8);
     }
-    bia[nt][0] = bias[nt * 8 + q2];
-    bia[nt][1] = bias[nt * 8 + q2 + 1];
   }
   // im2col offsets of this lane's 8 A columns: j = kk*16 + q2 + {0, 1, 8, 9}
   int off[2][4];
@@ -171,11 +204,14 @@ __global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict_
       }
       const int y = y0 + ly;
       const int xa = x0 + r, xb = xa + 8;
+      // (A quad transpose to 32-byte stores was measured here and changed nothing: this kernel is bound by how few warps
+      // fit an SM, not by its store requests.)
       __half* oa = out + ((size_t)y * W + xa) * 64 + q2;
       __half* ob = out + ((size_t)y * W + xb) * 64 + q2;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        float c[4] = {bia[nt][0], bia[nt][1], bia[nt][0], bia[nt][1]};
+        const float2 bia = *reinterpret_cast<const float2*>(sbias + nt * 8 + q2);   // (registers are what limits the CTAs per SM)
+        float c[4] = {bia.x, bia.y, bia.x, bia.y};
         mma16816(c, a[0], bf[nt][0][0], bf[nt][0][1]);
         mma16816(c, a[1], bf[nt][1][0], bf[nt][1][1]);
         if (y < H) {
@@ -262,7 +298,7 @@ __global__ void upsample2_kernel(const __half* __restrict__ in, int H, int W, in
 // ---------------------------------------------------------------------------------------------
 // NT n-tiles of 8 output columns: NT*8 >= C_out + 1 (5 for 32+1, 17 for 128+1)
 template <int NT>
-__global__ void __launch_bounds__(256) head_mma_kernel(const __half* __restrict__ x, int npix, int Cin, int Cout,
+__global__ void __launch_bounds__(256, NT <= 5 ? 3 : 1) head_mma_kernel(const __half* __restrict__ x, int npix, int Cin, int Cout,
                                                        const __half* __restrict__ w, const float* __restrict__ b,
                                                        float* __restrict__ feat, float* __restrict__ conf,
                                                        int normalize, int wpb) {
@@ -357,16 +393,32 @@ __global__ void __launch_bounds__(256) head_mma_kernel(const __half* __restrict_
       const float i0 = normalize ? 1.f / fmaxf(sqrtf(ss0), 1e-12f) : 1.f;
       const float i1 = normalize ? 1.f / fmaxf(sqrtf(ss1), 1e-12f) : 1.f;
       const int pa = p0 + mt * 16 + r, pb = pa + 8;
+      const int q = lane & 3;
+      // descriptor channels: groups of four n-tiles (32 channels) go through the quad transpose, lane q then writes
+      // channels [32 g + 8 q, + 8) of its pixel as one 32-byte store (Cout is 32 or 128)
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int n = nt * 8 + q2;
-        if (n < Cout) {
-          if (pa < npix) *reinterpret_cast<float2*>(feat + (size_t)pa * Cout + n) = make_float2(acc[mt][nt][0] * i0, acc[mt][nt][1] * i0);
-          if (pb < npix) *reinterpret_cast<float2*>(feat + (size_t)pb * Cout + n) = make_float2(acc[mt][nt][2] * i1, acc[mt][nt][3] * i1);
-        } else if (n == Cout) {   // uncertainty column: confidence = sigmoid(-u)
-          if (pa < npix) conf[pa] = 1.f / (1.f + expf(acc[mt][nt][0]));
-          if (pb < npix) conf[pb] = 1.f / (1.f + expf(acc[mt][nt][2]));
+      for (int g = 0; g < (NT - 1) / 4; ++g) {
+        uint32_t va[2][2][2], vb[2][2][2], oa[4][2], ob[4][2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int nt = g * 4 + t;
+          va[t >> 1][t & 1][0] = __float_as_uint(acc[mt][nt][0] * i0);
+          va[t >> 1][t & 1][1] = __float_as_uint(acc[mt][nt][1] * i0);
+          vb[t >> 1][t & 1][0] = __float_as_uint(acc[mt][nt][2] * i1);
+          vb[t >> 1][t & 1][1] = __float_as_uint(acc[mt][nt][3] * i1);
         }
+        quad_transpose<2>(va, q, oa);
+        quad_transpose<2>(vb, q, ob);
+        if (pa < npix)
+          st_global_256(feat + (size_t)pa * Cout + g * 32 + 8 * q, oa[0][0], oa[0][1], oa[1][0], oa[1][1], oa[2][0], oa[2][1], oa[3][0],
+                        oa[3][1]);
+        if (pb < npix)
+          st_global_256(feat + (size_t)pb * Cout + g * 32 + 8 * q, ob[0][0], ob[0][1], ob[1][0], ob[1][1], ob[2][0], ob[2][1], ob[3][0],
+                        ob[3][1]);
+      }
+      if (q2 == 0) {   // uncertainty column (n-tile NT - 1, column 0): confidence = sigmoid(-u)
+        if (pa < npix) conf[pa] = 1.f / (1.f + expf(acc[mt][NT - 1][0]));
+        if (pb < npix) conf[pb] = 1.f / (1.f + expf(acc[mt][NT - 1][2]));
       }
     }
     }   // compute warps
@@ -384,10 +436,12 @@ int launch_head(const PtkContext* ctx, const __half* x, long long npix, int Cin,
   static int configured = 0;
   if (configured < smem) {
     PTK_CUDA_CHECK(cudaFuncSetAttribute(head_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // the level-0 head (NT = 5) is compiled for three CTAs per SM (80 registers): ask for the shared memory to match
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(head_mma_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = smem;
   }
   long long blocks = (groups + wpb - 1) / wpb;
-  const long long cap = 2LL * ctx->num_sms;
+  const long long cap = (NT <= 5 ? 3LL : 2LL) * ctx->num_sms;
   if (blocks > cap) blocks = cap;
   PTK_CUDA_CHECK(ptk_launch_pdl(head_mma_kernel<NT>, dim3((unsigned)blocks), dim3(256), (size_t)smem, s, dim3(1, 1, 1), x, (int)npix, Cin, Cout,
                                 w, b, feat, conf, normalize, (int)wpb));
