@@ -1369,6 +1369,221 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
+// conv_row64_kernel: CTA pairs on maps at most 64 pixels wide (the 1/16-scale block: 36 x 64, 47 x 63, 512 channels).
+//
+// These layers ran on the per-tap kernel with its K loop split over two CTAs: 144 / 192 CTAs that each stage 1.15 MB
+// for 5 us of MMA work -- bound by L2 -> shared traffic (166 MB per layer) at ~500 TFLOP/s.  A 64-pixel row cannot use
+// conv_row2_kernel's view (an MMA's 128 rows must be 128 consecutive staged pixels, and a 66-pixel halo row breaks the
+// run at every image row).  Instead the halo of a 64-channel chunk is staged as THREE column-shifted copies, one per
+// dx: box {64 ch, 64 px, 4 rows} at x = dx - 1, dense 64-pixel pitch.  In copy dx, rows (dy, dy + 1) are 128 consecutive
+// pixels = the operand of tap (dy, dx) for the CTA's two output rows.  A pair (cta_group::2, M = 256 x N = 128, each CTA
+// stages half of every weight tile) owns four rows; activations are staged 3x instead of 9x and weights once per pair:
+// 97 MB per layer.  Taps run dx-major so that a copy is released after its three taps.
+// ---------------------------------------------------------------------------------------------
+constexpr int kR64ABytes = 4 * 64 * 128;            // one column-shifted halo copy: 32 KB
+constexpr int kR64ASlots = 4;
+constexpr int kR64BBytes = 64 * 128;                // this CTA's half of a 128-row weight tile: 8 KB
+constexpr int kR64BSlots = 11;
+constexpr int kR64Smem = kR64ASlots * kR64ABytes + kR64BSlots * kR64BBytes + (2 * kR64ASlots + 2 * kR64BSlots + 4) * 8 + 16 +
+                         4 * 128 * 4 + 1024;
+static_assert(kR64Smem <= 232448, "shared memory budget");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+    conv_row64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                      const __grid_constant__ CUtensorMap tmW, const HaloParams P) {
+  constexpr int N = 128;
+  constexpr uint32_t kTmemCols = 256;                // two accumulator sets of 128 columns
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kR64ASlots * kR64ABytes;
+  uint64_t* fullA = (uint64_t*)(sB + kR64BSlots * kR64BBytes);
+  uint64_t* emptyA = fullA + kR64ASlots;
+  uint64_t* fullB = emptyA + kR64ASlots;
+  uint64_t* emptyB = fullB + kR64BSlots;
+  uint64_t* tmem_full = emptyB + kR64BSlots;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float* s_bias_all = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][N]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int chunks = P.chunks0 + P.chunks1;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    if (P.chunks1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    for (int s = 0; s < kR64ASlots; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&emptyA[s], 1);
+    }
+    for (int s = 0; s < kR64BSlots; ++s) {
+      mbar_init(&fullB[s], 1);
+      mbar_init(&emptyB[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps of each CTA arrive on the leader's copy
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  cluster_sync_all();                // the peer is running before the pair allocation touches its shared memory (see conv_halo2_kernel)
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs: own halo copies, own half of the weight rows) ----------------
+      uint32_t a_it = 0, b_it = 0;
+      int b_ahead = 0;               // weight tiles already requested ahead of the sequence (before the dependent-launch wait)
+      bool waited = false;
+      for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs) {
+        const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
+        const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
+        const int h0 = (th * 2 + (int)rank) * 2, w0 = tw * 64, n0 = nb * N + (int)rank * (N / 2);
+        for (int c = 0; c < chunks; ++c) {
+          auto load_weight = [&](int dx, int dy) {
+            const int sb = b_it % kR64BSlots;
+            mbar_wait(&emptyB[sb], ((b_it / kR64BSlots) & 1u) ^ 1u);
+            if (leader) mbar_expect_tx(&fullB[sb], 2 * kR64BBytes);
+            tma_load_3d_pair(sB + sb * kR64BBytes, &tmW, &fullB[sb], c * kKChunk, n0, dy * 3 + dx);
+            ++b_it;
+          };
+          if (!waited) {   // the first chunk's nine weight tiles, then the programmatic-dependent-launch wait, then activations
+            for (int t = 0; t < 9; ++t) load_weight(t / 3, t % 3);
+            b_ahead = 9;
+            ptk_pdl_wait();
+            ptk_pdl_trigger();
+            waited = true;
+          }
+          for (int dx = 0; dx < 3; ++dx) {
+            const int sa = a_it % kR64ASlots;
+            mbar_wait(&emptyA[sa], ((a_it / kR64ASlots) & 1u) ^ 1u);
+            if (leader) mbar_expect_tx(&fullA[sa], 2 * kR64ABytes);    // both CTAs' copies are credited here
+            uint8_t* dst = sA + sa * kR64ABytes;
+            if (c < P.chunks0) tma_load_3d_pair(dst, &tmA0, &fullA[sa], c * kKChunk, w0 + dx - 1, h0 - 1);
+            else tma_load_3d_pair(dst, &tmA1, &fullA[sa], (c - P.chunks0) * kKChunk, w0 + dx - 1, h0 - 1);
+            ++a_it;
+            for (int dy = 0; dy < 3; ++dy) {
+              if (b_ahead > 0) --b_ahead;
+              else load_weight(dx, dy);
+            }
+          }
+        }
+      }
+      if (!waited) {
+        ptk_pdl_wait();
+        ptk_pdl_trigger();
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---------------- MMA issuer of the pair (warp-uniform loop, one elected lane issues) ----------------
+      uint32_t a_it = 0, b_it = 0, t_it = 0;
+      for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs, ++t_it) {
+        const uint32_t buf = t_it & 1u;
+        mbar_wait(&tmem_empty[buf], ((t_it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + buf * (uint32_t)N;
+        for (int c = 0; c < chunks; ++c) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int sa = a_it % kR64ASlots;
+            mbar_wait(&fullA[sa], (a_it / kR64ASlots) & 1u);
+            ++a_it;
+            int sb[3];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              sb[dy] = b_it % kR64BSlots;
+              mbar_wait(&fullB[sb[dy]], (b_it / kR64BSlots) & 1u);
+              ++b_it;
+            }
+            tc_fence_after();
+            // rows (dy, dy + 1) of the copy = 128 consecutive pixels, core matrices 1 024 B apart
+            const uint64_t adesc0 = make_sw128_desc(smem_u32(sA + sa * kR64ABytes));
+            if (elect_one()) {
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                const uint64_t adesc = adesc0 + (uint64_t)(dy * 64 * 8);
+                const uint64_t bdesc = make_sw128_desc(smem_u32(sB + sb[dy] * kR64BBytes));
+#pragma unroll
+                for (int k = 0; k < kKChunk / 16; ++k)
+                  tc_mma_f16_pair(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (c | dx | dy | k) != 0 ? 1u : 0u);
+                tc_commit_pair(&emptyB[sb[dy]]);
+              }
+              tc_commit_pair(&emptyA[sa]);
+            }
+            __syncwarp();
+          }
+        }
+        if (elect_one()) tc_commit_pair(&tmem_full[buf]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs, own TMEM lanes): lane m = pixel (row m / 64, column m % 64) ----------------
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    uint32_t t_it = 0;
+    for (int tile = pair_id; tile < P.total_tiles; tile += n_pairs, ++t_it) {
+      const int nb = tile / P.tiles_hw, sp = tile - nb * P.tiles_hw;
+      const int th = sp / P.tiles_w, tw = sp - th * P.tiles_w;
+      const int h = (th * 2 + (int)rank) * 2 + (m >> 6), w = tw * 64 + (m & 63), n0 = nb * N;
+      const uint32_t buf = t_it & 1u;
+      float* s_bias = s_bias_all + (warp - 2) * N;
+      stage_bias<N>(s_bias, P.bias + n0, lane);
+      const PairStore ps = pair_store_setup(P.out + ((size_t)h * P.W + w) * P.Cout + n0, h < P.H && w < P.W, lane);
+      mbar_wait(&tmem_full[buf], (t_it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < N; c += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)N + (uint32_t)c, v);
+        uint32_t pw[16];
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 bq = b4[j >> 1];
+          float a = __uint_as_float(v[2 * j]) + ((j & 1) ? bq.z : bq.x);
+          float b = __uint_as_float(v[2 * j + 1]) + ((j & 1) ? bq.w : bq.y);
+          if (P.relu) {
+            a = fmaxf(a, 0.f);
+            b = fmaxf(b, 0.f);
+          }
+          const __half2 hv = __floats2half2_rn(a, b);
+          pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+        }
+        pair_store(ps, c, pw, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();                // the peer may still read this CTA's shared memory / TMEM until here
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1468,6 +1683,18 @@ int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap
   }
   // the cluster shape is the kernel's compile-time __cluster_dims__(2, 1, 1)
   PTK_CUDA_CHECK(ptk_launch_pdl(conv_halo2_kernel<N>, dim3(2 * n_pairs), dim3(kHaloThreads), smem, stream, dim3(1, 1, 1), a0, a1, w, P));
+  return PTK_OK;
+}
+
+int launch_row64(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int n_pairs,
+                 cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_row64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kR64Smem));
+    configured = true;
+  }
+  // the cluster shape is the kernel's compile-time __cluster_dims__(2, 1, 1)
+  PTK_CUDA_CHECK(ptk_launch_pdl(conv_row64_kernel, dim3(2 * n_pairs), dim3(kHaloThreads), kR64Smem, stream, dim3(1, 1, 1), a0, a1, w, P));
   return PTK_OK;
 }
 
@@ -1588,6 +1815,39 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
         }
         if (pair_n == 64) return launch_halo2<64>(a0, a1, wm, Q, n_launch, s);
         return pair_n == 256 ? launch_halo2<256>(a0, a1, wm, Q, n_launch, s) : launch_halo2<128>(a0, a1, wm, Q, n_launch, s);
+      }
+      // Maps at most 64 pixels wide with a long K and many channels (the 1/16-scale block): conv_row64_kernel.
+      // PTK_CONV_ROW64: 0 = never, 1 = maps 48..64 pixels wide with >= 44 pair tiles (default), 2 = whenever legal.
+      // Measured, 512->512, 10 launches back to back: 47 x 63 (48 pair tiles) 29.4 -> 27.6 us; 36 x 64 (36 pair tiles =
+      // half of the SMs, each CTA pulling 72 B/clk at the MMA rate) 21.9 -> 26.1 us, so that one stays on the per-tap kernel.
+      static int row64_mode = -1;
+      if (row64_mode < 0) row64_mode = getenv("PTK_CONV_ROW64") ? atoi(getenv("PTK_CONV_ROW64")) : 1;
+      if (row64_mode != 0 && mode != 0 && taps == 9 && Cout % 128 == 0 && pool_out == nullptr) {
+        const int col_tiles = (W + 63) / 64, row_tiles = (H + 3) / 4;
+        const int tiles = col_tiles * row_tiles * (Cout / 128);
+        const bool wanted64 = row64_mode == 2 || (ctot >= 256 && W <= 64 && W >= 48 && tiles >= 44 && tiles <= 2 * pair_slots);
+        if (wanted64) {
+          rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, 64, 4);
+          if (rc != PTK_OK) return rc;
+          if (cin1 > 0) {
+            rc = make_map_3d(&a1, in1, cin1, W, H, cin1, (uint64_t)in1_W * cin1, kKChunk, 64, 4);
+            if (rc != PTK_OK) return rc;
+          } else {
+            a1 = a0;
+          }
+          rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, 64, 1);
+          if (rc != PTK_OK) return rc;
+          HaloParams Q;
+          Q.H = H; Q.W = W; Q.Cout = Cout; Q.chunks0 = cin0 / kKChunk; Q.chunks1 = cin1 / kKChunk; Q.relu = relu;
+          Q.tiles_w = col_tiles; Q.tiles_hw = col_tiles * row_tiles; Q.total_tiles = tiles;
+          Q.resident = 0;
+          Q.dbg = nullptr;
+          Q.rows_per_op = 4;
+          Q.bias = bias;
+          Q.out = (__half*)out;
+          Q.pool = nullptr;
+          return launch_row64(a0, a1, wm, Q, tiles < pair_slots ? tiles : pair_slots, s);
+        }
       }
       // Row tiles on CTA pairs (conv_row2_kernel): maps about 128 pixels wide with a long K, where 16x16 tiles quantise badly
       // and the per-tap kernel is bound by its L2 -> shared traffic.  PTK_CONV_ROW: 0 = never, 1 = when one of R = 2 / 3

@@ -172,6 +172,36 @@ def test_row_tile_pair_kernel_forced_shapes():
     assert r.returncode == 0 and 'row pair ok' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+ROW64_DEFAULT_SHAPES = [
+    (512, 0, 512, 47, 63, False),       # 1/16-scale block of the 1008x756 plan: 48 pair tiles, ragged last column and rows
+    (256, 256, 512, 45, 60, False),     # two inputs
+]
+ROW64_FORCED_SHAPES = [
+    (512, 0, 512, 36, 64, False),       # 1/16-scale block of the 1024x576 plan (by default on the per-tap kernel, which is faster there)
+    (128, 0, 128, 23, 100, False),      # two column tiles (the second 36 pixels wide), 2 chunks
+    (256, 0, 128, 610, 64, False),      # 153 pair tiles on 74 SM pairs: the persistent loop and both accumulator sets
+    (64, 64, 256, 9, 17, False),        # tiny map, two inputs of one chunk each, two C_out groups
+]
+
+
+def test_narrow_map_pair_kernel_default_dispatch():
+    """Long-K layers on maps 48..64 pixels wide (the 512-channel 1/16-scale block) run on conv_row64_kernel: the halo is
+    staged as three column-shifted copies so that two image rows form one 128-row MMA operand; CTA pairs, cta_group::2."""
+    _row_pair_checks(ROW64_DEFAULT_SHAPES)
+
+
+def test_narrow_map_pair_kernel_forced_shapes():
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PTK_CONV_ROW64='2', PTK_CONV_PAIR='0', PTK_CONV_ROW='0')
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, '-c', 'import sys; sys.path[:0] = [%r, %r]; import test_conv_paths_gpu as t; '
+                        't._row_pair_checks(t.ROW64_FORCED_SHAPES)' % (here, os.path.dirname(here))], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'row pair ok' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 SPLIT_SHAPES = [
     (512, 0, 512, 36, 64, False),       # 1/16-scale block of the 1024x576 plan: halo<128, SPLIT 2>, 48 tiles x 2 CTAs
     (512, 0, 512, 47, 63, False),       # ... of the 1008x756 plan (odd sizes, ragged tiles)
