@@ -610,7 +610,11 @@ def run_ours(args, rank, world, local_rank, wl):
             library = library_leg(trk, step, seq, wl, dev, args.steps)
             log('legs done')
         fps = args.steps * world / (ms_total * 1e-3)
-        launches_per_frame = 2 * n_launch_plan + 1 + 3 + (4 + 6 if tbs else 0)
+        # launches of the two extractor plans as they last ran (27 each with the level-0 head fused, else 28) + reference
+        # sampling + the three LM levels (+ the NeRF renders of a C5 frame)
+        counts = [n for key, n in ext.launch_counts().items()]
+        plan_launches = sum(sorted(counts)[:2]) if len(counts) >= 2 else 2 * n_launch_plan
+        launches_per_frame = plan_launches + 1 + 3 + (4 + 6 if tbs else 0)
         line = {
             'metric': 'tracked frames/sec (LM-to-convergence)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,

@@ -260,6 +260,9 @@ int ptk_extractor_run(PtkExtractor* e, const void* image, int32_t img_dtype, int
 int ptk_extractor_profile(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
                           float* const* feat, float* const* conf, int32_t normalize, void* stream, int32_t max_n,
                           float* ms, int32_t* kinds, double* flops, int32_t* n_out);
+/* Kernel launches of the plan's last run: 28, or 27 when the level-0 head ran inside the epilogue of the last decoder
+ * convolution (PTK_FUSE_HEAD=1; off by default, it measured slower). */
+int ptk_extractor_launch_count(const PtkExtractor* e, int32_t* n);
 /* test access to intermediate fp16 NHWC activations: kind 0 = encoder block output, 1 = decoder block output */
 int ptk_extractor_activation(const PtkExtractor* e, int32_t kind, int32_t index, const void** ptr, int32_t* C,
                              int32_t* H, int32_t* W);

@@ -100,6 +100,7 @@ SYMBOLS = {
     'ptk_extractor_profile': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int32, c_f32p, c_i32p,
                                         C.POINTER(C.c_double), c_i32p]),
+    'ptk_extractor_launch_count': (C.c_int, [C.c_void_p, c_i32p]),
     'ptk_extractor_activation': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_i32p, c_i32p,
                                            c_i32p]),
     'ptk_nerf_create': (C.c_int, [C.c_void_p, C.POINTER(NerfModelStruct), C.POINTER(C.c_void_p)]),

@@ -37,6 +37,21 @@ struct PtkDeviceGuard {
   }
 };
 
+// Level-0 head of the extractor, fused into the epilogue of the last decoder convolution (ptk_conv.cu, library-internal).
+// The 33 x 32 weights travel as a KERNEL PARAMETER: they then sit in the constant bank and every FMA of the head takes
+// its weight as a constant operand -- no load instruction and no shared-memory traffic next to the tensor core's operand
+// fetch (a first version that kept them in shared memory slowed the convolution down by more than the head costs).
+struct PtkHeadConst {
+  float w[33 * 32];   // 32 adaptation rows + the uncertainty row, fp32 copies of the fp16 weights
+  float b[33];
+  float* feat;        // [H][W][32]
+  float* conf;        // [H][W]
+  int normalize;
+};
+int ptk_conv_f16_head(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
+                      int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
+                      int32_t Cout, int32_t taps, int32_t relu, void* out, void* stream, const PtkHeadConst* head, int* fused);
+
 // ---- programmatic dependent launch (PDL) ----
 // Kernels of a chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may
 // start (barrier / TMEM set-up, tensor-map and weight prefetch) while the previous kernel drains, and block in

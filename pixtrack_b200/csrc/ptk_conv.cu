@@ -172,6 +172,55 @@ __device__ __forceinline__ void stage_bias(float* s_bias, const float* bias, int
   __syncwarp();
 }
 
+// The extractor's level-0 head fused into the epilogue of the last decoder convolution (C_out = 32): the lane holds its
+// pixel's 32 output channels (already rounded to fp16, which is what the separate head kernel would read back); the
+// 33 x 32 weights are kernel parameters, i.e. constant-bank operands of the FMAs: 1 056 FMAs per pixel on epilogue warps
+// that otherwise wait for the MMAs 80 % of the time.  Same arithmetic as head_mma_kernel up to the fp32 summation order.
+// (unet.py:175-188: adaptation layer, uncertainty layer, sigmoid(-u), L2 normalisation.)
+template <bool kHead>
+struct HeadArg {};
+template <>
+struct HeadArg<true> {
+  PtkHeadConst c;
+};
+__device__ __forceinline__ void fused_head32(const uint32_t (&pw)[16], const PtkHeadConst& hc, size_t pixel, bool inside) {
+  float x[32];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pw[j]));
+    x[2 * j] = f.x;
+    x[2 * j + 1] = f.y;
+  }
+  // k outer, n inner: 33 independent accumulator chains; the empty asm keeps the compiler from hoisting the constant
+  // loads of later k steps (which spilled ~1.8 KB per thread)
+  float y[33];
+#pragma unroll
+  for (int n = 0; n < 33; ++n) y[n] = hc.b[n];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+#pragma unroll
+    for (int n = 0; n < 33; ++n) y[n] = fmaf(x[k], hc.w[n * 32 + k], y[n]);
+    asm volatile("" ::: "memory");
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int n = 0; n < 32; ++n) ss = fmaf(y[n], y[n], ss);
+  const float inv = hc.normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+  if (inside) {
+    float* dst = hc.feat + pixel * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(y[8 * g + i] * inv);
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * g), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                   "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                   : "memory");
+    }
+    hc.conf[pixel] = 1.f / (1.f + expf(y[32]));
+  }
+}
+
 // Output rows are written by lane PAIRS: a lane holds 32 output channels (64 B) of its own pixel, but a warp-wide 16-byte
 // store of those scatters over 32 different lines -- 128 requests of 16 B per 32 channels, and the SM's store path, not
 // the tensor pipe, then bounds every layer with a large output map (measured: 9.4 K cycles of epilogue per 256 x 128 tile
@@ -483,11 +532,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // once rank 0's MMAs have retired (rank 0 tells rank 1 so through `go_bar`) -- column-major, so a warp writes 128
 // contiguous bytes per store, and arrives on rank 0's `peer_bar`; rank 0 adds them in its epilogue.  One tile per
 // cluster (not persistent): grid = 2 x total_tiles.
-template <int N, int SPLIT>
+template <int N, int SPLIT, bool kHead = false>
 __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                     const __grid_constant__ CUtensorMap tmA1,
                                                                     const __grid_constant__ CUtensorMap tmW,
-                                                                    const HaloParams P) {
+                                                                    const HaloParams P,
+                                                                    const __grid_constant__ HeadArg<kHead> head) {
+  static_assert(!kHead || (N == 32 && SPLIT == 1), "the fused head needs all 32 channels of a pixel in one lane");
   constexpr int kBBytes = N * 128;
   constexpr int kSlots = kBBudget / kBBytes;
   static_assert(SPLIT == 1 || N * 256 * 4 <= 2 * kHaloBytes + kBBudget, "partial sums must fit the operand staging area");
@@ -768,6 +819,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
             pw[j] = *reinterpret_cast<const uint32_t*>(&hv);
           }
           pair_store(ps, c, pw, lane);
+          if constexpr (kHead) fused_head32(pw, head.c, (size_t)h * P.W + w, inside);
           if (P.pool != nullptr) {   // x neighbour = lane ^ 1, y neighbour = lane ^ 8
             pool_quad<8>(pw);
             if (pool_writer) {
@@ -1661,12 +1713,29 @@ int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     configured = true;
   }
   if (SPLIT == 1) {
-    PTK_CUDA_CHECK(ptk_launch_pdl(conv_halo_kernel<N, SPLIT>, dim3(grid), dim3(kHalo1Threads), smem, stream, dim3(1, 1, 1), a0, a1, w, P));
+    PTK_CUDA_CHECK(ptk_launch_pdl(conv_halo_kernel<N, SPLIT>, dim3(grid), dim3(kHalo1Threads), smem, stream, dim3(1, 1, 1), a0, a1, w, P,
+                                  HeadArg<false>()));
   } else {   // one cluster of SPLIT CTAs per tile
     PTK_CUDA_CHECK(ptk_launch_pdl(conv_halo_kernel<N, SPLIT>, dim3(SPLIT * P.total_tiles), dim3(kHalo1Threads), smem, stream,
-                                  dim3(SPLIT, 1, 1), a0, a1, w, P));
+                                  dim3(SPLIT, 1, 1), a0, a1, w, P, HeadArg<false>()));
   }
   PTK_CUDA_CHECK(cudaGetLastError());
+  return PTK_OK;
+}
+
+// conv_halo_kernel<32> with the level-0 head in its epilogue
+int launch_halo32_head(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int grid,
+                       cudaStream_t stream, const PtkHeadConst& hc) {
+  constexpr int kSlots = kBBudget / (32 * 128);
+  constexpr int smem = 2 * kHaloBytes + kSlots * 32 * 128 + (4 + 2 * kSlots + 6) * 8 + 16 + 8 * 32 * 4 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<32, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  HeadArg<true> ha;
+  ha.c = hc;
+  PTK_CUDA_CHECK(ptk_launch_pdl(conv_halo_kernel<32, 1, true>, dim3(grid), dim3(kHalo1Threads), smem, stream, dim3(1, 1, 1), a0, a1, w, P, ha));
   return PTK_OK;
 }
 
@@ -1721,9 +1790,11 @@ static int pick_block_n(int Cout, int m_tiles, int num_sms) {
 }
 
 // ptk_conv_f16 plus an optional fused 2x2 max pool of the result (the extractor plan's encoder blocks)
-extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
-                      int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
-                      int32_t Cout, int32_t taps, int32_t relu, void* out, void* pool_out, void* stream) {
+static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
+                         int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
+                         int32_t Cout, int32_t taps, int32_t relu, void* out, void* pool_out, void* stream,
+                         const PtkHeadConst* head, int* head_fused) {
+  if (head_fused != nullptr) *head_fused = 0;
   PTK_REQUIRE(ctx && in0 && weights && bias && out, "null argument");
   PtkDeviceGuard guard(ctx->device);
   PTK_REQUIRE(taps == 9 || taps == 1, "taps must be 9 (3x3, pad 1) or 1 (1x1)");
@@ -1971,6 +2042,10 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
       Q.pool = (__half*)pool_out;
       Q.dbg = nullptr;
       const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+      if (head != nullptr && n_halo == 32 && Cout == 32) {   // the level-0 head rides in this kernel's epilogue
+        if (head_fused != nullptr) *head_fused = 1;
+        return launch_halo32_head(a0, a1, wm, Q, grid, s, *head);
+      }
       static int dbg_mode = -1;
       if (dbg_mode < 0) dbg_mode = getenv("PTK_CONV_DBG") ? atoi(getenv("PTK_CONV_DBG")) : 0;
       if (dbg_mode) {   // stall attribution (debug only: synchronises and prints)
@@ -2059,6 +2134,22 @@ extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0,
     case 128: return launch_conv<128, 3>(a0, a1, wm, P, s);
     default: return launch_conv<256, 3>(a0, a1, wm, P, s);
   }
+}
+
+extern "C" int ptk_conv_f16_pool(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
+                      int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
+                      int32_t Cout, int32_t taps, int32_t relu, void* out, void* pool_out, void* stream) {
+  return conv_dispatch(ctx, in0, cin0, in1, cin1, H, W, in0_H, in0_W, in1_H, in1_W, weights, bias, Cout, taps, relu, out, pool_out,
+                       stream, nullptr, nullptr);
+}
+
+// ptk_conv_f16 with the extractor's level-0 head fused into the epilogue when the layer lands on conv_halo_kernel<32>
+// (*fused tells; otherwise the caller launches the head itself).  Library-internal.
+int ptk_conv_f16_head(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H, int32_t W,
+                      int32_t in0_H, int32_t in0_W, int32_t in1_H, int32_t in1_W, const void* weights, const float* bias,
+                      int32_t Cout, int32_t taps, int32_t relu, void* out, void* stream, const PtkHeadConst* head, int* fused) {
+  return conv_dispatch(ctx, in0, cin0, in1, cin1, H, W, in0_H, in0_W, in1_H, in1_W, weights, bias, Cout, taps, relu, out, nullptr,
+                       stream, head, fused);
 }
 
 extern "C" int ptk_conv_f16(PtkContext* ctx, const void* in0, int32_t cin0, const void* in1, int32_t cin1, int32_t H,

@@ -475,6 +475,8 @@ struct PtkExtractor {
   // optional per-launch timing (ptk_extractor_profile): events recorded after every launch
   cudaEvent_t* prof_ev;
   int prof_n;
+  int head0_fused;   // last run: the level-0 head ran inside the last decoder convolution (one launch fewer)
+  PtkHeadConst* head0;   // host copy of the level-0 head's weights as fp32 (they travel as kernel parameters when fused)
   // the coarse heads run next to the decoder on a side stream (forked / joined with events, so the
   // plan is still one stream-ordered unit for the caller and can be captured in a CUDA graph)
   cudaStream_t side;
@@ -534,6 +536,14 @@ extern "C" int ptk_extractor_create(PtkContext* ctx, const PtkUnetWeights* w, in
     e->up[i] = (__half*)take((size_t)e->dh[i] * e->dw[i] * cprev * 2);
     e->dec[i] = (__half*)take((size_t)e->dh[i] * e->dw[i] * kDec[i] * 2);
   }
+  {   // level-0 head weights -> host fp32 (fp16 [33][32] + fp32 [33] on the device)
+    e->head0 = (PtkHeadConst*)calloc(1, sizeof(PtkHeadConst));
+    static_assert(sizeof(PtkHeadConst) < 8192, "kernel parameter budget");
+    __half hw[33 * 32];
+    PTK_CUDA_CHECK(cudaMemcpy(hw, e->wts.head_w[0], sizeof(hw), cudaMemcpyDeviceToHost));
+    PTK_CUDA_CHECK(cudaMemcpy(e->head0->b, e->wts.head_b[0], 33 * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 33 * 32; ++i) e->head0->w[i] = __half2float(hw[i]);
+  }
   PTK_CUDA_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) PTK_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming));
   PTK_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
@@ -549,6 +559,7 @@ extern "C" void ptk_extractor_destroy(PtkExtractor* e) {
   for (int i = 0; i < 2; ++i) if (e->ev_fork[i]) cudaEventDestroy(e->ev_fork[i]);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->arena) cudaFree(e->arena);
+  free(e->head0);
   free(e);
 }
 
@@ -576,6 +587,13 @@ extern "C" int ptk_extractor_activation(const PtkExtractor* e, int32_t kind, int
   }
   ptk_set_error("no such activation (%d, %d)", kind, index);
   return PTK_ERR_INVALID;
+}
+
+// Kernel launches of the last run of this plan (28 with the level-0 head as its own launch, 27 with it fused).
+extern "C" int ptk_extractor_launch_count(const PtkExtractor* e, int32_t* n) {
+  PTK_REQUIRE(e && n, "null argument");
+  *n = 28 - (e->head0_fused ? 1 : 0);
+  return PTK_OK;
 }
 
 static int run_plan(PtkExtractor* e, const void* image, int32_t img_dtype, int32_t img_h, int32_t img_w,
@@ -636,6 +654,15 @@ static int run_plan(PtkExtractor* e, const void* image, int32_t img_dtype, int32
   // stream next to the remaining decoder convolutions (which leave SMs idle at these map sizes).  With per-launch
   // profiling on, everything stays on the caller's stream.
   const bool fork = e->prof_ev == nullptr;
+  // PTK_FUSE_HEAD=1 runs the level-0 head inside the epilogue of the last decoder convolution (27 launches instead of 28).
+  // Off by default: measured on the C2 frame loop it LOSES 3 % (568 against 588 frames/s, one extraction 0.702 against
+  // 0.681 ms) -- that convolution (C_out = 32) is bound by the tensor core's operand fetch from shared memory, its MMA warp
+  // shares the SM's issue slots with the epilogue warps, and 2 100 more instructions per pixel row there cost more than
+  // the 34 us launch they replace.  (A first version with the weights in shared memory lost 5 %.)
+  static int fuse_mode = -1;
+  if (fuse_mode < 0) fuse_mode = getenv("PTK_FUSE_HEAD") ? atoi(getenv("PTK_FUSE_HEAD")) : 0;
+  const bool fuse_head0 = fuse_mode != 0 && e->prof_ev == nullptr && kHeadScale[0] == 0 && kHeadDim[0] == 32 && kDec[3] == 32;
+  int head0_fused = 0;
   if (fork) {
     PTK_CUDA_CHECK(cudaEventRecord(e->ev_fork[0], s));
     PTK_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->ev_fork[0], 0));
@@ -652,9 +679,19 @@ static int run_plan(PtkExtractor* e, const void* image, int32_t img_dtype, int32
     PTK_CUDA_CHECK(ptk_launch_pdl(upsample2_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, dim3(1, 1, 1), prev, ph, pw, cprev,
                                   e->up[i]));
     mark();
-    const int rc = ptk_conv_f16(e->ctx, e->up[i], cprev, e->enc[sb][kEncCount[sb] - 1], cskip, e->dh[i], e->dw[i],
-                                e->dh[i], e->dw[i], e->eh[sb], e->ew[sb], e->wts.conv_w[li], e->wts.conv_b[li], kDec[i], 9,
-                                1, e->dec[i], stream);
+    int rc;
+    if (i == 3 && fuse_head0) {   // the level-0 head rides in the epilogue of the last decoder convolution when it can
+      PtkHeadConst& hf = *e->head0;
+      hf.feat = feat[0];
+      hf.conf = conf[0];
+      hf.normalize = normalize;
+      rc = ptk_conv_f16_head(e->ctx, e->up[i], cprev, e->enc[sb][kEncCount[sb] - 1], cskip, e->dh[i], e->dw[i], e->dh[i], e->dw[i],
+                             e->eh[sb], e->ew[sb], e->wts.conv_w[li], e->wts.conv_b[li], kDec[i], 9, 1, e->dec[i], stream, &hf,
+                             &head0_fused);
+    } else {
+      rc = ptk_conv_f16(e->ctx, e->up[i], cprev, e->enc[sb][kEncCount[sb] - 1], cskip, e->dh[i], e->dw[i], e->dh[i], e->dw[i],
+                        e->eh[sb], e->ew[sb], e->wts.conv_w[li], e->wts.conv_b[li], kDec[i], 9, 1, e->dec[i], stream);
+    }
     if (rc != PTK_OK) return rc;
     mark();
     if (fork && i == 1) {   // dec[1] feeds the level-1 head
@@ -669,11 +706,12 @@ static int run_plan(PtkExtractor* e, const void* image, int32_t img_dtype, int32
     pw = e->dw[i];
     ++li;
   }
-  {
+  if (!head0_fused) {
     const int hrc = run_head(0, s);
     if (hrc != PTK_OK) return hrc;
     mark();
   }
+  e->head0_fused = head0_fused;
   if (fork) {
     PTK_CUDA_CHECK(cudaEventRecord(e->ev_join, e->side));
     PTK_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));

@@ -147,6 +147,16 @@ class B200FeatureExtractor(torch.nn.Module):
             self._plans[(H, W, slot)] = _Plan(self._lib, self._ctx, self._wts, H, W)
         return self._plans[(H, W, slot)]
 
+    def launch_counts(self):
+        """Kernel launches of the last run of every plan: {(H, W, slot): 28 or 27} (27 = the level-0 head ran fused into
+        the last decoder convolution)."""
+        out = {}
+        for key, plan in self._plans.items():
+            n = C.c_int32()
+            _lib.check(self._lib.ptk_extractor_launch_count(plan.h, C.byref(n)))
+            out[key] = n.value
+        return out
+
     def level_shapes(self, ih: int, iw: int, scale_image: int = 1):
         H, W, _ = self.network_size(ih, iw, scale_image)
         return self.plan(H, W).shapes

@@ -248,3 +248,46 @@ print("pair ok")
         env = dict(os.environ, PTK_CONV_PAIR='2', PTK_CONV_PAIR_N=pair_n)
         r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and 'pair ok' in r.stdout, (pair_n, r.stdout + r.stderr)
+
+
+def test_fused_level0_head_matches_the_separate_launch_in_a_subprocess():
+    """PTK_FUSE_HEAD=1 runs the level-0 adaptation + uncertainty layers inside the epilogue of the last decoder
+    convolution (weights as kernel parameters; off by default because it measured slower).  Same inputs, same weights:
+    the fused features must agree with the separate head kernel to fp32 summation order, through direct launches and
+    through the replayed plan graph, and the plan must report one launch fewer."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = '''
+import sys, torch
+sys.path[:0] = [%r, %r]
+import synthetic as syn
+from pixtrack_b200.extractor import B200FeatureExtractor
+torch.set_grad_enabled(False)
+ext = B200FeatureExtractor(syn.unet_weights(0), 'cuda:0')
+img = syn.textured_image(1080, 1920, seed=6).to('cuda:0')
+outs = []
+for _ in range(3):            # direct, capture + launch, replay
+    f, c, _ = ext.extract_device(img, normalize=True)
+    torch.cuda.synchronize()
+    outs.append((f[0].clone().cpu(), c[0].clone().cpu(), f[1].clone().cpu()))
+assert all(torch.equal(outs[0][i], o[i]) for o in outs[1:] for i in range(3))
+print('launches', sorted(ext.launch_counts().values()))
+torch.save(outs[0], sys.argv[1])
+''' % (here, os.path.dirname(here))
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for mode in ('0', '1'):
+            path = os.path.join(td, f'o{mode}.pt')
+            r = subprocess.run([sys.executable, '-c', code, path], env=dict(os.environ, PTK_FUSE_HEAD=mode), capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+            assert ('launches [27]' if mode == '1' else 'launches [28]') in r.stdout, r.stdout
+            res[mode] = torch.load(path)
+    f0, c0, f1_0 = res['0']
+    f1, c1, f1_1 = res['1']
+    assert torch.equal(f1_0, f1_1)                                   # the other levels are untouched
+    assert float((f0 - f1).abs().max()) < 2e-6 and float((c0 - c1).abs().max()) < 2e-6
+    assert abs(float(f1.pow(2).sum(-1).mean()) - 1.0) < 1e-4
