@@ -1156,26 +1156,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowW = 130;                           // staged pixels per halo row: 128 + 2
 
-template <int R>
+template <int R, int N_>
 struct RowGeom {
-  static constexpr int kN = 128;
+  static constexpr int kN = N_;                                        // 128, or 64 for the decoder's 64-channel layers
   static constexpr int kHaloRows = R + 2;
   static constexpr int kHaloBytesExact = kHaloRows * kRowW * 128;
   static constexpr int kStageA = (kHaloBytesExact + 1023) / 1024 * 1024;
-  static constexpr int kBBytes = (kN / 2) * 128;                       // this CTA's half of a weight tile: 8 KB
-  static constexpr int kSlots = (232448 - 1024 - 2 * kStageA - 512 - 4 * kN * 4) / kBBytes;
+  static constexpr int kBBytes = (kN / 2) * 128;                       // this CTA's half of a weight tile: 8 KB (4 KB at N = 64)
+  // halo stages: a single-row tile at N = 64 consumes a chunk in 1 600 cycles, less than one halo load takes to arrive
+  // (measured: 37.8 us with two stages on the first decoder convolution), so it gets a third stage
+  static constexpr int kAStages = (R == 1) ? 3 : 2;
+  static constexpr int kSlotsRaw = (232448 - 1024 - kAStages * kStageA - 768 - 4 * kN * 4) / kBBytes;
+  static constexpr int kSlots = kSlotsRaw > 27 ? 27 : kSlotsRaw;
   static constexpr int kBufs = (2 * R * kN <= 512) ? 2 : 1;            // accumulator sets in TMEM
-  static constexpr int kSmem = 2 * kStageA + kSlots * kBBytes + (4 + 2 * kSlots + 2 * kBufs) * 8 + 16 + 4 * kN * 4 + 1024;
+  static constexpr int kSmem =
+      kAStages * kStageA + kSlots * kBBytes + (2 * kAStages + 2 * kSlots + 2 * kBufs) * 8 + 16 + 4 * kN * 4 + 1024;
   static_assert(R * kN <= 512, "accumulators of one tile must fit TMEM");
   static_assert(kSlots >= 6, "weight ring too short");
   static_assert(kSmem <= 232448, "shared memory budget");
 };
 
-template <int R>
+template <int R, int NN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
     conv_row2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                      const __grid_constant__ CUtensorMap tmW, const HaloParams P) {
-  using G = RowGeom<R>;
+  using G = RowGeom<R, NN>;
   constexpr int N = G::kN;
   constexpr int kSlots = G::kSlots;
   constexpr int kBufs = G::kBufs;
@@ -1185,10 +1190,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + 2 * G::kStageA;
+  uint8_t* sB = smem + G::kAStages * G::kStageA;
   uint64_t* fullA = (uint64_t*)(sB + kSlots * G::kBBytes);
-  uint64_t* emptyA = fullA + 2;
-  uint64_t* fullB = emptyA + 2;
+  uint64_t* emptyA = fullA + G::kAStages;
+  uint64_t* fullB = emptyA + G::kAStages;
   uint64_t* emptyB = fullB + kSlots;
   uint64_t* tmem_full = emptyB + kSlots;
   uint64_t* tmem_empty = tmem_full + kBufs;
@@ -1205,7 +1210,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     if (P.chunks1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < G::kAStages; ++s) {
       mbar_init(&fullA[s], 1);
       mbar_init(&emptyA[s], 1);
     }
@@ -1262,8 +1267,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
             ptk_pdl_trigger();
             waited = true;
           }
-          const int sa = a_it & 1;
-          mbar_wait_t(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u, wA, timed);
+          const int sa = a_it % G::kAStages;
+          mbar_wait_t(&emptyA[sa], ((a_it / G::kAStages) & 1u) ^ 1u, wA, timed);
           if (leader) mbar_expect_tx(&fullA[sa], 2 * G::kHaloBytesExact);    // both CTAs' halos are credited here
           uint8_t* dst = sA + sa * G::kStageA;
           if (c < P.chunks0) tma_load_3d_pair(dst, &tmA0, &fullA[sa], c * kKChunk, w0 - 1, h0 - 1);
@@ -1294,8 +1299,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
         mbar_wait_t(&tmem_empty[buf], ((t_it / kBufs) & 1u) ^ 1u, wT, timed);
         tc_fence_after();
         for (int c = 0; c < chunks; ++c) {
-          const int sa = a_it & 1;
-          mbar_wait_t(&fullA[sa], (a_it >> 1) & 1u, wA, timed);
+          const int sa = a_it % G::kAStages;
+          mbar_wait_t(&fullA[sa], (a_it / G::kAStages) & 1u, wA, timed);
           ++a_it;
           // 128 consecutive pixels of a staged row: core matrices (8 pixels x 128 B) 1 024 B apart
           const uint64_t adesc0 = make_sw128_desc(smem_u32(sA + sa * G::kStageA));
@@ -1349,7 +1354,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       const int h0 = (th * 2 + (int)rank) * R, w = tw * 128 + m, n0 = nb * N;
       const uint32_t buf = t_it % kBufs;
       float* s_bias = s_bias_all + (warp - 2) * N;
-      stage_bias<N>(s_bias, P.bias + n0, lane);
+      if (N >= 128) stage_bias<N>(s_bias, P.bias + n0, lane);
+      else stage_bias<128>(s_bias, P.bias + n0, lane < N / 4 ? lane : 0);
       mbar_wait_t(&tmem_full[buf], (t_it / kBufs) & 1u, wF, timed);
       tc_fence_after();
       PairStore ps[R];
@@ -1767,17 +1773,29 @@ int launch_row64(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap
   return PTK_OK;
 }
 
-template <int R>
+template <int R, int N>
 int launch_row2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int n_pairs,
                 cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_row2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, RowGeom<R>::kSmem));
+    PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_row2_kernel<R, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, RowGeom<R, N>::kSmem));
     configured = true;
   }
   // the cluster shape is the kernel's compile-time __cluster_dims__(2, 1, 1)
-  PTK_CUDA_CHECK(ptk_launch_pdl(conv_row2_kernel<R>, dim3(2 * n_pairs), dim3(kHaloThreads), RowGeom<R>::kSmem, stream, dim3(1, 1, 1), a0, a1, w, P));
+  PTK_CUDA_CHECK(ptk_launch_pdl(conv_row2_kernel<R, N>, dim3(2 * n_pairs), dim3(kHaloThreads), RowGeom<R, N>::kSmem, stream, dim3(1, 1, 1), a0,
+                                a1, w, P));
   return PTK_OK;
+}
+int launch_row2_any(int r, int n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int n_pairs,
+                    cudaStream_t s) {
+  if (n == 64) {
+    if (r == 1) return launch_row2<1, 64>(a0, a1, w, P, n_pairs, s);
+    if (r == 2) return launch_row2<2, 64>(a0, a1, w, P, n_pairs, s);
+    return launch_row2<3, 64>(a0, a1, w, P, n_pairs, s);
+  }
+  if (r == 1) return launch_row2<1, 128>(a0, a1, w, P, n_pairs, s);
+  if (r == 2) return launch_row2<2, 128>(a0, a1, w, P, n_pairs, s);
+  return launch_row2<3, 128>(a0, a1, w, P, n_pairs, s);
 }
 
 }  // namespace
@@ -1926,21 +1944,24 @@ static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const v
       // still beats the per-tap kernel, 61 us), 2 = whenever legal.
       static int row_mode = -1;
       if (row_mode < 0) row_mode = getenv("PTK_CONV_ROW") ? atoi(getenv("PTK_CONV_ROW")) : 1;
-      if (row_mode != 0 && mode != 0 && taps == 9 && Cout % 128 == 0 && ctot >= 256) {
+      const int row_n = Cout == 64 ? 64 : 128;      // N = 64: the decoder's 64-channel layers with a long K
+      if (row_mode != 0 && mode != 0 && taps == 9 && Cout % row_n == 0 && ctot >= 256) {
         const int col_tiles = (W + 127) / 128;
         int best_r = 0;
         double best_eff = 0.0;
-        for (int r = 2; r <= 3; ++r) {
+        for (int r = 3; r >= 1; --r) {                        // (ties go to the larger R: less halo per output row)
           if (pool_out != nullptr && (r & 1)) continue;       // pooled rows must pair up inside one CTA
-          const long tiles = (long)col_tiles * ((H + 2 * r - 1) / (2 * r)) * (Cout / 128);
+          const long tiles = (long)col_tiles * ((H + 2 * r - 1) / (2 * r)) * (Cout / row_n);
           const long wv = (tiles + pair_slots - 1) / pair_slots;
-          const double eff = (double)H * W * (Cout / 128) / ((double)wv * pair_slots * 2 * r * 128);
-          if (eff > best_eff) {
+          const double eff = (double)H * W * (Cout / row_n) / ((double)wv * pair_slots * 2 * r * 128);
+          if (eff > best_eff + 1e-9) {
             best_eff = eff;
             best_r = r;
           }
         }
-        if (best_r != 0 && (row_mode == 2 || best_eff >= 0.6)) {
+        static double need = -1.0;      // PTK_CONV_ROW_EFF: smallest fill of the SM pairs this kernel is chosen for
+        if (need < 0) need = getenv("PTK_CONV_ROW_EFF") ? atof(getenv("PTK_CONV_ROW_EFF")) : 0.6;
+        if (best_r != 0 && (row_mode == 2 || best_eff >= need)) {
           rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kRowW, best_r + 2);
           if (rc != PTK_OK) return rc;
           if (cin1 > 0) {
@@ -1949,12 +1970,12 @@ static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const v
           } else {
             a1 = a0;
           }
-          rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, 64, 1);
+          rc = make_map_3d(&wm, weights, ctot, Cout, taps, ctot, (uint64_t)Cout * ctot, kKChunk, row_n / 2, 1);
           if (rc != PTK_OK) return rc;
           HaloParams Q;
           Q.H = H; Q.W = W; Q.Cout = Cout; Q.chunks0 = cin0 / kKChunk; Q.chunks1 = cin1 / kKChunk; Q.relu = relu;
           Q.tiles_w = col_tiles; Q.tiles_hw = col_tiles * ((H + 2 * best_r - 1) / (2 * best_r));
-          Q.total_tiles = Q.tiles_hw * (Cout / 128);
+          Q.total_tiles = Q.tiles_hw * (Cout / row_n);
           Q.resident = 0;
           Q.dbg = nullptr;
           Q.rows_per_op = best_r + 2;
@@ -1969,15 +1990,15 @@ static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const v
             if (!dbuf) cudaMalloc(&dbuf, 16 * sizeof(long long));
             cudaMemsetAsync(dbuf, 0, 16 * sizeof(long long), s);
             Q.dbg = dbuf;
-            const int lrc = best_r == 2 ? launch_row2<2>(a0, a1, wm, Q, n_launch, s) : launch_row2<3>(a0, a1, wm, Q, n_launch, s);
+            const int lrc = launch_row2_any(best_r, row_n, a0, a1, wm, Q, n_launch, s);
             long long h[16];
             cudaMemcpy(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[row2 R=%d %dx%d cin=%d cout=%d tiles/pair=%lld] producer: total %lld waitEmptyA %lld waitEmptyB %lld | "
+            fprintf(stderr, "[row2 R=%d N=%d %dx%d cin=%d cout=%d tiles/pair=%lld] producer: total %lld waitEmptyA %lld waitEmptyB %lld | "
                     "mma: total %lld waitTmemEmpty %lld waitFullA %lld waitFullB %lld | epilogue: total %lld waitTmemFull %lld\n",
-                    best_r, H, W, cin0 + cin1, Cout, h[7], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[8], h[9]);
+                    best_r, row_n, H, W, cin0 + cin1, Cout, h[7], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[8], h[9]);
             return lrc;
           }
-          return best_r == 2 ? launch_row2<2>(a0, a1, wm, Q, n_launch, s) : launch_row2<3>(a0, a1, wm, Q, n_launch, s);
+          return launch_row2_any(best_r, row_n, a0, a1, wm, Q, n_launch, s);
         }
       }
     }

@@ -16,7 +16,9 @@ LAYERS = [('enc0.1', 64, 0, 64, 576, 1024, True), ('enc1.0', 64, 0, 128, 288, 51
           ('dec2', 64, 128, 64, 288, 512, False), ('dec3', 64, 64, 32, 576, 1024, False),
           # the 1/8-scale block on conv_row2_kernel (row tiles, CTA pairs)
           ('enc3.0', 256, 0, 512, 72, 128, False), ('enc3.1', 512, 0, 512, 72, 128, False), ('enc3.3', 512, 0, 512, 72, 128, True),
-          ('enc3.1r', 512, 0, 512, 94, 126, False)]
+          ('enc3.1r', 512, 0, 512, 94, 126, False),
+          # first / second decoder convolutions (N = 64 row tiles where the dispatch picks them)
+          ('dec0', 512, 512, 64, 72, 128, False), ('dec0r', 512, 512, 64, 94, 126, False), ('dec1r', 64, 256, 64, 188, 252, False)]
 if len(sys.argv) > 1:
     LAYERS = [l for l in LAYERS if l[0] in sys.argv[1:]]
 for name, c0, c1, cout, h, w, pool in LAYERS:

@@ -144,8 +144,12 @@ ROW_DEFAULT_SHAPES = [
     (512, 0, 512, 72, 128, True),       # its last layer, fused pool (rows pair up inside a CTA)
     (512, 0, 512, 94, 126, False),      # the 1008x756 plan: conv_row2_kernel<3>, 64 pair tiles, ragged right and bottom edges
     (256, 256, 512, 94, 126, False),    # two inputs
+    (512, 512, 64, 72, 128, False),     # first decoder convolution (N = 64, R = 1: 36 single-row pair tiles, 16 chunks)
+    (512, 512, 64, 94, 126, False),     # ... of the 1008x756 plan
+    (64, 256, 64, 188, 252, False),     # second decoder convolution of the 1008x756 plan (N = 64, R = 3, two column tiles)
 ]
 ROW_FORCED_SHAPES = [
+    (256, 0, 64, 38, 200, True),        # N = 64 with the fused pool (R = 2), two column tiles
     (256, 0, 128, 37, 200, True),       # two column tiles (the second 72 pixels wide), odd height, pooled
     (256, 0, 128, 300, 256, False),     # 150 pair tiles on 74 SM pairs: the persistent loop and both accumulator sets
     (192, 64, 256, 41, 130, False),     # a 2-pixel-wide second column tile, two inputs, two C_out groups
