@@ -491,20 +491,24 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 // The tap-shifted operand of conv_tc_kernel re-fetches every input pixel nine times from L2
 // (L2 -> SMEM bandwidth, not the tensor pipe, bounds it: 85 flop per staged byte at best).  Here a
 // CTA owns a 16 x 16 pixel output tile and stages the (16+2) x (16+2) halo of a 64-channel chunk
-// once: TMA box {64 ch, 24 px, 18 px} -> 432 rows of 128 B, 128B-swizzled.  With a 24-pixel row
-// pitch (3 x 1024 B) every 8-pixel run of a halo row is one swizzle atom row group, so the operand
-// of tap (dy, dx) for the 8-wide half tile `sx` is the SAME buffer seen through a descriptor whose
-// start address is shifted by ((1+dy)*24 + 8*sx + 1+dx) rows and whose 8-row groups are 24 rows
-// (3072 B) apart.  The tensor core applies the 128B swizzle to the absolute shared-memory address
+// once: TMA box {64 ch, 18 px, 18 px} -> 324 rows of 128 B, 128B-swizzled, densely packed.  The
+// operand of tap (dy, dx) for the 8-wide half tile `sx` is the SAME buffer seen through a descriptor
+// whose start address is shifted by ((1+dy)*18 + 8*sx + 1+dx) rows and whose 8-row groups are 18 rows
+// (2304 B) apart.  The tensor core applies the 128B swizzle to the absolute shared-memory address
 // bits (measured: the descriptor's base-offset field must stay 0 for a start that is not
-// 1024-B aligned), so the shifted view reads exactly what TMA wrote.  Two M=128 MMAs (the two half tiles) share each weight tile, the weights of a
-// layer with <= 112 KB of them stay resident in shared memory, accumulators are double-buffered in
+// 1024-B aligned), so the shifted view reads exactly what TMA wrote -- whatever the row pitch.  Two M=128 MMAs (the two half tiles) share each weight tile, the weights of a
+// layer with <= 128 KB of them stay resident in shared memory, accumulators are double-buffered in
 // TMEM so the epilogue of one tile overlaps the MMAs of the next, and CTAs are persistent.
 // Staged bytes per flop drop 2.5-5x against conv_tc_kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int kHaloW = 24, kHaloH = 18;
-constexpr int kHaloBytes = kHaloW * kHaloH * 128;      // 55296
-constexpr int kBBudget = 114688;                       // weight slots: 112 KB (7 x 16 KB at N = 128: the ring has to
+// Halo rows are staged densely, 18 pixels = 2 304 B apart (round 1 padded them to 24 pixels = 3 x 1 024 B so that every
+// 8-pixel run started a swizzle atom; the row-tile kernel showed that the tensor core, like TMA, applies the 128B swizzle
+// to absolute address bits whatever the pitch, and the padding cost 25 % of the activation bytes of layers that sit at
+// the per-SM TMA ingest rate).  A stage is 40.5 KB, rounded up to 41 KB so that both stages start 1 024-B aligned.
+constexpr int kHaloW = 18, kHaloH = 18;
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;      // 41 472: bytes one halo load brings in
+constexpr int kHaloStage = (kHaloBytes + 1023) / 1024 * 1024;   // 41 984
+constexpr int kBBudget = 131072;                       // weight slots: 128 KB (8 x 16 KB at N = 128: the ring has to
                                                        // cover ~2 us of commit -> refill -> TMA round trip)
 constexpr int kHaloThreads = 192;      // CTA-pair kernel: TMA warp, MMA warp, 4 epilogue warps
 constexpr int kHalo1Threads = 320;     // single-CTA kernel: TMA warp, MMA warp, 8 epilogue warps (4 per half tile)
@@ -541,14 +545,14 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
   static_assert(!kHead || (N == 32 && SPLIT == 1), "the fused head needs all 32 channels of a pixel in one lane");
   constexpr int kBBytes = N * 128;
   constexpr int kSlots = kBBudget / kBBytes;
-  static_assert(SPLIT == 1 || N * 256 * 4 <= 2 * kHaloBytes + kBBudget, "partial sums must fit the operand staging area");
+  static_assert(SPLIT == 1 || N * 256 * 4 <= 2 * kHaloStage + kBBudget, "partial sums must fit the operand staging area");
   constexpr uint32_t kTmemCols = 4 * N < 32 ? 32 : 4 * N;      // 2 buffers x 2 half tiles
   constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                              // 2 halo stages
-  uint8_t* sB = smem + 2 * kHaloBytes;             // kSlots weight tiles
+  uint8_t* sB = smem + 2 * kHaloStage;             // kSlots weight tiles
   uint64_t* fullA = (uint64_t*)(sB + kSlots * kBBytes);
   uint64_t* emptyA = fullA + 2;
   uint64_t* fullB = emptyA + 2;
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
           mbar_wait_t(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u, wA, timed);
           mbar_expect_tx(&fullA[sa], kHaloBytes);
           for (int r = 0; r < kHaloH; r += P.rows_per_op) {
-            uint8_t* dst = sA + sa * kHaloBytes + r * (kHaloW * 128);
+            uint8_t* dst = sA + sa * kHaloStage + r * (kHaloW * 128);
             if (c < P.chunks0) tma_load_3d(dst, &tmA0, &fullA[sa], c * kKChunk, w0 - 1, h0 - 1 + r);
             else tma_load_3d(dst, &tmA1, &fullA[sa], (c - P.chunks0) * kKChunk, w0 - 1, h0 - 1 + r);
           }
@@ -675,7 +679,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
         const int sa = a_it & 1;
         mbar_wait_t(&fullA[sa], (a_it >> 1) & 1u, wA, timed);
         ++a_it;
-        const uint32_t abase = smem_u32(sA + sa * kHaloBytes);
+        const uint32_t abase = smem_u32(sA + sa * kHaloStage);
         // descriptor of tap (0,0) of half tile 0; the other taps / half tile are constant offsets of it
         const uint64_t adesc0 = (uint64_t)((abase & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) |
                                 ((uint64_t)((kHaloW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -862,7 +866,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
 // TMEM lanes (2 half tiles x 256 columns = all 512 columns, so the epilogue is not overlapped).
 // ---------------------------------------------------------------------------------------------
 constexpr int kPairN = 256;                          // widest pair tile (C_out = k * 256); N = 128 is the double-buffered form
-constexpr int kPairBudget = 7 * 128 * 128;           // weight ring per CTA: 112 KB
+constexpr int kPairBudget = 17 * 64 * 128;           // weight ring per CTA: 136 KB (17 half tiles of 8 KB at N = 128)
 
 // TMA load whose completion bytes are credited to the mbarrier at the same offset in the pair's leader CTA
 __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
@@ -906,7 +910,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + 2 * kHaloBytes;
+  uint8_t* sB = smem + 2 * kHaloStage;
   uint64_t* fullA = (uint64_t*)(sB + kPairSlots * kPairBBytes);
   uint64_t* emptyA = fullA + 2;
   uint64_t* fullB = emptyA + 2;
@@ -992,7 +996,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
           mbar_wait_t(&emptyA[sa], ((a_it >> 1) & 1u) ^ 1u, wA, timed);
           if (leader) mbar_expect_tx(&fullA[sa], 2 * kHaloBytes);    // both CTAs' halos are credited here
           for (int r = 0; r < kHaloH; r += P.rows_per_op) {
-            uint8_t* dst = sA + sa * kHaloBytes + r * (kHaloW * 128);
+            uint8_t* dst = sA + sa * kHaloStage + r * (kHaloW * 128);
             if (c < P.chunks0) tma_load_3d_pair(dst, &tmA0, &fullA[sa], c * kKChunk, w0 - 1, h0 - 1 + r);
             else tma_load_3d_pair(dst, &tmA1, &fullA[sa], (c - P.chunks0) * kKChunk, w0 - 1, h0 - 1 + r);
           }
@@ -1025,7 +1029,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
           const int sa = a_it & 1;
           mbar_wait_t(&fullA[sa], (a_it >> 1) & 1u, wA, timed);
           ++a_it;
-          const uint32_t abase = smem_u32(sA + sa * kHaloBytes);
+          const uint32_t abase = smem_u32(sA + sa * kHaloStage);
           const uint64_t adesc0 = (uint64_t)((abase & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) |
                                   ((uint64_t)((kHaloW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 #pragma unroll
@@ -1711,7 +1715,7 @@ template <int N, int SPLIT = 1>
 int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int grid,
                 cudaStream_t stream) {
   constexpr int kSlots = kBBudget / (N * 128);
-  constexpr int smem = 2 * kHaloBytes + kSlots * N * 128 + (4 + 2 * kSlots + 6) * 8 + 16 + 8 * N * 4 + 1024;
+  constexpr int smem = 2 * kHaloStage + kSlots * N * 128 + (4 + 2 * kSlots + 6) * 8 + 16 + 8 * N * 4 + 1024;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
@@ -1733,7 +1737,7 @@ int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
 int launch_halo32_head(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int grid,
                        cudaStream_t stream, const PtkHeadConst& hc) {
   constexpr int kSlots = kBBudget / (32 * 128);
-  constexpr int smem = 2 * kHaloBytes + kSlots * 32 * 128 + (4 + 2 * kSlots + 6) * 8 + 16 + 8 * 32 * 4 + 1024;
+  constexpr int smem = 2 * kHaloStage + kSlots * 32 * 128 + (4 + 2 * kSlots + 6) * 8 + 16 + 8 * 32 * 4 + 1024;
   static bool configured = false;
   if (!configured) {
     PTK_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<32, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1749,7 +1753,7 @@ template <int N>
 int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int n_pairs,
                  cudaStream_t stream) {
   constexpr int kSlots = kPairBudget / ((N / 2) * 128);
-  constexpr int smem = 2 * kHaloBytes + kPairBudget + (4 + 2 * kSlots + 4) * 8 + 16 + 4 * N * 4 + 1024;
+  constexpr int smem = 2 * kHaloStage + kPairBudget + (4 + 2 * kSlots + 4) * 8 + 16 + 4 * N * 4 + 1024;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
@@ -1827,7 +1831,9 @@ static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const v
   cudaStream_t s = (cudaStream_t)stream;
   // ---- halo kernel (3x3 only): one halo load per chunk, persistent CTAs ----
   {
-    static int mode = -1, rows_per_op = 3;   // PTK_CONV_HALO: 0 = never, 1 = when it fills the machine (default), 2 = whenever legal
+    // PTK_CONV_HALO: 0 = never, 1 = when it fills the machine (default), 2 = whenever legal.  PTK_CONV_HALO_ROWS: halo rows
+    // per TMA operation (18 = the whole halo in one box, the default: pieces would start at multiples of 2 304 B)
+    static int mode = -1, rows_per_op = 18;
     if (mode < 0) {
       const char* e = getenv("PTK_CONV_HALO");
       mode = e ? atoi(e) : 1;
