@@ -976,9 +976,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
         const int h0 = th * 16, w0 = (tw * 2 + (int)rank) * 16, n0 = nb * N + (int)rank * (N / 2);
         for (int c = 0; c < chunks; ++c) {
           auto load_weights = [&](int tap_begin, int tap_end) {
+            if (P.resident && tile != pair_id) return;      // resident weights: loaded with the first tile only
             for (int tap = tap_begin; tap < tap_end; ++tap) {
-              const int sb = b_it % kPairSlots;
-              mbar_wait_t(&emptyB[sb], ((b_it / kPairSlots) & 1u) ^ 1u, wB, timed);
+              int sb;
+              if (P.resident) {
+                sb = c * 9 + tap;
+              } else {
+                sb = b_it % kPairSlots;
+                mbar_wait_t(&emptyB[sb], ((b_it / kPairSlots) & 1u) ^ 1u, wB, timed);
+              }
               if (leader) mbar_expect_tx(&fullB[sb], 2 * kPairBBytes);
               tma_load_3d_pair(sB + sb * kPairBBytes, &tmW, &fullB[sb], c * kKChunk, n0, tap);
               ++b_it;
@@ -1034,9 +1040,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
                                   ((uint64_t)((kHaloW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int sb = b_it % kPairSlots;
-            mbar_wait_t(&fullB[sb], (b_it / kPairSlots) & 1u, wB, timed);
-            ++b_it;
+            int sb;
+            if (P.resident) {      // every weight tile of the layer has its own slot, filled once
+              sb = c * 9 + tap;
+              if (t_it == 0) mbar_wait_t(&fullB[sb], 0, wB, timed);
+            } else {
+              sb = b_it % kPairSlots;
+              mbar_wait_t(&fullB[sb], (b_it / kPairSlots) & 1u, wB, timed);
+              ++b_it;
+            }
             tc_fence_after();
             const uint64_t bdesc = make_sw128_desc(smem_u32(sB + sb * kPairBBytes));
             if (elect_one()) {
@@ -1049,7 +1061,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
                 for (int k = 0; k < kKChunk / 16; ++k)
                   tc_mma_f16_pair(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (c | tap | k) != 0 ? 1u : 0u);
               }
-              tc_commit_pair(&emptyB[sb]);
+              if (!P.resident) tc_commit_pair(&emptyB[sb]);
             }
             __syncwarp();
           }
@@ -1859,7 +1871,7 @@ static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const v
         const char* n = getenv("PTK_CONV_PAIR_N");
         if (n && atoi(n) == 256) pair_n_env = 256;
       }
-      const int pair_n = Cout == 64 ? 64 : ((pair_n_env == 256 && Cout % 256 == 0) ? 256 : 128);
+      const int pair_n = Cout == 32 ? 32 : (Cout == 64 ? 64 : ((pair_n_env == 256 && Cout % 256 == 0) ? 256 : 128));
       const int pairs_w = (tiles_w16 + 1) / 2;
       const int total_pairs = pairs_w * tiles_h16 * (Cout / pair_n);
       const int pair_slots = ctx->num_sms / 2;
@@ -1869,9 +1881,20 @@ static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const v
       // chunks): there is no weight traffic to halve, and the pair's ring re-streams them per tile (64->64 at full
       // resolution: 62 us single, 84 us as pairs)
       const bool single_resident = Cout == n_halo && 9 * (ctot / kKChunk) <= kBBudget / (n_halo * 128);
+      // ... unless the pair keeps them resident too (PTK_CONV_PAIR_RES, default 1): each SM then reads half of every
+      // weight tile per MMA, which is what the thin full-resolution layers are bound by (operand fetch from shared
+      // memory).  Measured, 10 launches back to back: 64+64->32 @576x1024 83.7 -> 59.8 us, 64+128->64 @288x512
+      // 33.5 -> 30.3, 64->128 @288x512 24.8 -> 23.0; but 64->64 @576x1024 (+pool) 54.8 -> 68.9 us: with one chunk and
+      // N = 64 a tile's MMAs (3.2 K cycles) are shorter than its epilogue on the pair kernel's four epilogue warps, so that
+      // shape stays on the single-CTA kernel (eight).
+      static int pair_res_mode = -1;
+      if (pair_res_mode < 0) pair_res_mode = getenv("PTK_CONV_PAIR_RES") ? atoi(getenv("PTK_CONV_PAIR_RES")) : 1;
+      const bool pair_resident = Cout == pair_n && 9 * (ctot / kKChunk) <= kPairBudget / ((pair_n / 2) * 128) &&
+                                 !(ctot == kKChunk && Cout <= 64 && pair_res_mode != 2);
       const bool pair_wanted = pair_mode == 2 ||
-                               (pair_mode == 1 && !single_resident && total_pairs * 10 >= pwaves * pair_slots * 8);
-      if (pair_legal && pair_wanted) {
+                               (pair_mode == 1 && (!single_resident || (pair_res_mode != 0 && pair_resident)) &&
+                                total_pairs * 10 >= pwaves * pair_slots * 8);
+      if (pair_legal && pair_wanted && head == nullptr) {   // (a fused head only exists in the single-CTA kernel's epilogue)
         rc = make_map_3d(&a0, in0, cin0, W, H, cin0, (uint64_t)in0_W * cin0, kKChunk, kHaloW, rows_per_op);
         if (rc != PTK_OK) return rc;
         if (cin1 > 0) {
@@ -1885,7 +1908,7 @@ static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const v
         HaloParams Q;
         Q.H = H; Q.W = W; Q.Cout = Cout; Q.chunks0 = cin0 / kKChunk; Q.chunks1 = cin1 / kKChunk; Q.relu = relu;
         Q.tiles_w = pairs_w; Q.tiles_hw = pairs_w * tiles_h16; Q.total_tiles = total_pairs;
-        Q.resident = 0;
+        Q.resident = (pair_res_mode != 0 && pair_resident) ? 1 : 0;
         Q.dbg = nullptr;
         Q.rows_per_op = rows_per_op;
         Q.bias = bias;
@@ -1899,8 +1922,9 @@ static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const v
           if (!dbuf) cudaMalloc(&dbuf, 16 * sizeof(long long));
           cudaMemsetAsync(dbuf, 0, 16 * sizeof(long long), s);
           Q.dbg = dbuf;
-          const int lrc = pair_n == 64 ? launch_halo2<64>(a0, a1, wm, Q, n_launch, s)
-                                       : (pair_n == 256 ? launch_halo2<256>(a0, a1, wm, Q, n_launch, s) : launch_halo2<128>(a0, a1, wm, Q, n_launch, s));
+          const int lrc = pair_n == 32 ? launch_halo2<32>(a0, a1, wm, Q, n_launch, s)
+                          : pair_n == 64 ? launch_halo2<64>(a0, a1, wm, Q, n_launch, s)
+                                         : (pair_n == 256 ? launch_halo2<256>(a0, a1, wm, Q, n_launch, s) : launch_halo2<128>(a0, a1, wm, Q, n_launch, s));
           long long h[16];
           cudaMemcpy(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost);
           fprintf(stderr, "[halo2 N=%d %dx%d cin=%d cout=%d tiles/pair=%lld] producer: total %lld waitEmptyA %lld waitEmptyB %lld | "
@@ -1908,6 +1932,7 @@ static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const v
                   pair_n, H, W, cin0 + cin1, Cout, h[7], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[8], h[9], h[10], h[11]);
           return lrc;
         }
+        if (pair_n == 32) return launch_halo2<32>(a0, a1, wm, Q, n_launch, s);
         if (pair_n == 64) return launch_halo2<64>(a0, a1, wm, Q, n_launch, s);
         return pair_n == 256 ? launch_halo2<256>(a0, a1, wm, Q, n_launch, s) : launch_halo2<128>(a0, a1, wm, Q, n_launch, s);
       }
