@@ -510,7 +510,8 @@ constexpr int kHaloBytes = kHaloW * kHaloH * 128;      // 41 472: bytes one halo
 constexpr int kHaloStage = (kHaloBytes + 1023) / 1024 * 1024;   // 41 984
 constexpr int kBBudget = 131072;                       // weight slots: 128 KB (8 x 16 KB at N = 128: the ring has to
                                                        // cover ~2 us of commit -> refill -> TMA round trip)
-constexpr int kHaloThreads = 192;      // CTA-pair kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kHaloThreads = 192;      // row-tile pair kernels: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kPair8Threads = 320;     // 16x16 pair kernel: TMA warp, MMA warp, 8 epilogue warps (4 per half tile)
 constexpr int kHalo1Threads = 320;     // single-CTA kernel: TMA warp, MMA warp, 8 epilogue warps (4 per half tile)
 
 struct HaloParams {
@@ -866,7 +867,7 @@ __global__ void __launch_bounds__(kHalo1Threads, 1) conv_halo_kernel(const __gri
 // TMEM lanes (2 half tiles x 256 columns = all 512 columns, so the epilogue is not overlapped).
 // ---------------------------------------------------------------------------------------------
 constexpr int kPairN = 256;                          // widest pair tile (C_out = k * 256); N = 128 is the double-buffered form
-constexpr int kPairBudget = 17 * 64 * 128;           // weight ring per CTA: 136 KB (17 half tiles of 8 KB at N = 128)
+constexpr int kPairBudget = 16 * 64 * 128;           // weight ring per CTA: 128 KB (16 half tiles of 8 KB at N = 128)
 
 // TMA load whose completion bytes are credited to the mbarrier at the same offset in the pair's leader CTA
 __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
@@ -897,7 +898,7 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc,
 // N = 128: two accumulator sets, so the epilogue of a tile runs under the MMAs of the next one -- the pair then keeps what
 //          it gains on weight traffic (each CTA stages only half of every weight tile).
 template <int N>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPair8Threads, 1)
     conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmW, const HaloParams P) {
   constexpr int kPairBBytes = (N / 2) * 128;           // this CTA's half of a weight tile
@@ -918,7 +919,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
   uint64_t* tmem_full = emptyB + kPairSlots;
   uint64_t* tmem_empty = tmem_full + kBufs;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + kBufs);
-  float* s_bias_all = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][N]
+  float* s_bias_all = reinterpret_cast<float*>(tmem_slot + 4);   // [8 epilogue warps][N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -940,7 +941,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
     }
     for (int s = 0; s < kBufs; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps of each CTA arrive on the leader's copy
+      mbar_init(&tmem_empty[s], 16);  // 8 epilogue warps of each CTA arrive on the leader's copy
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1080,8 +1081,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       }
     }
   } else {
-    // ---------------- epilogue (both CTAs, own TMEM lanes) ----------------
+    // ---------------- epilogue (both CTAs, own TMEM lanes): 8 warps; warp w reads TMEM lane quadrant q = w % 4 of half
+    //                  tile sx = (w - 2) / 4, so the two half tiles drain in parallel (with four warps a tile's epilogue
+    //                  outlasted its MMAs on the one-chunk layers) ----------------
     const int q = warp & 3;
+    const int sx = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int y = m >> 3, xx = m & 7;
     uint32_t t_it = 0;
@@ -1098,8 +1102,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       else stage_bias<128>(s_bias, P.bias + n0, lane < N / 4 ? lane : 0);
       mbar_wait_t(&tmem_full[buf], (t_it / kBufs) & 1u, wF, timed);
       tc_fence_after();
-#pragma unroll 1
-      for (int sx = 0; sx < 2; ++sx) {
+      {
         const int w = (tw * 2 + (int)rank) * 16 + 8 * sx + xx;
         const bool inside = (h < P.H) && (w < P.W);
         __half* orow = P.out + ((size_t)h * P.W + w) * P.Cout + n0;
@@ -1765,7 +1768,7 @@ template <int N>
 int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const HaloParams& P, int n_pairs,
                  cudaStream_t stream) {
   constexpr int kSlots = kPairBudget / ((N / 2) * 128);
-  constexpr int smem = 2 * kHaloStage + kPairBudget + (4 + 2 * kSlots + 4) * 8 + 16 + 4 * N * 4 + 1024;
+  constexpr int smem = 2 * kHaloStage + kPairBudget + (4 + 2 * kSlots + 4) * 8 + 16 + 8 * N * 4 + 1024;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
@@ -1773,7 +1776,7 @@ int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap
     configured = true;
   }
   // the cluster shape is the kernel's compile-time __cluster_dims__(2, 1, 1)
-  PTK_CUDA_CHECK(ptk_launch_pdl(conv_halo2_kernel<N>, dim3(2 * n_pairs), dim3(kHaloThreads), smem, stream, dim3(1, 1, 1), a0, a1, w, P));
+  PTK_CUDA_CHECK(ptk_launch_pdl(conv_halo2_kernel<N>, dim3(2 * n_pairs), dim3(kPair8Threads), smem, stream, dim3(1, 1, 1), a0, a1, w, P));
   return PTK_OK;
 }
 
