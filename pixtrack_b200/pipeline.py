@@ -93,6 +93,8 @@ class FrameTracker:
         # overlap the other plan's); the LM launches wait for it through an event
         self._side = torch.cuda.Stream(dev) if overlap_reference else None
         self._ref_done = None
+        self._pre_extract = None
+        self._query_ready = False
         self.n_active = N
 
     def set_points(self, xyz):
@@ -148,7 +150,13 @@ class FrameTracker:
                 self.valid[view, self.n_active:].zero_()
             return
         cur = torch.cuda.current_stream(dev)
-        self._side.wait_stream(cur)          # the previous frame's LM has finished reading the observation cache
+        if self._query_ready and self._pre_extract is not None:
+            # this frame's query extraction was enqueued ahead (extract_query): wait for what preceded it on the caller's
+            # stream -- the previous frame's LM, the uploads the stream had waited for -- not for the extraction itself,
+            # so that the two plans still run side by side
+            self._side.wait_event(self._pre_extract)
+        else:
+            self._side.wait_stream(cur)      # the previous frame's LM has finished reading the observation cache
         with torch.cuda.stream(self._side):
             feats, confs, scales = self.extractor.extract_device(image, scale_image, normalize=False, out=bufs, slot=1)
             sample_reference(feats, confs, scales, camera, T_w2cam, self.p3d64, pad=self.pad, normalize=True,
@@ -159,22 +167,37 @@ class FrameTracker:
             self._ref_done.record(self._side)
         image.record_stream(self._side)
 
-    def track(self, image: Tensor, T_init: Optional[Tensor] = None, mask_depth: Optional[Tensor] = None):
-        """image: CUDA [H,W,3] uint8/fp32 query frame.  mask_depth: optional CUDA uint8 [H,W,3] depth-mode NeRF
-        render at the query resolution; the frame is then multiplied by the eroded/dilated object mask first
-        (r9.py:207-214,224-225), on the device.  Returns (T [B,12], failed [B]) device tensors; stream-ordered,
-        no synchronisation."""
+    def extract_query(self, image: Tensor, mask_depth: Optional[Tensor] = None):
+        """The pose-independent half of `track`: (mask and) extract the query frame's features into the tracker's maps.
+        A caller that has to read frame i's poses on the host before it can start frame i+1's refinement can enqueue this
+        for frame i+1 first -- the extraction then runs while the host waits for frame i's result -- and call
+        `track(None, T_init)` afterwards.  Stream-ordered after the previous `track` (whose LM reads the same maps)."""
         if mask_depth is not None:
             from .mask import query_mask
             if self._masked is None or self._masked.shape != image.shape or self._masked.dtype != image.dtype:
                 self._masked = torch.empty_like(image)
             image, _ = query_mask(mask_depth, image, out=self._masked)
+        if self._side is not None:
+            self._pre_extract = torch.cuda.Event()
+            self._pre_extract.record(torch.cuda.current_stream(self.extractor.device))
+        self.extractor.extract_device(image, self.scale_image, normalize=True, out=(self.feats, self.confs))
+        self._query_ready = True
+
+    def track(self, image: Optional[Tensor], T_init: Optional[Tensor] = None, mask_depth: Optional[Tensor] = None):
+        """image: CUDA [H,W,3] uint8/fp32 query frame, or None when `extract_query` already ran for this frame.
+        mask_depth: optional CUDA uint8 [H,W,3] depth-mode NeRF render at the query resolution; the frame is then
+        multiplied by the eroded/dilated object mask first (r9.py:207-214,224-225), on the device.  Returns
+        (T [B,12], failed [B]) device tensors; stream-ordered, no synchronisation."""
         if self._use_graph and not self._captured:
             self.plan.capture()
             self._captured = True
         if T_init is not None:
             self.T_init.copy_(T_init, non_blocking=True)
-        self.extractor.extract_device(image, self.scale_image, normalize=True, out=(self.feats, self.confs))
+        if image is not None:
+            self.extract_query(image, mask_depth)
+        elif not self._query_ready:
+            raise RuntimeError('track(None, ...) needs a preceding extract_query() for this frame')
+        self._query_ready = False
         if self._ref_done is not None:       # observations refreshed on the side stream must be complete
             torch.cuda.current_stream(self.extractor.device).wait_event(self._ref_done)
             self._ref_done = None

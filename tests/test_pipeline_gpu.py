@@ -165,3 +165,30 @@ def test_whole_r9_frame_stays_on_the_device():
     assert torch.isfinite(a[2]).all()
     from pixtrack_b200 import _lib
     _lib.device_status(0)
+
+
+def test_extract_query_then_track_equals_track():
+    """FrameTracker.extract_query + track(None, T) (the split a host loop uses to overlap frame i+1's extraction with the
+    read-back of frame i's poses) gives bit-identical poses to track(image, T), through direct launches, graph capture
+    and replay."""
+    outs = []
+    for split in (False, True):
+        dev, seq, sd, lam, fr, trk = _setup()
+        T_ref = torch.cat([fr['R_r'].reshape(-1), fr['t_r']])
+        res = []
+        for rep in range(4):
+            for v in range(trk.B):
+                trk.refresh_reference(v, fr['img_r'].to(dev), seq['cam_r'], T_ref)
+            if split:
+                trk.extract_query(fr['img_q'].to(dev))
+                T, failed = trk.track(None, fr['T_init'].to(dev))
+            else:
+                T, failed = trk.track(fr['img_q'].to(dev), fr['T_init'].to(dev))
+            torch.cuda.synchronize()
+            res.append((T.clone(), failed.clone()))
+        outs.append(res)
+    for (Ta, fa), (Tb, fb) in zip(*outs):
+        assert torch.equal(Ta, Tb) and torch.equal(fa, fb)
+    dev, seq, sd, lam, fr, trk = _setup()
+    with pytest.raises(RuntimeError):
+        trk.track(None, fr['T_init'].to(dev))
