@@ -556,6 +556,9 @@ def run_ours(args, rank, world, local_rank, wl):
                     'peak_source': ('MEASURED_PEAKS.json bf16_tflops (burst; kernels timed alone with CUDA events)'
                                     if peaks else 'fallback 1590 TFLOP/s'),
                     'avg_launch_us': b2b_us / len(b2b_rows), 'flop_per_launch': b2b_fl / len(b2b_rows),
+                    # for context: MEASURED_PEAKS.json also holds the SUSTAINED cuBLAS rate (back to back for 4 s)
+                    'peak_sustained': peaks.get('bf16_tflops_sustained'),
+                    'frac_of_sustained_peak': (b2b / float(peaks['bf16_tflops_sustained'])) if peaks.get('bf16_tflops_sustained') else None,
                     'method': 'every layer of the plan launched 10 times back to back on its own shapes between one pair of '
                               'CUDA events, median of 7 samples: the duration a launch has inside the replayed plan graph',
                     'layers': b2b_rows,
