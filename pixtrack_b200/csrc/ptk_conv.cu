@@ -4,15 +4,19 @@
 // Replaces the cuDNN convolutions under UNet._forward (reference
 // pixloc/pixloc/pixlib/models/unet.py:68-99 encoder blocks, :15-44 decoder blocks).
 //
-// Three kernels, chosen per layer by ptk_conv_f16_pool (bottom of the file):
-//   conv_halo_kernel   persistent, one halo load per 64-channel chunk, taps = shifted descriptors (default for the
-//                      large maps; see its header comment)
-//   conv_halo2_kernel  the same on CTA pairs (tcgen05 cta_group::2, M = 256 x N = 128 with two accumulator sets in TMEM):
-//                      the many-channel layers on large maps (PTK_CONV_PAIR)
+// Five kernels, chosen per layer by conv_dispatch (bottom of the file; every choice has an environment switch):
+//   conv_halo_kernel   persistent, 16 x 16 tiles, one halo load per 64-channel chunk, taps = shifted descriptors (the
+//                      full-resolution 64 -> 64 layer; see its header comment)
+//   conv_halo2_kernel  the same on CTA pairs (tcgen05 cta_group::2, M = 256 x N = 32 / 64 / 128 with two accumulator sets
+//                      in TMEM, weights streamed or resident): most layers on the large maps (PTK_CONV_PAIR)
+//   conv_row2_kernel   CTA pairs on ROW tiles (an MMA's 128 rows = 128 consecutive pixels of an image row), N = 64 / 128,
+//                      R = 1..3 rows per CTA: maps about 128 pixels wide, where 16 x 16 tiles quantise badly (PTK_CONV_ROW)
+//   conv_row64_kernel  CTA pairs on maps <= 64 pixels wide (three column-shifted halo copies) (PTK_CONV_ROW64)
 //   conv_tc_kernel     one tap-shifted TMA box per k-step; small maps and 1x1 (described next); SPLIT = 2 shares the
 //                      K loop of a tile between the two CTAs of a cluster (partial sums through DSMEM)
-// All epilogues add the bias (conv bias or folded BatchNorm), apply ReLU, write fp16 and can also write the
-// 2x2 max pool of the result.
+// All epilogues add the bias (conv bias or folded BatchNorm) from shared memory, apply ReLU, write fp16 as 32-byte
+// pieces per lane (lane pairs swap halves: pair_store) and can also write the 2x2 max pool of the result.  All kernels
+// are launched with programmatic dependent launch and prefetch their first weight tiles before griddepcontrol.wait.
 //
 // conv_tc_kernel, GEMM view:  D[128 pixels, BLOCK_N channels] += A[128, 64] * B[BLOCK_N, 64]^T over
 //             K = taps x (C_in / 64) steps.

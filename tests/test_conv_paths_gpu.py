@@ -2,13 +2,15 @@
 against an fp32 convolution of the SAME fp16-rounded operands (so the only differences are the fp32 summation order
 and the fp16 rounding of the output).
 
-Dispatch (pixtrack_b200/csrc/ptk_conv.cu, ptk_conv_f16_pool): the persistent halo kernel conv_halo_kernel<N>,
-N = 32 / 64 / 128, takes 3x3 layers whose 16x16 tiles fill >= 80 % of their last wave of 148 SMs -- the shapes below
-are chosen to land there (143 tiles of 16x16 for 170x200 / 171x203 maps) with ragged right / bottom tiles; everything
-else goes to conv_tc_kernel.  The benchmark's plans use: halo<64> (64->64 full resolution, pooled), halo<128>
-(128/256-channel blocks, pooled, several C_out groups), halo<32> with two inputs (last decoder block: 64 upsampled +
-64 skip channels -> 32), halo<64> with two inputs (decoder 64+128 -> 64), and the fused 2x2 max pool on odd sizes
-(the 1008x756 plan pools 189 -> 94).
+Dispatch (pixtrack_b200/csrc/ptk_conv.cu, conv_dispatch), in this order: the 16x16 CTA-pair kernel conv_halo2_kernel<N>
+(N = 32 / 64 / 128; weights streamed or resident) when the tile pairs fill >= 80 % of their last wave of 74 SM pairs; the
+narrow-map pair kernel conv_row64_kernel (maps 48..64 pixels wide with >= 44 pair tiles); the row-tile pair kernel
+conv_row2_kernel<R, N> (long K, >= 60 % fill); the single-CTA halo kernel conv_halo_kernel<N> when its 16x16 tiles fill
+>= 80 % of their last wave of 148 SMs (with the default switches: layers whose weights it keeps resident and the pair
+kernel does not take, e.g. 64 -> 64 at full resolution); everything else conv_tc_kernel (per-tap boxes, K split).  The
+shapes below are chosen to land on each of them, with ragged right / bottom tiles, two inputs, the fused 2x2 max pool
+on odd sizes (the 1008x756 plan pools 189 -> 94), and the switches that force the non-default choices run in child
+processes (the library reads them once).
 """
 import pytest
 import torch
