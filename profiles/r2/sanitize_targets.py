@@ -1,5 +1,6 @@
-"""Targets for `compute-sanitizer --tool memcheck` beyond smoke(): the kernels added or changed in round 2 -- the K-split
-convolutions (per-tap and halo form), the cp.async head / pipelined conv1 kernels inside a small extractor plan, the
+"""Targets for `compute-sanitizer --tool memcheck` beyond smoke(): the kernels added or changed in round 2 -- every
+convolution kernel variant the dispatch reaches by default (per-tap K split, single-CTA halo, 16x16 pairs, row-tile pairs,
+narrow-map pairs; ragged and odd sizes, fused pool), the cp.async head / pipelined conv1 kernels inside a small extractor plan, the
 LM launch on its own workspace with two CTAs per SM, the NeRF network entry point and the overlay."""
 import os
 import sys
@@ -19,13 +20,18 @@ from pixtrack_b200.overlay import overlay  # noqa: E402
 torch.set_grad_enabled(False)
 D = torch.device('cuda:0')
 g = torch.Generator().manual_seed(0)
-for cin, cout, H, W in ((512, 512, 36, 64), (1024, 64, 72, 128), (64, 64, 170, 200)):
+# (cin, cout, H, W, pool): per-tap K split; single-CTA halo; 16x16 pairs streamed / resident (N = 128, 64, 32) with the fused
+# pool and ragged odd sizes; row-tile pairs R = 2 (pooled) / R = 3 and N = 64; the narrow-map pair kernel
+for cin, cout, H, W, pool in ((512, 512, 36, 64, False), (1024, 64, 72, 128, False), (64, 64, 170, 200, False),
+                              (256, 256, 145, 255, True), (64, 128, 289, 511, False), (128, 32, 577, 1023, False),
+                              (192, 64, 287, 513, False), (512, 512, 72, 128, True), (512, 512, 94, 126, False),
+                              (320, 64, 188, 252, False), (512, 512, 47, 63, False)):
     x = torch.randn(H, W, cin, generator=g).half().to(D)
     w = pack_conv3x3((torch.randn(cout, cin, 3, 3, generator=g) / 50).half().to(D))
     b = torch.randn(cout, generator=g).to(D)
-    y = conv_f16(x, w, b)
+    y = conv_f16(x, w, b, pool=pool)
     torch.cuda.synchronize()
-    assert bool(torch.isfinite(y.float()).all())
+    assert bool(torch.isfinite((y[0] if pool else y).float()).all())
 ext = B200FeatureExtractor(syn.unet_weights(0), D, dict(resize=None))
 f, c, _ = ext.extract_device(syn.textured_image(96, 160, seed=1).to(D), normalize=True)
 torch.cuda.synchronize()
