@@ -278,6 +278,16 @@ __device__ __forceinline__ uint32_t map_to_rank0(uint32_t smem_addr) {   // the 
   asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_addr));
   return remote;
 }
+// "This accumulator set has been read": arrives on rank 0's copy of `bar` WITHOUT release semantics.  The only thing the
+// waiter (the MMA warp) does afterwards is overwrite TMEM, and the reads of it have completed (tcgen05.wait::ld) before
+// the arrive is issued.  A releasing arrive at cluster scope compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. the epilogue warp
+// waited for all of its OUTPUT STORES to become visible before it could free the accumulators: 21 % of all stall samples
+// of the pair kernel on the 64 -> 64 full-resolution layer (ncu source page), once per tile and warp.
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(bar)));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on rank 0's copy of `bar`
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_rank0(smem_u32(bar))) : "memory");
 }
@@ -531,8 +541,8 @@ struct HaloParams {
   __half* pool;          // optional [H/2][W/2][Cout]: 2x2 max pool of `out`, written by the same epilogue
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {   // (relaxed: see mbar_arrive_leader_relaxed)
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // SPLIT = 2: the 64-channel chunks (K) of ONE output tile are shared by a cluster of two CTAs (small maps: too few
@@ -1148,7 +1158,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPair8Threads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
+      if (lane == 0) mbar_arrive_leader_relaxed(&tmem_empty[buf]);
     }
     if (timed && lane == 0) {
       P.dbg[8] = clock64() - tstart;
@@ -1433,7 +1443,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
+      if (lane == 0) mbar_arrive_leader_relaxed(&tmem_empty[buf]);
     }
     if (timed && lane == 0) {
       P.dbg[8] = clock64() - tstart;
@@ -1652,7 +1662,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
+      if (lane == 0) mbar_arrive_leader_relaxed(&tmem_empty[buf]);
     }
   }
 
