@@ -1901,13 +1901,14 @@ static int conv_dispatch(PtkContext* ctx, const void* in0, int32_t cin0, const v
       // ... unless the pair keeps them resident too (PTK_CONV_PAIR_RES, default 1): each SM then reads half of every
       // weight tile per MMA, which is what the thin full-resolution layers are bound by (operand fetch from shared
       // memory).  Measured, 10 launches back to back: 64+64->32 @576x1024 83.7 -> 59.8 us, 64+128->64 @288x512
-      // 33.5 -> 30.3, 64->128 @288x512 24.8 -> 23.0; but 64->64 @576x1024 (+pool) 54.8 -> 68.9 us: with one chunk and
-      // N = 64 a tile's MMAs (3.2 K cycles) are shorter than its epilogue on the pair kernel's four epilogue warps, so that
-      // shape stays on the single-CTA kernel (eight).
+      // 33.5 -> 30.3, 64->128 @288x512 24.8 -> 23.0.  The one-chunk 64->64 layer (+pool) at first LOST as a pair
+      // (54.8 -> 68.9 us: its epilogue outlasts its MMAs, and every epilogue warp waited at a GPU-scope fence per tile); with
+      // eight epilogue warps and the relaxed accumulator-release arrive it wins too: 54.8 -> ~48 us at 576x1024,
+      // 68.3 -> 58.0 us at 756x1008.  (PTK_CONV_PAIR_RES=3 keeps that shape on the single-CTA kernel.)
       static int pair_res_mode = -1;
       if (pair_res_mode < 0) pair_res_mode = getenv("PTK_CONV_PAIR_RES") ? atoi(getenv("PTK_CONV_PAIR_RES")) : 1;
       const bool pair_resident = Cout == pair_n && 9 * (ctot / kKChunk) <= kPairBudget / ((pair_n / 2) * 128) &&
-                                 !(ctot == kKChunk && Cout <= 64 && pair_res_mode != 2);
+                                 !(ctot == kKChunk && Cout <= 64 && pair_res_mode == 3);
       const bool pair_wanted = pair_mode == 2 ||
                                (pair_mode == 1 && (!single_resident || (pair_res_mode != 0 && pair_resident)) &&
                                 total_pairs * 10 >= pwaves * pair_slots * 8);
